@@ -1,0 +1,71 @@
+"""Mirror of the reference pybind module `hydrainfer._C.kernel.flash_attn`
+(csrc/kernel/flash_attn/flash_api.cpp:216-355, stub hydrainfer/_C/kernel/flash_attn/__init__.pyi:23-40):
+`mha_varlen_fwd` with the same 16 positional arguments, writing `out` in place.  Backed by hi_paged_attention
+(split-KV CUDA-core kernel for decode rows, tcgen05/TMEM tile kernel for prefill)."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from ... import _lib
+
+_workspaces: dict[torch.device, Tensor] = {}
+
+
+def _workspace(dev: torch.device, head_dim: int) -> Tensor:
+    need = _lib.lib.hi_attention_workspace_bytes(0, 0, head_dim, 0)
+    ws = _workspaces.get(dev)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)  # persistent, like flashinfer's workspace (executor.py:99)
+        _workspaces[dev] = ws
+    return ws
+
+
+def mha_varlen_fwd(out: Tensor, q: Tensor, k: Tensor, v: Tensor, cu_seqlens_q: Tensor, cu_seqlens_k: Tensor,
+                   block_table_: Optional[Tensor], cu_block_lens: Optional[Tensor], alibi_slopes: Optional[Tensor],
+                   max_seqlen_q: int, max_seqlen_k: int, softmax_scale: float, softcap: float, window_size_left: int,
+                   window_size_right: int, num_splits: int, path: int = _lib.HI_ATTN_AUTO) -> None:
+    """Paged causal varlen attention. q/out [T, Hq, d] (row stride free), k/v caches [NB, bs, Hkv, d] contiguous,
+    int32 cu_seqlens_q/k [B+1], flattened block table + cu_block_lens [B+1] (flash_api.cpp:216-232).
+
+    Only the configuration the reference's attention layer uses is implemented (causal_attention.py:274-291):
+    no alibi, no softcap, window (-1, 0) == causal, paged KV; anything else raises RuntimeError like TORCH_CHECK."""
+    if block_table_ is None or cu_block_lens is None:
+        raise RuntimeError("mha_varlen_fwd: only the paged-KV form (block_table + cu_block_lens) is implemented")
+    if alibi_slopes is not None or softcap != 0 or window_size_left != -1 or window_size_right != 0:
+        raise RuntimeError("mha_varlen_fwd: alibi / softcap / sliding window are not used by the paged attention layer and are not implemented")
+    dev = _lib.require_cuda(out, q, k, v, cu_seqlens_q, cu_seqlens_k, block_table_, cu_block_lens)
+    if q.dim() != 3 or out.shape != q.shape or q.stride(-1) != 1 or q.stride(-2) != q.size(-1) or out.stride(-1) != 1 or out.stride(-2) != out.size(-1):
+        raise RuntimeError("mha_varlen_fwd: q and out must be [n_tokens, n_heads, head_dim], contiguous over the last two dims")
+    if k.dim() != 4 or k.shape != v.shape or not k.is_contiguous() or not v.is_contiguous():
+        raise RuntimeError("mha_varlen_fwd: k and v must be contiguous paged caches [n_blocks, block_size, n_kv_heads, head_dim]")
+    if not (q.dtype == out.dtype == k.dtype == v.dtype):
+        raise RuntimeError("mha_varlen_fwd: dtype mismatch")
+    for name, t in (("cu_seqlens_q", cu_seqlens_q), ("cu_seqlens_k", cu_seqlens_k), ("block_table", block_table_), ("cu_block_lens", cu_block_lens)):
+        if t.dtype != torch.int32 or not t.is_contiguous():
+            raise RuntimeError(f"mha_varlen_fwd: {name} must be a contiguous int32 tensor")
+    n_tokens, n_qo_heads, head_dim = q.shape
+    n_blocks, block_size, n_kv_heads, kd = k.shape
+    if kd != head_dim or n_qo_heads % n_kv_heads != 0:
+        raise RuntimeError(f"mha_varlen_fwd: head mismatch q {tuple(q.shape)} cache {tuple(k.shape)}")
+    n_seqs = cu_seqlens_q.shape[0] - 1
+    if cu_seqlens_k.shape[0] != n_seqs + 1 or cu_block_lens.shape[0] != n_seqs + 1:
+        raise RuntimeError("mha_varlen_fwd: cu_seqlens_q, cu_seqlens_k and cu_block_lens must all have batch + 1 entries")
+    ws = _workspace(dev, head_dim)
+    row = n_qo_heads * head_dim
+    args = _lib.HiAttnArgs(
+        q=q.data_ptr(), out=out.data_ptr(), key_cache=k.data_ptr(), value_cache=v.data_ptr(),
+        q_row_stride=q.stride(0) if n_tokens > 1 else row, out_row_stride=out.stride(0) if n_tokens > 1 else row,
+        q_cu_seq_lens=cu_seqlens_q.data_ptr(), kv_cu_seq_lens=cu_seqlens_k.data_ptr(),
+        block_tables=block_table_.data_ptr(), cu_blocks_lens=cu_block_lens.data_ptr(),
+        n_seqs=n_seqs, n_tokens=n_tokens, max_q_len=int(max_seqlen_q), max_kv_len=int(max_seqlen_k),
+        n_qo_heads=n_qo_heads, n_kv_heads=n_kv_heads, head_dim=head_dim, block_size=block_size, n_blocks=n_blocks,
+        dtype=_lib.dtype_code(q.dtype), softmax_scale=float(softmax_scale),
+        workspace=ws.data_ptr(), workspace_bytes=ws.numel(), path=int(path), device=dev.index or 0)
+    _lib.check(_lib.lib.hi_paged_attention(args, _lib.current_stream_ptr(dev)))
+
+
+def last_launch_count() -> int:
+    return _lib.lib.hi_last_launch_count()

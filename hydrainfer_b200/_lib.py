@@ -1,0 +1,115 @@
+"""ctypes binding of libhi_b200.so — the C ABI declared in include/hi_b200.h.
+
+The product path has no CPU fallback: if the shared library cannot be loaded (or built from the in-tree sources)
+importing this module raises, and every entry point raises RuntimeError on a non-zero status.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_uint8, c_void_p
+from pathlib import Path
+
+import torch
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "lib" / "libhi_b200.so"
+
+HI_F32, HI_F16, HI_BF16 = 0, 1, 2
+HI_ATTN_AUTO, HI_ATTN_SIMT, HI_ATTN_TCGEN05 = 0, 1, 2
+
+_DTYPES = {torch.float32: HI_F32, torch.float16: HI_F16, torch.bfloat16: HI_BF16}
+
+
+class HiAttnArgs(Structure):
+    _fields_ = [
+        ("q", c_void_p), ("out", c_void_p), ("key_cache", c_void_p), ("value_cache", c_void_p),
+        ("q_row_stride", c_int64), ("out_row_stride", c_int64),
+        ("q_cu_seq_lens", c_void_p), ("kv_cu_seq_lens", c_void_p), ("block_tables", c_void_p), ("cu_blocks_lens", c_void_p),
+        ("n_seqs", c_int32), ("n_tokens", c_int32), ("max_q_len", c_int32), ("max_kv_len", c_int32),
+        ("n_qo_heads", c_int32), ("n_kv_heads", c_int32), ("head_dim", c_int32), ("block_size", c_int32),
+        ("n_blocks", c_int64),
+        ("dtype", c_int32), ("softmax_scale", c_float),
+        ("workspace", c_void_p), ("workspace_bytes", c_int64),
+        ("path", c_int32), ("device", c_int32), ("reserved", c_int32 * 4),
+    ]
+
+
+class HiPoolGeom(Structure):
+    _fields_ = [("n_layers", c_int64), ("n_tokens", c_int64), ("n_blocks", c_int64), ("run_bytes", c_int64)]
+
+
+# name -> (restype, argtypes); also the list the symbol-export test checks against include/hi_b200.h
+SIGNATURES = {
+    "hi_last_error": (c_char_p, []),
+    "hi_abi_version": (c_int, []),
+    "hi_last_launch_count": (c_int, []),
+    "hi_event_create": (c_int, [POINTER(c_void_p)]),
+    "hi_event_destroy": (c_int, [c_void_p]),
+    "hi_event_record": (c_int, [c_void_p, c_void_p]),
+    "hi_event_elapsed_ms": (c_int, [c_void_p, c_void_p, POINTER(c_float)]),
+    "hi_set_kernel_timing_events": (c_int, [c_void_p, c_void_p]),
+    "hi_set_kv_cache": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
+                                c_int, c_int, c_void_p]),
+    "hi_set_image_cache": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
+    "hi_attention_workspace_bytes": (c_int64, [c_int32, c_int32, c_int32, c_int32]),
+    "hi_paged_attention": (c_int, [POINTER(HiAttnArgs), c_void_p]),
+    "hi_migrate_blocks": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, HiPoolGeom, HiPoolGeom, c_int, c_void_p]),
+    "hi_ipc_get_handle": (c_int, [c_void_p, POINTER(c_uint8), POINTER(c_int64), c_int]),
+    "hi_ipc_open_handle": (c_int, [POINTER(c_uint8), c_int64, c_int, POINTER(c_void_p)]),
+    "hi_ipc_close_all": (c_int, []),
+    "hi_enable_peer_access": (c_int, [c_int, c_int]),
+    "hi_peer_copy": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p]),
+}
+
+
+def _load() -> ctypes.CDLL:
+    from . import build as _build
+
+    force = os.environ.get("HI_B200_REBUILD") == "1"
+    if force or not LIB_PATH.exists() or not _build.is_current():
+        try:
+            _build.build(force=force)  # needs nvcc
+        except Exception as e:
+            if not LIB_PATH.exists():
+                raise ImportError(f"hydrainfer_b200: {LIB_PATH} is missing and cannot be built: {e}") from e
+            raise
+    try:
+        lib = ctypes.CDLL(str(LIB_PATH))
+    except OSError as e:  # pragma: no cover - exercised only on a broken install
+        raise ImportError(f"hydrainfer_b200: cannot load the CUDA extension {LIB_PATH}: {e}") from e
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    return lib
+
+
+lib = _load()
+
+
+def check(status: int) -> None:
+    """Translate a HiStatus into the RuntimeError the reference's pybind modules raise (TORCH_CHECK)."""
+    if status != 0:
+        raise RuntimeError(f"hi_b200 error {status}: {lib.hi_last_error().decode()}")
+
+
+def dtype_code(dtype: torch.dtype) -> int:
+    try:
+        return _DTYPES[dtype]
+    except KeyError:
+        raise RuntimeError(f"hi_b200: dtype {dtype} is not supported (float32, float16, bfloat16)") from None
+
+
+def require_cuda(*tensors: torch.Tensor) -> torch.device:
+    dev = tensors[0].device
+    for t in tensors:
+        if t.device.type != "cuda":
+            raise RuntimeError("hi_b200: the CUDA extension only accepts CUDA tensors; there is no CPU fallback")
+        if t.device != dev:
+            raise RuntimeError(f"hi_b200: tensors on different devices ({t.device} vs {dev})")
+    return dev
+
+
+def current_stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream

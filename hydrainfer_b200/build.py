@@ -1,0 +1,88 @@
+"""Builds libhi_b200.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+No torch headers are involved: the library is plain CUDA behind `extern "C"` (include/hi_b200.h), so the build is a
+handful of `nvcc -c` calls plus one link, and the .so travels with the source tree to the GPU box.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+CSRC = PKG_DIR / "csrc"
+LIB_DIR = PKG_DIR / "lib"
+LIB_PATH = LIB_DIR / "libhi_b200.so"
+OBJ_DIR = CSRC / "build"
+SOURCES = ["api.cu", "scatter.cu", "attn_simt.cu", "attn_tc.cu", "migrate.cu"]
+HEADERS = ["common.cuh", "ptx_sm100.cuh", "../../include/hi_b200.h"]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "-Xcompiler", "-fPIC",
+    "--expt-relaxed-constexpr",
+    "-Xptxas", "-v",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found; the CUDA extension cannot be built")
+
+
+def _stamp() -> str:
+    h = hashlib.sha256()
+    for name in SOURCES + HEADERS:
+        h.update((CSRC / name).read_bytes())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def is_current() -> bool:
+    """True when lib/libhi_b200.so was built from the sources as they are now."""
+    stamp_file = LIB_DIR / "build.stamp"
+    return LIB_PATH.exists() and stamp_file.exists() and stamp_file.read_text() == _stamp()
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile (if sources changed) and return the path of the shared library."""
+    stamp_file = LIB_DIR / "build.stamp"
+    stamp = _stamp()
+    if not force and LIB_PATH.exists() and stamp_file.exists() and stamp_file.read_text() == stamp:
+        return LIB_PATH
+    nvcc = _nvcc()
+    OBJ_DIR.mkdir(parents=True, exist_ok=True)
+    LIB_DIR.mkdir(parents=True, exist_ok=True)
+
+    def compile_one(name: str) -> tuple[str, str]:
+        obj = OBJ_DIR / (Path(name).stem + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / name), "-o", str(obj)]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {name}:\n{res.stdout}\n{res.stderr}")
+        return str(obj), res.stderr
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    if verbose:
+        for _, log in results:
+            sys.stderr.write(log)
+    (OBJ_DIR / "ptxas.log").write_text("\n".join(log for _, log in results))
+    link = [nvcc, "-shared", "-o", str(LIB_PATH), *[o for o, _ in results], "-cudart", "static"]
+    res = subprocess.run(link, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    stamp_file.write_text(stamp)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    path = build(force="--force" in sys.argv, verbose=True)
+    print(path)

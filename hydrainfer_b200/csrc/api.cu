@@ -1,0 +1,131 @@
+// hi_paged_attention: argument validation and kernel selection, plus the error / launch-count plumbing
+// shared by every entry point of include/hi_b200.h.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+
+#include "common.cuh"
+
+static_assert(sizeof(HiAttnArgs) == 168, "HiAttnArgs layout is part of the ABI (ctypes mirror in hydrainfer_b200/_lib.py)");
+static_assert(sizeof(HiPoolGeom) == 32, "HiPoolGeom layout is part of the ABI");
+
+namespace hi {
+
+static thread_local char g_error[512] = "";
+static thread_local int g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+static thread_local cudaEvent_t g_ev_start = nullptr;
+static thread_local cudaEvent_t g_ev_stop = nullptr;
+void timing_mark_start(cudaStream_t stream) {
+  if (g_ev_start != nullptr) {
+    cudaEventRecord(g_ev_start, stream);
+    g_ev_start = nullptr;
+  }
+}
+void timing_mark_stop(cudaStream_t stream) {
+  if (g_ev_stop != nullptr) {
+    cudaEventRecord(g_ev_stop, stream);
+    g_ev_stop = nullptr;
+  }
+}
+void note_launch() { ++g_launches; }
+void reset_launch_count() { g_launches = 0; }
+
+int launch_attn_simt(const HiAttnArgs& args, cudaStream_t stream);
+int launch_attn_tc(const HiAttnArgs& args, cudaStream_t stream);
+bool attn_tc_supported(const HiAttnArgs& args);
+int64_t simt_workspace_bytes(int head_dim);
+
+}  // namespace hi
+
+extern "C" const char* hi_last_error(void) { return hi::g_error; }
+extern "C" int hi_abi_version(void) { return HI_B200_ABI_VERSION; }
+extern "C" int hi_last_launch_count(void) { return hi::g_launches; }
+
+extern "C" int64_t hi_attention_workspace_bytes(int32_t n_tokens, int32_t n_qo_heads, int32_t head_dim, int32_t max_kv_len) {
+  (void)n_tokens;
+  (void)n_qo_heads;
+  (void)max_kv_len;
+  const int64_t need = hi::simt_workspace_bytes(head_dim > 0 ? head_dim : 128);
+  return (need + 255) / 256 * 256;
+}
+
+extern "C" int hi_paged_attention(const HiAttnArgs* p, void* stream_) {
+  using namespace hi;
+  reset_launch_count();
+  HI_CHECK_ARG(p != nullptr, "paged_attention: null args");
+  const HiAttnArgs& a = *p;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  HI_CHECK_ARG(a.n_seqs >= 0 && a.n_tokens >= 0, "paged_attention: negative extents");
+  if (a.n_seqs == 0 || a.n_tokens == 0) return HI_OK;
+  HI_CHECK_ARG(a.q && a.out && a.key_cache && a.value_cache, "paged_attention: null tensor pointer");
+  HI_CHECK_ARG(a.q_cu_seq_lens && a.kv_cu_seq_lens && a.block_tables && a.cu_blocks_lens,
+               "paged_attention: null metadata pointer");
+  HI_CHECK_ARG(a.n_qo_heads > 0 && a.n_kv_heads > 0 && a.n_qo_heads % a.n_kv_heads == 0,
+               "paged_attention: n_qo_heads %d is not divisible by n_kv_heads %d", a.n_qo_heads, a.n_kv_heads);
+  HI_CHECK_ARG(a.block_size > 0 && a.head_dim > 0, "paged_attention: bad block_size %d / head_dim %d", a.block_size, a.head_dim);
+  HI_CHECK_ARG(a.max_q_len >= 1 && a.max_kv_len >= a.max_q_len, "paged_attention: bad max lens q=%d kv=%d", a.max_q_len, a.max_kv_len);
+  const int es = dtype_size(a.dtype);
+  HI_CHECK_SUPPORTED(es != 0, "paged_attention: unsupported dtype %d", a.dtype);
+  const int64_t row = static_cast<int64_t>(a.n_qo_heads) * a.head_dim;
+  HI_CHECK_ARG(a.q_row_stride >= row && a.out_row_stride >= row, "paged_attention: row stride smaller than n_qo_heads*head_dim");
+  // Every lane-level access is at least 8 bytes wide.
+  HI_CHECK_ARG(aligned_to(a.q, 16) && aligned_to(a.out, 16) && aligned_to(a.key_cache, 16) && aligned_to(a.value_cache, 16),
+               "paged_attention: tensors must be 16-byte aligned");
+  HI_CHECK_ARG((a.q_row_stride * es) % 16 == 0 && (a.out_row_stride * es) % 16 == 0,
+               "paged_attention: row strides must be multiples of 16 bytes");
+  HI_CUDA(cudaSetDevice(a.device));
+
+  int path = a.path;
+  if (const char* env = getenv("HI_ATTN_PATH")) {  // test / profiling override: "simt" or "tc"
+    if (env[0] == 's') path = HI_ATTN_SIMT;
+    if (env[0] == 't') path = HI_ATTN_TCGEN05;
+  }
+  if (path == HI_ATTN_AUTO) {
+    // Rows with q_len > 1 are dense contractions: tensor pipe.  Pure decode batches stream KV once per row: the
+    // split-KV kernel keeps more bytes in flight and balances ragged lengths.
+    path = (a.max_q_len > 1 && attn_tc_supported(a)) ? HI_ATTN_TCGEN05 : HI_ATTN_SIMT;
+  }
+  if (path == HI_ATTN_TCGEN05) return launch_attn_tc(a, stream);
+  if (path == HI_ATTN_SIMT) return launch_attn_simt(a, stream);
+  set_error("paged_attention: unknown path %d", path);
+  return HI_ERR_INVALID_ARGUMENT;
+}
+
+extern "C" int hi_event_create(void** event_out) {
+  using namespace hi;
+  HI_CHECK_ARG(event_out != nullptr, "event_create: null output");
+  cudaEvent_t ev;
+  HI_CUDA(cudaEventCreate(&ev));
+  *event_out = ev;
+  return HI_OK;
+}
+extern "C" int hi_event_destroy(void* event) {
+  using namespace hi;
+  if (event != nullptr) HI_CUDA(cudaEventDestroy(static_cast<cudaEvent_t>(event)));
+  return HI_OK;
+}
+extern "C" int hi_event_record(void* event, void* stream) {
+  using namespace hi;
+  HI_CHECK_ARG(event != nullptr, "event_record: null event");
+  HI_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(event), static_cast<cudaStream_t>(stream)));
+  return HI_OK;
+}
+extern "C" int hi_event_elapsed_ms(void* start, void* stop, float* ms_out) {
+  using namespace hi;
+  HI_CHECK_ARG(start && stop && ms_out, "event_elapsed_ms: null argument");
+  HI_CUDA(cudaEventSynchronize(static_cast<cudaEvent_t>(stop)));
+  HI_CUDA(cudaEventElapsedTime(ms_out, static_cast<cudaEvent_t>(start), static_cast<cudaEvent_t>(stop)));
+  return HI_OK;
+}
+extern "C" int hi_set_kernel_timing_events(void* start, void* stop) {
+  hi::g_ev_start = static_cast<cudaEvent_t>(start);
+  hi::g_ev_stop = static_cast<cudaEvent_t>(stop);
+  return HI_OK;
+}

@@ -1,0 +1,438 @@
+// Split-KV paged attention on CUDA cores — the memory-bound decode kernel, and the any-shape generic path.
+//
+// Computes what TorchCausalGroupedQueryPageAttentionHandler.forward computes (reference
+// hydrainfer/layer/causal_attention.py:307-374): query row t of sequence b attends to the first
+// vis = L_b - q_b + i + 1 cached tokens (mask rule :339-342), softmax in fp32, output rounded to the
+// input dtype.  It supersedes the reference's fused backends for q_len == 1 rows: the FA2 paged kernel
+// (csrc/kernel/flash_attn/src/flash_fwd_launch_template.h:71-105, one CTA per (seq, q-head), no KV
+// split) and flashinfer's BatchDecodeWithPagedKVCacheKernel.
+//
+// Work decomposition (grid = rows x kv-head-groups x kv-chunks):
+//   * a CTA owns one query row, G query heads that share one KV head, and one contiguous chunk of the
+//     row's visible keys; a KV byte is fetched once per CTA for all G heads;
+//   * the CTA is 4 warps = 8 half-warps; a half-warp walks 16-token tiles (one page at block_size 16);
+//     its 16 lanes each own D/16 contiguous head dims, so one token row of K or V is one fully
+//     coalesced 128-bit-per-lane load (d=128, 16-bit dtype: 256 B = two whole 128-B lines);
+//   * Q.K partials of the 16 tokens of a tile are reduced across the 16 lanes with a transposing
+//     butterfly (15 shuffles for 16 dot products) that leaves token k's score in lane k, which is
+//     exactly the layout the online softmax (warp-shuffle max) and the P.V broadcast need;
+//   * half-warp states (m, l, o) are merged through shared memory; if the row was split over chunks the
+//     CTA writes an fp32 partial (o, m, l) and merge_partials_kernel does the LSE-weighted reduction.
+//
+// HBM traffic per row and KV head: 2 * vis * D * sizeof(T) bytes of K and V, read exactly once.
+#include <cfloat>
+
+#include "common.cuh"
+
+namespace hi {
+
+struct SimtArgs {
+  const void* q;
+  void* out;
+  const void* kc;
+  const void* vc;
+  int64_t q_row_stride, out_row_stride;  // elements
+  int64_t tok_stride;                    // elements between consecutive slots of the cache: Hkv * D
+  const int32_t* q_cu;
+  const int32_t* kv_cu;
+  const int32_t* block_tables;
+  const int32_t* cu_blocks;
+  int n_seqs, n_tokens, n_qo_heads, n_kv_heads, group, block_size;
+  int chunk_tiles;  // 16-token tiles per chunk
+  int n_chunks;
+  float scale_log2;  // softmax_scale * log2(e)
+  float* part_o;     // [n_tokens * Hq * n_chunks][D]
+  float* part_ml;    // [n_tokens * Hq * n_chunks][2]
+};
+
+constexpr int kSimtThreads = 128;
+constexpr int kHalfWarps = kSimtThreads / 16;
+constexpr unsigned kFull = 0xffffffffu;
+
+// Sequence owning query row t: largest b with q_cu[b] <= t.
+__device__ __forceinline__ int find_seq(const int32_t* __restrict__ q_cu, int n_seqs, int t) {
+  int lo = 0, hi = n_seqs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(q_cu + mid) <= t) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// E contiguous elements of one lane, as raw 32-bit words.
+template <typename T, int E>
+struct LaneRow {
+  static constexpr int W = E * static_cast<int>(sizeof(T)) / 4;
+  static_assert(W >= 2, "a lane owns at least 8 bytes of a row");
+  uint32_t w[W];
+
+  __device__ __forceinline__ void load(const T* p) {
+    if constexpr (W == 2) {
+      const uint2 v = ldg_stream_8(p);
+      w[0] = v.x;
+      w[1] = v.y;
+    } else {
+#pragma unroll
+      for (int i = 0; i < W / 4; ++i) {
+        const uint4 v = ldg_stream_16(reinterpret_cast<const char*>(p) + 16 * i);
+        w[4 * i + 0] = v.x;
+        w[4 * i + 1] = v.y;
+        w[4 * i + 2] = v.z;
+        w[4 * i + 3] = v.w;
+      }
+    }
+  }
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int i = 0; i < W; ++i) w[i] = 0u;
+  }
+  __device__ __forceinline__ void to_f32(float (&f)[E]) const {
+    if constexpr (sizeof(T) == 4) {
+#pragma unroll
+      for (int i = 0; i < E; ++i) f[i] = __uint_as_float(w[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < W; ++i) unpack2<T>(w[i], f[2 * i], f[2 * i + 1]);
+    }
+  }
+};
+
+// Sum N per-lane values across the 16 lanes of a half-warp so that lane l ends with the total of value l.
+template <int N>
+__device__ __forceinline__ void transpose_reduce16(float (&v)[16], int lane) {
+  if constexpr (N >= 2) {
+    constexpr int H = N / 2;
+    const bool upper = (lane & H) != 0;
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+      const float send = upper ? v[i] : v[i + H];
+      const float keep = upper ? v[i + H] : v[i];
+      v[i] = keep + __shfl_xor_sync(kFull, send, H);
+    }
+    transpose_reduce16<H>(v, lane);
+  }
+}
+
+template <typename T, int D, int G>
+__global__ void __launch_bounds__(kSimtThreads) paged_attn_simt_kernel(const SimtArgs a) {
+  constexpr int E = D / 16;                                        // head dims per lane
+  constexpr int W = LaneRow<T, E>::W;                              // 32-bit words per lane per row
+  constexpr int TB = (64 / W) < 16 ? (64 / W) : 16;                // tokens loaded per batch (<= 64 raw regs)
+  static_assert(16 % TB == 0, "token batch must divide the tile");
+
+  const int t = blockIdx.x;
+  const int groups_per_kv = a.group / G;
+  const int kvh = blockIdx.y / groups_per_kv;
+  const int qh0 = kvh * a.group + (blockIdx.y % groups_per_kv) * G;
+  const int chunk = blockIdx.z;
+
+  const int b = find_seq(a.q_cu, a.n_seqs, t);
+  const int q_start = __ldg(a.q_cu + b);
+  const int q_len = __ldg(a.q_cu + b + 1) - q_start;
+  const int kv_len = __ldg(a.kv_cu + b + 1) - __ldg(a.kv_cu + b);
+  const int vis = kv_len - q_len + (t - q_start) + 1;  // keys 0 .. vis-1 are visible to this row
+  const int tiles_total = (vis + 15) >> 4;
+  const int tile_begin = chunk * a.chunk_tiles;
+  if (tile_begin >= tiles_total) return;  // merge_partials_kernel recomputes the valid chunk count
+  const int tile_end = min(tiles_total, tile_begin + a.chunk_tiles);
+  const int n_iters = (tile_end - tile_begin + kHalfWarps - 1) / kHalfWarps;
+  const int32_t* __restrict__ bt = a.block_tables + __ldg(a.cu_blocks + b);
+
+  const int lane = threadIdx.x & 31;
+  const int l16 = lane & 15;
+  const int hw = threadIdx.x >> 4;
+
+  const T* __restrict__ kbase = static_cast<const T*>(a.kc) + kvh * D + l16 * E;
+  const T* __restrict__ vbase = static_cast<const T*>(a.vc) + kvh * D + l16 * E;
+
+  // This lane's slice of the G query heads, pre-multiplied by scale*log2(e) so scores live in the exp2 domain.
+  float qf[G][E];
+  {
+    const T* qrow = static_cast<const T*>(a.q) + static_cast<int64_t>(t) * a.q_row_stride + qh0 * D + l16 * E;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      LaneRow<T, E> r;
+      r.load(qrow + g * D);
+      r.to_f32(qf[g]);
+#pragma unroll
+      for (int e = 0; e < E; ++e) qf[g][e] *= a.scale_log2;
+    }
+  }
+
+  float m[G], lsum[G], o[G][E];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    m[g] = -INFINITY;
+    lsum[g] = 0.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) o[g][e] = 0.f;
+  }
+
+  for (int it = 0; it < n_iters; ++it) {
+    const int tile = tile_begin + it * kHalfWarps + hw;
+    const int pos = tile * 16 + l16;
+    const bool valid = (tile < tile_end) && (pos < vis);
+    // Physical slot of this lane's token (block_table[pos / bs] * bs + pos % bs, token_cache_manger.py:126-133).
+    int slot = -1;
+    if (valid) {
+      const int pg = pos / a.block_size;
+      slot = __ldg(bt + pg) * a.block_size + (pos - pg * a.block_size);
+    }
+
+    // ---- S = q . K^T for the 16 tokens of the tile -------------------------------------------------------
+    float acc[G][16];
+#pragma unroll
+    for (int kb = 0; kb < 16; kb += TB) {
+      LaneRow<T, E> raw[TB];
+#pragma unroll
+      for (int k = 0; k < TB; ++k) {
+        const int sk = __shfl_sync(kFull, slot, kb + k, 16);
+        raw[k].load(kbase + static_cast<int64_t>(sk < 0 ? 0 : sk) * a.tok_stride);  // masked below if sk < 0
+      }
+#pragma unroll
+      for (int k = 0; k < TB; ++k) {
+        float kf[E];
+        raw[k].to_f32(kf);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          float s = 0.f;
+#pragma unroll
+          for (int e = 0; e < E; ++e) s = fmaf(qf[g][e], kf[e], s);
+          acc[g][kb + k] = s;
+        }
+      }
+    }
+
+    // ---- online softmax; lane k now owns token k ------------------------------------------------------------
+    float p[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      transpose_reduce16<16>(acc[g], l16);
+      const float s = valid ? acc[g][0] : -INFINITY;
+      float mx = s;
+#pragma unroll
+      for (int off = 8; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, off));
+      const float m_new = fmaxf(m[g], mx);
+      const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;  // half-warp with no valid token yet
+      const float alpha = fast_exp2(m[g] - m_safe);
+      p[g] = fast_exp2(s - m_safe);
+      lsum[g] = lsum[g] * alpha + p[g];  // lane-partial; summed over lanes once at the end
+      m[g] = m_new;
+#pragma unroll
+      for (int e = 0; e < E; ++e) o[g][e] *= alpha;
+    }
+
+    // ---- O += P . V -------------------------------------------------------------------------------------------
+#pragma unroll
+    for (int kb = 0; kb < 16; kb += TB) {
+      LaneRow<T, E> raw[TB];
+#pragma unroll
+      for (int k = 0; k < TB; ++k) {
+        const int sk = __shfl_sync(kFull, slot, kb + k, 16);
+        raw[k].load(vbase + static_cast<int64_t>(sk < 0 ? 0 : sk) * a.tok_stride);
+        if (sk < 0) raw[k].zero();  // p is 0 there, but 0 * garbage could be NaN
+      }
+#pragma unroll
+      for (int k = 0; k < TB; ++k) {
+        float vf[E];
+        raw[k].to_f32(vf);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const float pk = __shfl_sync(kFull, p[g], kb + k, 16);
+#pragma unroll
+          for (int e = 0; e < E; ++e) o[g][e] = fmaf(pk, vf[e], o[g][e]);
+        }
+      }
+    }
+  }
+
+  // ---- merge the 8 half-warp states ----------------------------------------------------------------------------
+  __shared__ float sm_o[kHalfWarps][G][D];
+  __shared__ float sm_m[kHalfWarps][G];
+  __shared__ float sm_l[kHalfWarps][G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    float l = lsum[g];
+#pragma unroll
+    for (int off = 8; off >= 1; off >>= 1) l += __shfl_xor_sync(kFull, l, off);
+    if (l16 == 0) {
+      sm_m[hw][g] = m[g];
+      sm_l[hw][g] = l;
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) sm_o[hw][g][l16 * E + e] = o[g][e];
+  }
+  __syncthreads();
+
+  for (int idx = threadIdx.x; idx < G * D; idx += kSimtThreads) {
+    const int g = idx / D;
+    const int d = idx - g * D;
+    float mm = -INFINITY;
+#pragma unroll
+    for (int h = 0; h < kHalfWarps; ++h) mm = fmaxf(mm, sm_m[h][g]);
+    float osum = 0.f, l = 0.f;
+#pragma unroll
+    for (int h = 0; h < kHalfWarps; ++h) {
+      const float w = fast_exp2(sm_m[h][g] - mm);  // mm is finite: the chunk has at least one visible key
+      osum = fmaf(w, sm_o[h][g][d], osum);
+      l = fmaf(w, sm_l[h][g], l);
+    }
+    const int head = qh0 + g;
+    if (a.n_chunks == 1) {
+      T* orow = static_cast<T*>(a.out) + static_cast<int64_t>(t) * a.out_row_stride + head * D;
+      orow[d] = Elem<T>::from_f32(osum / l);
+    } else {
+      const int64_t pidx = (static_cast<int64_t>(t) * a.n_qo_heads + head) * a.n_chunks + chunk;
+      a.part_o[pidx * D + d] = osum;
+      if (d == 0) {
+        a.part_ml[pidx * 2 + 0] = mm;
+        a.part_ml[pidx * 2 + 1] = l;
+      }
+    }
+  }
+}
+
+// LSE-weighted reduction of the per-chunk partials of one (row, head): the split-merge step.
+template <typename T, int D>
+__global__ void __launch_bounds__(D / 4) merge_partials_kernel(const SimtArgs a) {
+  const int t = blockIdx.x;
+  const int head = blockIdx.y;
+  const int b = find_seq(a.q_cu, a.n_seqs, t);
+  const int q_start = __ldg(a.q_cu + b);
+  const int q_len = __ldg(a.q_cu + b + 1) - q_start;
+  const int kv_len = __ldg(a.kv_cu + b + 1) - __ldg(a.kv_cu + b);
+  const int vis = kv_len - q_len + (t - q_start) + 1;
+  const int tiles_total = (vis + 15) >> 4;
+  const int n_valid = (tiles_total + a.chunk_tiles - 1) / a.chunk_tiles;
+
+  const int64_t base = (static_cast<int64_t>(t) * a.n_qo_heads + head) * a.n_chunks;
+  float mm = -INFINITY;
+  for (int c = 0; c < n_valid; ++c) mm = fmaxf(mm, a.part_ml[(base + c) * 2]);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float l = 0.f;
+  const int d4 = threadIdx.x;
+  for (int c = 0; c < n_valid; ++c) {
+    const float w = fast_exp2(a.part_ml[(base + c) * 2] - mm);
+    l = fmaf(w, a.part_ml[(base + c) * 2 + 1], l);
+    const float4 v = *reinterpret_cast<const float4*>(a.part_o + (base + c) * D + d4 * 4);
+    acc.x = fmaf(w, v.x, acc.x);
+    acc.y = fmaf(w, v.y, acc.y);
+    acc.z = fmaf(w, v.z, acc.z);
+    acc.w = fmaf(w, v.w, acc.w);
+  }
+  const float inv = 1.f / l;
+  T* orow = static_cast<T*>(a.out) + static_cast<int64_t>(t) * a.out_row_stride + head * D + d4 * 4;
+  orow[0] = Elem<T>::from_f32(acc.x * inv);
+  orow[1] = Elem<T>::from_f32(acc.y * inv);
+  orow[2] = Elem<T>::from_f32(acc.z * inv);
+  orow[3] = Elem<T>::from_f32(acc.w * inv);
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------------
+
+constexpr int kTargetCtas = 148 * 32;  // enough CTAs that the last partial wave is a few % of the launch
+constexpr int kMinChunkTiles = 16;     // never split finer than 256 tokens
+
+int64_t simt_workspace_bytes(int head_dim) {
+  // Partials exist only when n_chunks > 1, i.e. when rows*heads/G < kTargetCtas; then
+  // rows*heads*n_chunks <= 2*G*kTargetCtas with G <= 4.
+  return static_cast<int64_t>(8) * kTargetCtas * (head_dim + 2) * 4;
+}
+
+template <typename T, int D, int G>
+static int launch_simt_g(const SimtArgs& a, cudaStream_t stream) {
+  const dim3 grid(a.n_tokens, a.n_kv_heads * (a.group / G), a.n_chunks);
+  timing_mark_start(stream);
+  paged_attn_simt_kernel<T, D, G><<<grid, kSimtThreads, 0, stream>>>(a);
+  timing_mark_stop(stream);
+  note_launch();
+  HI_CUDA(cudaGetLastError());
+  if (a.n_chunks > 1) {
+    merge_partials_kernel<T, D><<<dim3(a.n_tokens, a.n_qo_heads), D / 4, 0, stream>>>(a);
+    note_launch();
+    HI_CUDA(cudaGetLastError());
+  }
+  return HI_OK;
+}
+
+static int pick_group(int group, int max_g) {
+  for (int g = max_g; g > 1; g >>= 1)
+    if (group % g == 0) return g;
+  return 1;
+}
+
+template <typename T, int D>
+static int launch_simt_td(SimtArgs& a, const HiAttnArgs& args, cudaStream_t stream) {
+  // fp32 is the reference-parity path only: one head per CTA keeps it within the register budget.
+  const int G = pick_group(a.group, sizeof(T) == 4 ? 1 : 4);
+  const int64_t ctas_per_chunk = static_cast<int64_t>(a.n_tokens) * a.n_kv_heads * (a.group / G);
+  const int max_tiles = (args.max_kv_len + 15) / 16;
+  int want_chunks = static_cast<int>((kTargetCtas + ctas_per_chunk - 1) / ctas_per_chunk);
+  const int max_chunks = (max_tiles + kMinChunkTiles - 1) / kMinChunkTiles;
+  if (want_chunks > max_chunks) want_chunks = max_chunks;
+  if (want_chunks < 1) want_chunks = 1;
+  a.chunk_tiles = (max_tiles + want_chunks - 1) / want_chunks;
+  a.chunk_tiles = (a.chunk_tiles + kHalfWarps - 1) / kHalfWarps * kHalfWarps;  // keep all 8 half-warps busy
+  a.n_chunks = (max_tiles + a.chunk_tiles - 1) / a.chunk_tiles;
+  if (a.n_chunks < 1) a.n_chunks = 1;
+  if (a.n_chunks > 1) {
+    const int64_t entries = static_cast<int64_t>(a.n_tokens) * a.n_qo_heads * a.n_chunks;
+    const int64_t need = entries * (D + 2) * 4;
+    if (args.workspace == nullptr || args.workspace_bytes < need) {
+      set_error("paged_attention: workspace of %lld bytes is smaller than the %lld needed for %d KV chunks",
+                (long long)args.workspace_bytes, (long long)need, a.n_chunks);
+      return HI_ERR_WORKSPACE;
+    }
+    a.part_o = static_cast<float*>(args.workspace);
+    a.part_ml = a.part_o + entries * D;
+  }
+  switch (G) {
+    case 4:
+      if constexpr (sizeof(T) == 2) return launch_simt_g<T, D, 4>(a, stream);
+    case 2:
+      if constexpr (sizeof(T) == 2) return launch_simt_g<T, D, 2>(a, stream);
+    default: return launch_simt_g<T, D, 1>(a, stream);
+  }
+}
+
+template <typename T>
+static int launch_simt_t(SimtArgs& a, const HiAttnArgs& args, cudaStream_t stream) {
+  switch (args.head_dim) {
+    case 64: return launch_simt_td<T, 64>(a, args, stream);
+    case 128: return launch_simt_td<T, 128>(a, args, stream);
+    case 256: return launch_simt_td<T, 256>(a, args, stream);
+    default:
+      set_error("paged_attention: head_dim %d not supported (64, 128, 256)", args.head_dim);
+      return HI_ERR_UNSUPPORTED;
+  }
+}
+
+int launch_attn_simt(const HiAttnArgs& args, cudaStream_t stream) {
+  SimtArgs a{};
+  a.q = args.q;
+  a.out = args.out;
+  a.kc = args.key_cache;
+  a.vc = args.value_cache;
+  a.q_row_stride = args.q_row_stride;
+  a.out_row_stride = args.out_row_stride;
+  a.tok_stride = static_cast<int64_t>(args.n_kv_heads) * args.head_dim;
+  a.q_cu = args.q_cu_seq_lens;
+  a.kv_cu = args.kv_cu_seq_lens;
+  a.block_tables = args.block_tables;
+  a.cu_blocks = args.cu_blocks_lens;
+  a.n_seqs = args.n_seqs;
+  a.n_tokens = args.n_tokens;
+  a.n_qo_heads = args.n_qo_heads;
+  a.n_kv_heads = args.n_kv_heads;
+  a.group = args.n_qo_heads / args.n_kv_heads;
+  a.block_size = args.block_size;
+  a.scale_log2 = args.softmax_scale * 1.4426950408889634f;
+  switch (args.dtype) {
+    case HI_F32: return launch_simt_t<float>(a, args, stream);
+    case HI_F16: return launch_simt_t<__half>(a, args, stream);
+    case HI_BF16: return launch_simt_t<__nv_bfloat16>(a, args, stream);
+    default: set_error("paged_attention: unsupported dtype %d", args.dtype); return HI_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace hi

@@ -1,0 +1,506 @@
+// Paged causal attention on the 5th-gen tensor cores: tcgen05.mma with TMEM accumulators, operands staged by TMA.
+//
+// Same function as TorchCausalGroupedQueryPageAttentionHandler.forward (reference
+// hydrainfer/layer/causal_attention.py:307-374) for q_len > 1 rows (prefill / chunked prefill) and, through
+// GQA packing, for decode rows of grouped models.  It supersedes the reference's FA2 `flash_fwd_splitkv_kernel`
+// (csrc/kernel/flash_attn/src/flash_fwd_launch_template.h:71-141: mma.sync m16n8k16, kBlockM = 64, one q-head per
+// CTA) and flashinfer's BatchPrefillWithPagedKVCache (mma.sync as well).
+//
+// One CTA = one 128-row query tile of one (sequence, KV head):
+//   * rows are (token, head-in-group) pairs, row = token * G + g, so the G query heads that share a KV head are
+//     packed into the same MMA M dimension and every K/V byte staged in shared memory serves all of them;
+//     the tile holds TQ = 128 / G tokens (one TMA box {64 dims, G heads, TQ tokens} per 64-dim half);
+//   * KV is walked in 128-token tiles = 128/block_size pages; each page of a KV head is one TMA box
+//     {64 dims, 1 head, block_size slots} per half of the head dim, written 128B-swizzled, so a tile is exactly
+//     the K-major (for Q.K^T) / MN-major (for P.V) canonical UMMA layout with no data movement by threads;
+//   * S = Q.K^T (M=128, N=128, K=128) accumulates in TMEM columns [0,128); the 4 softmax warps read their row
+//     with tcgen05.ld (one thread = one row = one TMEM lane), apply the bottom-right causal mask
+//     (key j visible to row i iff j <= i + L - q, causal_attention.py:339-342), keep a running max / sum, and
+//     write P as packed 16-bit pairs back into TMEM columns [0,64) (aliasing S);
+//   * O += P.V is issued with A = P from TMEM (tcgen05.mma ..., [tmem_a], ...) and B = V from shared memory;
+//     O lives in TMEM columns [128,256) for the whole tile and is rescaled in place only when the running max
+//     grows by more than 2^8 (lazy rescale), normalised by the row sum in the epilogue.
+//   * warp roles: warps 0-3 softmax + epilogue, warp 4 TMA producer (and TMEM allocator), warp 5 MMA issuer;
+//     all hand-offs are mbarriers (TMA transaction bytes, tcgen05.commit, thread arrivals).
+// Two CTAs are co-resident per SM (256 TMEM columns and ~97 KiB of shared memory each) so one CTA's softmax
+// overlaps the other's MMAs.
+#include <cuda.h>
+
+#include <cstdlib>
+
+#include <mutex>
+#include <type_traits>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace hi {
+
+constexpr int kTcThreads = 192;
+constexpr int kTileM = 128;
+constexpr int kTileN = 128;
+constexpr int kHeadDim = 128;
+constexpr int kHalfBytes = kTileM * 128;       // one 64-dim half of a 128-row tile: 16 KiB
+constexpr int kTileBytes = 2 * kHalfBytes;     // 32 KiB
+constexpr uint32_t kTmemCols = 256;
+constexpr uint32_t kColS = 0;                  // S accumulator (fp32) and, aliased, P (16-bit pairs)
+constexpr uint32_t kColO = 128;                // O accumulator (fp32)
+constexpr float kRescaleThreshold = 8.0f;      // log2 of the largest stale-max overshoot P may carry
+
+struct TcArgs {
+  void* out;
+  int64_t out_row_stride;  // elements
+  const int32_t* q_cu;
+  const int32_t* kv_cu;
+  const int32_t* block_tables;
+  const int32_t* cu_blocks;
+  int n_qo_heads, n_kv_heads, group, block_size;
+  int tq;            // query tokens per tile: 128 / group
+  float scale_log2;  // softmax_scale * log2(e)
+  int serialize;     // debug: wait for P.V to finish before the next Q.K^T is issued (HI_TC_SERIALIZE=1)
+};
+
+template <int NST>
+struct TcSmem {
+  static constexpr int kQ = 0;
+  static constexpr int kK = kTileBytes;
+  static constexpr int kV = kTileBytes + NST * kTileBytes;
+  static constexpr int kBars = kTileBytes + 2 * NST * kTileBytes;
+  // barrier slots (8 bytes each)
+  static constexpr int bQFull = 0;
+  static constexpr int bKFull = 1;
+  static constexpr int bKEmpty = 1 + NST;
+  static constexpr int bVFull = 1 + 2 * NST;
+  static constexpr int bVEmpty = 1 + 3 * NST;
+  static constexpr int bSFull = 1 + 4 * NST;
+  static constexpr int bPFull = 2 + 4 * NST;
+  static constexpr int bOFull = 3 + 4 * NST;
+  static constexpr int kNumBars = 4 + 4 * NST;
+  static constexpr int kTmemPtr = kBars + kNumBars * 8;
+  static constexpr int kTotal = kTmemPtr + 16;
+  static constexpr int kDynamicBytes = kTotal + 1024;  // slack to align the base to 1024 B (128B swizzle atoms)
+};
+
+template <typename T, int NST>
+__global__ void __launch_bounds__(kTcThreads, NST == 1 ? 2 : 1)
+paged_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                     const __grid_constant__ CUtensorMap tm_v, const TcArgs a) {
+  using L = TcSmem<NST>;
+  constexpr bool kBf16 = sizeof(T) == 2 && !std::is_same<T, __half>::value;
+
+  // ---- which tile --------------------------------------------------------------------------------------------------
+  const int b = blockIdx.z;
+  const int kvh = blockIdx.y;
+  const int q_start = __ldg(a.q_cu + b);
+  const int q_len = __ldg(a.q_cu + b + 1) - q_start;
+  const int kv_len = __ldg(a.kv_cu + b + 1) - __ldg(a.kv_cu + b);
+  const int n_q_tiles = (q_len + a.tq - 1) / a.tq;
+  // Heaviest tiles (the end of the sequence sees the most keys) are scheduled first.
+  const int q_tile = n_q_tiles - 1 - static_cast<int>(blockIdx.x);
+  if (q_tile < 0) return;
+  const int i0 = q_tile * a.tq;                                   // first query position of the tile
+  const int i_last = min(q_len, i0 + a.tq) - 1;                   // last valid query position
+  const int kv_end = i_last + (kv_len - q_len) + 1;               // keys [0, kv_end) are visible to the tile
+  const int n_kv_tiles = (kv_end + kTileN - 1) / kTileN;
+  const int blk0 = __ldg(a.cu_blocks + b);
+  const int n_pages = __ldg(a.cu_blocks + b + 1) - blk0;
+  const int pages_per_tile = kTileN / a.block_size;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  auto bar = [&](int idx) -> uint32_t { return smem_base + L::kBars + idx * 8; };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + L::kTmemPtr);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- one-time setup ------------------------------------------------------------------------------------------------
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(bar(L::bQFull), 1);
+    for (int s = 0; s < NST; ++s) {
+      ptx::mbar_init(bar(L::bKFull + s), 1);
+      ptx::mbar_init(bar(L::bKEmpty + s), 1);
+      ptx::mbar_init(bar(L::bVFull + s), 1);
+      ptx::mbar_init(bar(L::bVEmpty + s), 1);
+    }
+    ptx::mbar_init(bar(L::bSFull), 1);
+    ptx::mbar_init(bar(L::bPFull), kTileM);  // every softmax thread arrives
+    ptx::mbar_init(bar(L::bOFull), 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 4) {
+    if (lane == 0) {
+      ptx::prefetch_tensormap(&tm_q);
+      ptx::prefetch_tensormap(&tm_k);
+      ptx::prefetch_tensormap(&tm_v);
+    }
+    __syncwarp();
+    ptx::tmem_alloc(smem_base + L::kTmemPtr, kTmemCols);
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 4) {
+    // ================================================ TMA producer ================================================
+    if (lane == 0) {
+      // Q tile: both 64-dim halves, rows ordered (token, head-in-group).
+      const uint32_t q_bytes = 2u * static_cast<uint32_t>(a.group * a.tq) * 128u;
+      ptx::mbar_arrive_expect_tx(bar(L::bQFull), q_bytes);
+      ptx::tma_load_3d(smem_base + L::kQ, &tm_q, bar(L::bQFull), 0, kvh * a.group, q_start + i0);
+      ptx::tma_load_3d(smem_base + L::kQ + kHalfBytes, &tm_q, bar(L::bQFull), 64, kvh * a.group, q_start + i0);
+    }
+    const uint32_t page_half_bytes = static_cast<uint32_t>(a.block_size) * 128u;
+    for (int j = 0; j < n_kv_tiles; ++j) {
+      const int st = j % NST;
+      const uint32_t ph = static_cast<uint32_t>(j / NST) & 1u;
+      const int page0 = j * pages_per_tile;
+      const int n_valid = min(pages_per_tile, n_pages - page0);
+      // lane p stages page p of the tile
+      int blk = 0;
+      if (lane < n_valid) blk = __ldg(a.block_tables + blk0 + page0 + lane);
+      const uint32_t tx = static_cast<uint32_t>(n_valid) * 2u * page_half_bytes;
+      // K
+      if (lane == 0) {
+        ptx::mbar_wait(bar(L::bKEmpty + st), ph ^ 1u);
+        ptx::mbar_arrive_expect_tx(bar(L::bKFull + st), tx);
+      }
+      __syncwarp();
+      if (lane < n_valid) {
+        const uint32_t dst = smem_base + L::kK + st * kTileBytes + lane * page_half_bytes;
+        ptx::tma_load_3d(dst, &tm_k, bar(L::bKFull + st), 0, kvh, blk * a.block_size);
+        ptx::tma_load_3d(dst + kHalfBytes, &tm_k, bar(L::bKFull + st), 64, kvh, blk * a.block_size);
+      }
+      // V
+      if (lane == 0) {
+        ptx::mbar_wait(bar(L::bVEmpty + st), ph ^ 1u);
+        ptx::mbar_arrive_expect_tx(bar(L::bVFull + st), tx);
+      }
+      __syncwarp();
+      if (lane < n_valid) {
+        const uint32_t dst = smem_base + L::kV + st * kTileBytes + lane * page_half_bytes;
+        ptx::tma_load_3d(dst, &tm_v, bar(L::bVFull + st), 0, kvh, blk * a.block_size);
+        ptx::tma_load_3d(dst + kHalfBytes, &tm_v, bar(L::bVFull + st), 64, kvh, blk * a.block_size);
+      }
+    }
+  } else if (warp == 5) {
+    // ================================================ MMA issuer ==================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = ptx::make_idesc_f16(kBf16, false, false, kTileM, kTileN);
+      constexpr uint32_t idesc_pv = ptx::make_idesc_f16(kBf16, false, true, kTileM, kHeadDim);
+      const uint32_t tmem_s = tmem_base + kColS;
+      const uint32_t tmem_o = tmem_base + kColO;
+      ptx::mbar_wait(bar(L::bQFull), 0);
+      for (int j = 0; j < n_kv_tiles; ++j) {
+        const int st = j % NST;
+        const uint32_t ph = static_cast<uint32_t>(j / NST) & 1u;
+        // ---- S = Q . K^T : 2 halves x 4 k-steps of 16 dims; both operands K-major, 8-row groups 1024 B apart
+        ptx::mbar_wait(bar(L::bKFull + st), ph);
+        ptx::tc_fence_after_sync();
+        const uint32_t q_addr = smem_base + L::kQ;
+        const uint32_t k_addr = smem_base + L::kK + st * kTileBytes;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t off = (kk >> 2) * kHalfBytes + (kk & 3) * 32;
+          ptx::mma_f16_ss(tmem_s, ptx::make_smem_desc_sw128(q_addr + off, 16, 1024),
+                          ptx::make_smem_desc_sw128(k_addr + off, 16, 1024), idesc_qk, kk > 0);
+        }
+        ptx::mma_commit(bar(L::bKEmpty + st));  // K slot reusable once these MMAs have read it
+        ptx::mma_commit(bar(L::bSFull));        // S ready (also implies the previous P.V finished)
+        // ---- O += P . V : 8 k-steps of 16 tokens; A = P in TMEM (8 columns per step), B = V MN-major
+        ptx::mbar_wait(bar(L::bPFull), static_cast<uint32_t>(j) & 1u);
+        ptx::mbar_wait(bar(L::bVFull + st), ph);
+        ptx::tc_fence_after_sync();
+        const uint32_t v_addr = smem_base + L::kV + st * kTileBytes;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          ptx::mma_f16_ts(tmem_o, tmem_s + kk * 8, ptx::make_smem_desc_sw128(v_addr + kk * 2048, kHalfBytes, 1024),
+                          idesc_pv, (j > 0) || (kk > 0));
+        }
+        ptx::mma_commit(bar(L::bVEmpty + st));
+        if (j == n_kv_tiles - 1) ptx::mma_commit(bar(L::bOFull));
+        if (a.serialize) ptx::mbar_wait(bar(L::bVEmpty + st), ph);
+      }
+    }
+  } else {
+    // ================================================ softmax + epilogue ===========================================
+    const int r = threadIdx.x;                       // tile row == TMEM lane
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    const uint32_t tmem_s = tmem_base + lane_base + kColS;
+    const uint32_t tmem_o = tmem_base + lane_base + kColO;
+    const int tok = r / a.group;                     // token within the tile
+    const int g = r - tok * a.group;
+    const int i = i0 + tok;                          // query position within the sequence
+    const bool row_valid = (tok < a.tq) && (i < q_len);
+    const int lim = i + (kv_len - q_len);            // last visible key index for this row
+    float m_used = 0.f;                              // exponent reference, scaled log2 domain
+    float l = 0.f;
+
+    for (int j = 0; j < n_kv_tiles; ++j) {
+      const int kv0 = j * kTileN;
+      const int col_lim = lim - kv0;                 // columns [0, col_lim] are visible
+      const bool need_mask = col_lim < kTileN - 1;
+      ptx::mbar_wait(bar(L::bSFull), static_cast<uint32_t>(j) & 1u);
+      ptx::tc_fence_after_sync();
+
+      // pass 1: row max of the raw scores
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        ptx::tmem_ld_x32(tmem_s + c * 32, v);
+        ptx::tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          float s = __uint_as_float(v[e]);
+          if (need_mask && (c * 32 + e > col_lim)) s = -INFINITY;
+          mx = fmaxf(mx, s);
+        }
+      }
+      const float mxs = mx * a.scale_log2;
+      if (j == 0) {
+        m_used = (mxs == -INFINITY) ? 0.f : mxs;
+      } else if (__any_sync(0xffffffffu, mxs > m_used + kRescaleThreshold)) {
+        // Lazy rescale: the whole warp pays the TMEM round trip only when some row's max grew by > 2^8.
+        const float m_new = fmaxf(m_used, mxs);
+        const float alpha = fast_exp2(m_used - m_new);
+        l *= alpha;
+        m_used = m_new;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          ptx::tmem_ld_x32(tmem_o + c * 32, v);
+          ptx::tmem_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+          ptx::tmem_st_x32(tmem_o + c * 32, v);
+        }
+      }
+
+      // pass 2: P = exp2(S * scale - m) as 16-bit pairs, written over S
+      float lsum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        ptx::tmem_ld_x32(tmem_s + c * 32, v);
+        ptx::tmem_wait_ld();
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          float s0 = __uint_as_float(v[e]);
+          float s1 = __uint_as_float(v[e + 1]);
+          if (need_mask) {
+            if (c * 32 + e > col_lim) s0 = -INFINITY;
+            if (c * 32 + e + 1 > col_lim) s1 = -INFINITY;
+          }
+          const float p0 = fast_exp2(fmaf(s0, a.scale_log2, -m_used));
+          const float p1 = fast_exp2(fmaf(s1, a.scale_log2, -m_used));
+          lsum += p0 + p1;
+          pk[e >> 1] = pack2<T>(p0, p1);
+        }
+        ptx::tmem_st_x16(tmem_s + c * 16, pk);
+      }
+      l += lsum;
+
+      // Keys at or beyond kv_len (tail of the last page, pages that do not exist) carry P == 0, but their V rows are
+      // whatever the pool / stale shared memory holds; zero them so 0 * NaN cannot reach O.
+      if (kv0 + kTileN > kv_len) {
+        const int st = j % NST;
+        ptx::mbar_wait(bar(L::bVFull + st), static_cast<uint32_t>(j / NST) & 1u);
+        if (kv0 + r >= kv_len) {
+          uint4* row0 = reinterpret_cast<uint4*>(smem_gen + L::kV + st * kTileBytes + r * 128);
+          uint4* row1 = reinterpret_cast<uint4*>(smem_gen + L::kV + st * kTileBytes + kHalfBytes + r * 128);
+          const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            row0[e] = z;
+            row1[e] = z;
+          }
+        }
+        ptx::fence_proxy_async_smem();
+      }
+      ptx::tmem_wait_st();
+      ptx::tc_fence_before_sync();
+      ptx::mbar_arrive(bar(L::bPFull));
+    }
+
+    // ---- epilogue: O / l -> out ----------------------------------------------------------------------------------
+    ptx::mbar_wait(bar(L::bOFull), 0);
+    ptx::tc_fence_after_sync();
+    const float inv_l = 1.f / l;
+    T* orow = static_cast<T*>(a.out) + static_cast<int64_t>(q_start + i) * a.out_row_stride +
+              (kvh * a.group + g) * kHeadDim;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      ptx::tmem_ld_x32(tmem_o + c * 32, v);
+      ptx::tmem_wait_ld();
+      if (row_valid) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 8) {
+          uint4 w;
+          w.x = pack2<T>(__uint_as_float(v[e + 0]) * inv_l, __uint_as_float(v[e + 1]) * inv_l);
+          w.y = pack2<T>(__uint_as_float(v[e + 2]) * inv_l, __uint_as_float(v[e + 3]) * inv_l);
+          w.z = pack2<T>(__uint_as_float(v[e + 4]) * inv_l, __uint_as_float(v[e + 5]) * inv_l);
+          w.w = pack2<T>(__uint_as_float(v[e + 6]) * inv_l, __uint_as_float(v[e + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(orow + c * 32 + e) = w;
+        }
+      }
+    }
+  }
+
+  // ---- teardown ----------------------------------------------------------------------------------------------------
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---- host: tensor maps ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int get_encode_fn(EncodeTiledFn* out) {
+  static EncodeTiledFn cached = nullptr;
+  if (cached == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    HI_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+      set_error("cuTensorMapEncodeTiled is not available from this driver");
+      return HI_ERR_CUDA;
+    }
+    cached = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  *out = cached;
+  return HI_OK;
+}
+
+// 3-D map over [rows, heads, 128] 16-bit elements; box = {64 dims, box_heads, box_rows}, 128B swizzle.
+static int make_map(CUtensorMap* map, int dtype, const void* base, int64_t rows, int64_t heads, int64_t row_stride_elems,
+                    int box_heads, int box_rows) {
+  EncodeTiledFn encode = nullptr;
+  const int rc = get_encode_fn(&encode);
+  if (rc != HI_OK) return rc;
+  const cuuint64_t dims[3] = {static_cast<cuuint64_t>(kHeadDim), static_cast<cuuint64_t>(heads), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[2] = {static_cast<cuuint64_t>(kHeadDim) * 2, static_cast<cuuint64_t>(row_stride_elems) * 2};
+  const cuuint32_t box[3] = {64u, static_cast<cuuint32_t>(box_heads), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  const CUresult res = encode(map, dtype == HI_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                              const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (res != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld heads=%lld stride=%lld box=%d,%d)", (int)res,
+              (long long)rows, (long long)heads, (long long)row_stride_elems, box_heads, box_rows);
+    return HI_ERR_CUDA;
+  }
+  return HI_OK;
+}
+
+// Pool maps are reused by every layer call with the same base pointer; cache them.
+struct MapKey {
+  const void* base;
+  int64_t rows, heads;
+  int dtype, box_rows;
+  bool operator==(const MapKey& o) const {
+    return base == o.base && rows == o.rows && heads == o.heads && dtype == o.dtype && box_rows == o.box_rows;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    return std::hash<const void*>()(k.base) ^ (std::hash<int64_t>()(k.rows) * 31) ^ (std::hash<int64_t>()(k.heads) * 131) ^
+           (static_cast<size_t>(k.dtype) << 8) ^ (static_cast<size_t>(k.box_rows) << 16);
+  }
+};
+static std::mutex g_map_mu;
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_pool_maps;
+
+static int pool_map(CUtensorMap* out, int dtype, const void* base, int64_t n_slots, int heads, int block_size) {
+  const MapKey key{base, n_slots, heads, dtype, block_size};
+  std::lock_guard<std::mutex> lock(g_map_mu);
+  auto it = g_pool_maps.find(key);
+  if (it != g_pool_maps.end()) {
+    *out = it->second;
+    return HI_OK;
+  }
+  CUtensorMap m;
+  const int rc = make_map(&m, dtype, base, n_slots, heads, static_cast<int64_t>(heads) * kHeadDim, 1, block_size);
+  if (rc != HI_OK) return rc;
+  if (g_pool_maps.size() > 4096) g_pool_maps.clear();
+  g_pool_maps.emplace(key, m);
+  *out = m;
+  return HI_OK;
+}
+
+bool attn_tc_supported(const HiAttnArgs& args) {
+  const int group = args.n_kv_heads > 0 ? args.n_qo_heads / args.n_kv_heads : 0;
+  return (args.dtype == HI_F16 || args.dtype == HI_BF16) && args.head_dim == kHeadDim && group >= 1 && group <= kTileM &&
+         args.block_size >= 8 && args.block_size <= kTileN && (kTileN % args.block_size) == 0 &&
+         (args.q_row_stride % 8) == 0 && (args.out_row_stride % 8) == 0 && aligned_to(args.q, 16) &&
+         aligned_to(args.out, 16) && aligned_to(args.key_cache, 16) && aligned_to(args.value_cache, 16) &&
+         args.n_blocks > 0;
+}
+
+template <typename T, int NST>
+static int launch_tc_t(const HiAttnArgs& args, const TcArgs& a, const CUtensorMap& mq, const CUtensorMap& mk,
+                       const CUtensorMap& mv, cudaStream_t stream) {
+  using L = TcSmem<NST>;
+  static bool configured = false;
+  if (!configured) {
+    HI_CUDA(cudaFuncSetAttribute(paged_attn_tc_kernel<T, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamicBytes));
+    configured = true;
+  }
+  const int q_tiles = (args.max_q_len + a.tq - 1) / a.tq;
+  const dim3 grid(q_tiles, args.n_kv_heads, args.n_seqs);
+  timing_mark_start(stream);
+  paged_attn_tc_kernel<T, NST><<<grid, kTcThreads, L::kDynamicBytes, stream>>>(mq, mk, mv, a);
+  timing_mark_stop(stream);
+  note_launch();
+  HI_CUDA(cudaGetLastError());
+  return HI_OK;
+}
+
+int launch_attn_tc(const HiAttnArgs& args, cudaStream_t stream) {
+  if (!attn_tc_supported(args)) {
+    set_error("paged_attention: the tcgen05 path needs fp16/bf16, head_dim 128, block_size in {8,16,32,64,128} and 16-byte aligned rows");
+    return HI_ERR_UNSUPPORTED;
+  }
+  TcArgs a{};
+  a.out = args.out;
+  a.out_row_stride = args.out_row_stride;
+  a.q_cu = args.q_cu_seq_lens;
+  a.kv_cu = args.kv_cu_seq_lens;
+  a.block_tables = args.block_tables;
+  a.cu_blocks = args.cu_blocks_lens;
+  a.n_qo_heads = args.n_qo_heads;
+  a.n_kv_heads = args.n_kv_heads;
+  a.group = args.n_qo_heads / args.n_kv_heads;
+  a.block_size = args.block_size;
+  a.tq = kTileM / a.group;
+  a.scale_log2 = args.softmax_scale * 1.4426950408889634f;
+  {
+    const char* env = getenv("HI_TC_SERIALIZE");
+    a.serialize = (env != nullptr && env[0] == '1') ? 1 : 0;
+  }
+
+  CUtensorMap mq, mk, mv;
+  int rc = make_map(&mq, args.dtype, args.q, args.n_tokens, args.n_qo_heads, args.q_row_stride, a.group, a.tq);
+  if (rc != HI_OK) return rc;
+  const int64_t n_slots = args.n_blocks * args.block_size;
+  rc = pool_map(&mk, args.dtype, args.key_cache, n_slots, args.n_kv_heads, args.block_size);
+  if (rc != HI_OK) return rc;
+  rc = pool_map(&mv, args.dtype, args.value_cache, n_slots, args.n_kv_heads, args.block_size);
+  if (rc != HI_OK) return rc;
+
+  if (args.dtype == HI_BF16) return launch_tc_t<__nv_bfloat16, 1>(args, a, mq, mk, mv, stream);
+  return launch_tc_t<__half, 1>(args, a, mq, mk, mv, stream);
+}
+
+}  // namespace hi

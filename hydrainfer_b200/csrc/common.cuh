@@ -1,0 +1,134 @@
+// Shared host/device helpers for the hi_b200 C-ABI library (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/hi_b200.h"
+
+namespace hi {
+
+// ---- error plumbing -------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+void note_launch();          // counts kernels launched by the current API call
+void reset_launch_count();
+// bench hooks: record the armed event pair around the dominant kernel of the current call (no-ops when disarmed)
+void timing_mark_start(cudaStream_t stream);
+void timing_mark_stop(cudaStream_t stream);
+
+#define HI_CHECK_ARG(cond, ...)            \
+  do {                                     \
+    if (!(cond)) {                         \
+      ::hi::set_error(__VA_ARGS__);        \
+      return HI_ERR_INVALID_ARGUMENT;      \
+    }                                      \
+  } while (0)
+
+#define HI_CHECK_SUPPORTED(cond, ...)      \
+  do {                                     \
+    if (!(cond)) {                         \
+      ::hi::set_error(__VA_ARGS__);        \
+      return HI_ERR_UNSUPPORTED;           \
+    }                                      \
+  } while (0)
+
+#define HI_CUDA(call)                                                                              \
+  do {                                                                                             \
+    cudaError_t err__ = (call);                                                                    \
+    if (err__ != cudaSuccess) {                                                                    \
+      ::hi::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(err__)); \
+      return HI_ERR_CUDA;                                                                          \
+    }                                                                                              \
+  } while (0)
+
+inline int dtype_size(int dtype) {
+  switch (dtype) {
+    case HI_F32: return 4;
+    case HI_F16: return 2;
+    case HI_BF16: return 2;
+    default: return 0;
+  }
+}
+
+inline bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+// ---- device: element conversion ---------------------------------------------------------------------------
+template <typename T>
+struct Elem;
+
+template <>
+struct Elem<float> {
+  static constexpr int kBytes = 4;
+  __device__ static __forceinline__ float to_f32(float v) { return v; }
+  __device__ static __forceinline__ float from_f32(float v) { return v; }
+};
+template <>
+struct Elem<__half> {
+  static constexpr int kBytes = 2;
+  __device__ static __forceinline__ float to_f32(__half v) { return __half2float(v); }
+  __device__ static __forceinline__ __half from_f32(float v) { return __float2half_rn(v); }
+};
+template <>
+struct Elem<__nv_bfloat16> {
+  static constexpr int kBytes = 2;
+  __device__ static __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+  __device__ static __forceinline__ __nv_bfloat16 from_f32(float v) { return __float2bfloat16_rn(v); }
+};
+
+// Unpack one 32-bit word holding two 16-bit elements (low half = lower address).
+template <typename T>
+__device__ __forceinline__ void unpack2(uint32_t w, float& lo, float& hi);
+template <>
+__device__ __forceinline__ void unpack2<__nv_bfloat16>(uint32_t w, float& lo, float& hi) {
+  lo = __uint_as_float(w << 16);
+  hi = __uint_as_float(w & 0xffff0000u);
+}
+template <>
+__device__ __forceinline__ void unpack2<__half>(uint32_t w, float& lo, float& hi) {
+  const __half2 h = *reinterpret_cast<const __half2*>(&w);
+  const float2 f = __half22float2(h);
+  lo = f.x;
+  hi = f.y;
+}
+
+template <typename T>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi);
+template <>
+__device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+template <>
+__device__ __forceinline__ uint32_t pack2<__half>(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// Streaming 16-byte global load that does not pollute L1 (KV pages are read once per launch).
+__device__ __forceinline__ uint4 ldg_stream_16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint2 ldg_stream_8(const void* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+}  // namespace hi

@@ -1,0 +1,215 @@
+// KV-page migration: one gather kernel over (possibly peer-mapped) pools + cached CUDA-IPC mappings.
+//
+// Replaces csrc/data_transfer/block_migration.cpp of the reference: migrate_blocks (:194-245) issues
+// n_layers * n_tokens * n_blocks cudaMemcpyAsync calls (262 144 for a 4096-block LLaVA-7B request) and
+// re-opens the IPC handle on every call (:213-215).  Here the peer pool is mapped once per process and all
+// runs of a request move in ONE launch: the destination GPU pulls through NVLink with 128-bit loads and
+// writes its own HBM, the same direction the reference's receiver-side memcpy moves data.
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace hi {
+
+struct MigrateArgs {
+  const int32_t* src_blocks;
+  const int32_t* dst_blocks;
+  const char* src_pool;
+  char* dst_pool;
+  int64_t n;               // blocks to move
+  int64_t planes;          // n_layers * n_tokens
+  int64_t run_bytes;       // contiguous bytes of one (plane, block)
+  int64_t src_plane_bytes; // src n_blocks * run_bytes
+  int64_t dst_plane_bytes;
+  int64_t pieces_per_run;  // run_bytes / kPieceBytes (rounded up)
+  int64_t total_pieces;
+};
+
+constexpr int kMigrateThreads = 256;
+constexpr int kVecPerThread = 4;                                       // independent 16-B loads in flight per thread
+constexpr int64_t kPieceBytes = kMigrateThreads * kVecPerThread * 16;  // 16 KiB handled by a CTA per step
+
+// Persistent CTAs walk 16-KiB pieces of the (plane, block) runs.  A run is contiguous in both pools
+// (INDEX_6D of block_migration.cpp:26-27 with the three innermost indices 0), so every access is a
+// fully coalesced 128-bit vector; each thread keeps kVecPerThread loads in flight to cover NVLink latency.
+__global__ void __launch_bounds__(kMigrateThreads) migrate_gather_kernel(const MigrateArgs a) {
+  for (int64_t piece = blockIdx.x; piece < a.total_pieces; piece += gridDim.x) {
+    const int64_t run = piece / a.pieces_per_run;
+    const int64_t off = (piece - run * a.pieces_per_run) * kPieceBytes;
+    const int64_t plane = run / a.n;
+    const int64_t i = run - plane * a.n;
+    const int64_t sb = __ldg(a.src_blocks + i);
+    const int64_t db = __ldg(a.dst_blocks + i);
+    const char* __restrict__ src = a.src_pool + plane * a.src_plane_bytes + sb * a.run_bytes + off;
+    char* __restrict__ dst = a.dst_pool + plane * a.dst_plane_bytes + db * a.run_bytes + off;
+    const int64_t left = a.run_bytes - off;
+    const int n_vec = static_cast<int>((left < kPieceBytes ? left : kPieceBytes) >> 4);
+    uint4 v[kVecPerThread];
+#pragma unroll
+    for (int k = 0; k < kVecPerThread; ++k) {
+      const int idx = threadIdx.x + k * kMigrateThreads;
+      if (idx < n_vec) v[k] = ldg_stream_16(src + static_cast<int64_t>(idx) * 16);
+    }
+#pragma unroll
+    for (int k = 0; k < kVecPerThread; ++k) {
+      const int idx = threadIdx.x + k * kMigrateThreads;
+      if (idx < n_vec) *reinterpret_cast<uint4*>(dst + static_cast<int64_t>(idx) * 16) = v[k];
+    }
+  }
+}
+
+// ---- IPC mapping cache -------------------------------------------------------------------------------------------
+struct IpcEntry {
+  uint8_t handle[64];
+  int device;
+  void* base;
+};
+static std::mutex g_ipc_mu;
+static std::vector<IpcEntry> g_ipc_entries;
+
+}  // namespace hi
+
+extern "C" int hi_migrate_blocks(const int32_t* src_blocks, const int32_t* dst_blocks, int64_t n, const void* src_pool,
+                                 void* dst_pool, HiPoolGeom src, HiPoolGeom dst, int device, void* stream) {
+  using namespace hi;
+  reset_launch_count();
+  HI_CHECK_ARG(n >= 0, "migrate_blocks: negative block count");
+  if (n == 0) return HI_OK;
+  HI_CHECK_ARG(src_blocks && dst_blocks && src_pool && dst_pool, "migrate_blocks: null pointer");
+  HI_CHECK_ARG(src.n_layers == dst.n_layers && src.n_tokens == dst.n_tokens && src.run_bytes == dst.run_bytes,
+               "migrate_blocks: pools differ in more than n_blocks (layers %lld/%lld, tokens %lld/%lld, run bytes %lld/%lld)",
+               (long long)src.n_layers, (long long)dst.n_layers, (long long)src.n_tokens, (long long)dst.n_tokens,
+               (long long)src.run_bytes, (long long)dst.run_bytes);
+  HI_CHECK_ARG(src.run_bytes > 0 && src.run_bytes % 16 == 0, "migrate_blocks: run of %lld bytes is not a multiple of 16",
+               (long long)src.run_bytes);
+  HI_CHECK_ARG(aligned_to(src_pool, 16) && aligned_to(dst_pool, 16), "migrate_blocks: pools must be 16-byte aligned");
+  HI_CUDA(cudaSetDevice(device));
+
+  MigrateArgs a{};
+  a.src_blocks = src_blocks;
+  a.dst_blocks = dst_blocks;
+  a.src_pool = static_cast<const char*>(src_pool);
+  a.dst_pool = static_cast<char*>(dst_pool);
+  a.n = n;
+  a.planes = src.n_layers * src.n_tokens;
+  a.run_bytes = src.run_bytes;
+  a.src_plane_bytes = src.n_blocks * src.run_bytes;
+  a.dst_plane_bytes = dst.n_blocks * dst.run_bytes;
+  a.pieces_per_run = (a.run_bytes + kPieceBytes - 1) / kPieceBytes;
+  a.total_pieces = a.planes * n * a.pieces_per_run;
+
+  static int sm_count = 0;
+  if (sm_count == 0) HI_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+  // 8 resident CTAs of 256 threads per SM = 128 KiB of loads in flight per SM.
+  int64_t grid = static_cast<int64_t>(sm_count) * 8;
+  if (grid > a.total_pieces) grid = a.total_pieces;
+  migrate_gather_kernel<<<static_cast<unsigned>(grid), kMigrateThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  note_launch();
+  HI_CUDA(cudaGetLastError());
+  return HI_OK;
+}
+
+extern "C" int hi_ipc_get_handle(const void* ptr, uint8_t handle_out[64], int64_t* offset_out, int device) {
+  using namespace hi;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  HI_CHECK_ARG(ptr && handle_out && offset_out, "ipc_get_handle: null pointer");
+  HI_CUDA(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  HI_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(ptr)));
+  std::memcpy(handle_out, &h, 64);
+  // The handle names the whole allocation; recover where ptr sits inside it.
+  void* base = nullptr;
+  size_t size = 0;
+  typedef int (*GetRangeFn)(void**, size_t*, void*);  // cuMemGetAddressRange(CUdeviceptr*, size_t*, CUdeviceptr)
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  HI_CUDA(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres));
+  if (fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+    set_error("ipc_get_handle: cuMemGetAddressRange not available");
+    return HI_ERR_CUDA;
+  }
+  const int rc = reinterpret_cast<GetRangeFn>(fn)(&base, &size, const_cast<void*>(ptr));
+  if (rc != 0) {
+    set_error("ipc_get_handle: cuMemGetAddressRange failed with CUresult %d", rc);
+    return HI_ERR_CUDA;
+  }
+  *offset_out = static_cast<const char*>(ptr) - static_cast<const char*>(base);
+  return HI_OK;
+}
+
+extern "C" int hi_ipc_open_handle(const uint8_t handle[64], int64_t offset, int device, void** ptr_out) {
+  using namespace hi;
+  HI_CHECK_ARG(handle && ptr_out && offset >= 0, "ipc_open_handle: bad argument");
+  std::lock_guard<std::mutex> lock(g_ipc_mu);
+  for (const IpcEntry& e : g_ipc_entries) {
+    if (e.device == device && std::memcmp(e.handle, handle, 64) == 0) {
+      *ptr_out = static_cast<char*>(e.base) + offset;
+      return HI_OK;
+    }
+  }
+  HI_CUDA(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, 64);
+  void* base = nullptr;
+  const cudaError_t err = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+  if (err == cudaErrorPeerAccessUnsupported) {
+    (void)cudaGetLastError();
+    set_error("ipc_open_handle: peer access to the exporting GPU is unsupported from device %d", device);
+    return HI_ERR_PEER_UNSUPPORTED;
+  }
+  if (err != cudaSuccess) {
+    (void)cudaGetLastError();
+    set_error("cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(err));
+    return HI_ERR_CUDA;
+  }
+  IpcEntry e;
+  std::memcpy(e.handle, handle, 64);
+  e.device = device;
+  e.base = base;
+  g_ipc_entries.push_back(e);
+  *ptr_out = static_cast<char*>(base) + offset;
+  return HI_OK;
+}
+
+extern "C" int hi_ipc_close_all(void) {
+  using namespace hi;
+  std::lock_guard<std::mutex> lock(g_ipc_mu);
+  int rc = HI_OK;
+  for (const IpcEntry& e : g_ipc_entries) {
+    if (cudaSetDevice(e.device) != cudaSuccess || cudaIpcCloseMemHandle(e.base) != cudaSuccess) {
+      (void)cudaGetLastError();
+      set_error("ipc_close_all: cudaIpcCloseMemHandle failed");
+      rc = HI_ERR_CUDA;
+    }
+  }
+  g_ipc_entries.clear();
+  return rc;
+}
+
+extern "C" int hi_peer_copy(void* dst, int dst_device, const void* src, int src_device, int64_t bytes, void* stream) {
+  using namespace hi;
+  HI_CHECK_ARG(dst && src && bytes >= 0, "peer_copy: bad argument");
+  HI_CUDA(cudaMemcpyPeerAsync(dst, dst_device, src, src_device, static_cast<size_t>(bytes), static_cast<cudaStream_t>(stream)));
+  return HI_OK;
+}
+
+extern "C" int hi_enable_peer_access(int device, int peer_device) {
+  using namespace hi;
+  if (device == peer_device) return HI_OK;
+  int can = 0;
+  HI_CUDA(cudaDeviceCanAccessPeer(&can, device, peer_device));
+  if (!can) {
+    set_error("enable_peer_access: device %d cannot access device %d", device, peer_device);
+    return HI_ERR_PEER_UNSUPPORTED;
+  }
+  HI_CUDA(cudaSetDevice(device));
+  const cudaError_t err = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (err == cudaErrorPeerAccessAlreadyEnabled) {
+    (void)cudaGetLastError();
+    return HI_OK;
+  }
+  HI_CUDA(err);
+  return HI_OK;
+}

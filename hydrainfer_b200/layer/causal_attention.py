@@ -1,0 +1,172 @@
+"""Paged causal grouped-query attention layer with the reference's interface
+(hydrainfer/layer/causal_attention.py): AttentionParameters (:31-68), AttentionParametersBuilder (:110-210),
+CausalGroupedQueryPageAttentionConfig / Output (:213-222) and CausalGroupedQueryPageAttention.forward (:394-406).
+
+The reference dispatches through a chain FlashInfer -> FlashAttention(csrc) -> Torch (:385-392).  Here there is one
+handler, B200CausalGroupedQueryPageAttentionHandler, backed by the sm_100a kernels; it keeps the handler protocol
+(`next_handler`, `forward(query, attention_params)`), so it can also be inserted at the head of the reference's own
+chain.  CPU tensors are passed to `next_handler` if one is linked and rejected otherwise: this
+package ships no CPU implementation (the fp32 restatement lives in oracle/ and is test infrastructure only).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+from torch import Tensor, nn
+
+from .._C.kernel.flash_attn import mha_varlen_fwd
+from ..memory.kv_cache import KVCache
+
+
+@dataclass
+class AttentionParameters:
+    """Per-step attention metadata; one instance per layer, all sharing the same int32 device tensors."""
+    kv_cache: KVCache
+    q_cu_seq_lens: Tensor = None           # int32 [n_seqs + 1]  cumulative new tokens
+    kv_cu_seq_lens: Tensor = None          # int32 [n_seqs + 1]  cumulative cached + new tokens
+    paged_kv_last_page_len: Tensor = None  # int32 [n_seqs]      tokens in each sequence's last block
+    new_cache_slots: Tensor = None         # int32 [n_tokens]    physical slot of every new token
+    block_tables: Tensor = None            # int32 [sum blocks]  flattened per-sequence block ids
+    cu_blocks_lens: Tensor = None          # int32 [n_seqs + 1]
+    num_sequences: int = None
+    all_sequences_decode: bool = False
+    q_max_seq_len: int = 128
+    kv_max_seq_len: int = 128
+    flash_infer_handler: Optional[object] = None  # kept for signature compatibility; unused
+
+    _TENSOR_FIELDS = ("q_cu_seq_lens", "kv_cu_seq_lens", "paged_kv_last_page_len", "new_cache_slots", "block_tables", "cu_blocks_lens")
+
+    def to(self, device: torch.device) -> None:
+        for name in self._TENSOR_FIELDS:
+            t = getattr(self, name)
+            if t is not None:
+                setattr(self, name, t.to(device))
+
+
+class AttentionParametersBuilder:
+    """add_request() per sequence, add_kv_cache() per layer, then build_attention_parameters()
+    (causal_attention.py:110-210).  The six metadata lists are uploaded ONCE as a single pinned int32 buffer and
+    sliced on the device (the reference does six torch.tensor(list) H2D copies, :163-168)."""
+
+    def __init__(self, num_qo_heads: int, num_kv_heads: int, head_dim: int, block_size: int, device: torch.device,
+                 flash_infer_batch_prefill_handler=None, flash_infer_batch_decode_handler=None):
+        self.num_qo_heads = num_qo_heads
+        self.num_kv_heads = num_kv_heads
+        self.head_dim = head_dim
+        self.block_size = block_size
+        self.device = torch.device(device)
+        self.kv_caches: list[KVCache] = []
+        self.q_cu_seq_lens: list[int] = [0]
+        self.kv_cu_seq_lens: list[int] = [0]
+        self.paged_kv_last_page_len: list[int] = []
+        self.new_cache_slots: list[int] = []
+        self.block_tables: list[int] = []
+        self.cu_blocks_lens: list[int] = [0]
+        self.num_sequences = 0
+        self.all_sequences_decode = True
+        self.q_max_seq_len = 0
+        self.kv_max_seq_len = 0
+
+    def add_request(self, q_seq_len: int, kv_seq_len: int, new_cache_slots: list[int], block_table: list[int]) -> None:
+        self.q_cu_seq_lens.append(self.q_cu_seq_lens[-1] + q_seq_len)
+        self.kv_cu_seq_lens.append(self.kv_cu_seq_lens[-1] + kv_seq_len)
+        self.paged_kv_last_page_len.append((kv_seq_len + self.block_size - 1) % self.block_size + 1)
+        self.new_cache_slots += new_cache_slots
+        self.block_tables += block_table
+        self.cu_blocks_lens.append(self.cu_blocks_lens[-1] + len(block_table))
+        self.num_sequences += 1
+        self.all_sequences_decode = self.all_sequences_decode and q_seq_len == 1
+        self.q_max_seq_len = max(self.q_max_seq_len, q_seq_len)
+        self.kv_max_seq_len = max(self.kv_max_seq_len, kv_seq_len)
+
+    def add_kv_cache(self, kv_cache: KVCache) -> None:
+        self.kv_caches.append(kv_cache)
+
+    def build_attention_parameters(self) -> list[AttentionParameters]:
+        parts = [self.q_cu_seq_lens, self.kv_cu_seq_lens, self.paged_kv_last_page_len, self.new_cache_slots,
+                 self.block_tables, self.cu_blocks_lens]
+        # each slice starts on a 16-byte boundary (4 int32) so the kernels' vector paths never see a misaligned table
+        offsets, flat = [], []
+        for part in parts:
+            offsets.append(len(flat))
+            flat += part
+            flat += [0] * (-len(flat) % 4)
+        host = torch.tensor(flat, dtype=torch.int32)
+        if self.device.type == "cuda":
+            host = host.pin_memory()
+        dev = host.to(self.device, non_blocking=True)
+        views = [dev[o:o + len(part)] for o, part in zip(offsets, parts)]
+        return [AttentionParameters(
+            kv_cache=kv_cache,
+            q_cu_seq_lens=views[0], kv_cu_seq_lens=views[1], paged_kv_last_page_len=views[2], new_cache_slots=views[3],
+            block_tables=views[4], cu_blocks_lens=views[5],
+            num_sequences=self.num_sequences, all_sequences_decode=self.all_sequences_decode,
+            q_max_seq_len=self.q_max_seq_len, kv_max_seq_len=self.kv_max_seq_len, flash_infer_handler=None,
+        ) for kv_cache in self.kv_caches]
+
+
+@dataclass
+class CausalGroupedQueryPageAttentionConfig:
+    n_qo_heads: int
+    n_kv_heads: int
+    head_dim: int
+
+
+@dataclass
+class CausalGroupedQueryPageAttentionOutput:
+    o: Tensor
+
+
+class B200CausalGroupedQueryPageAttentionHandler(nn.Module):
+    """Handler backed by hi_paged_attention.  query [n_tokens, n_qo_heads, head_dim] (rows may be strided),
+    KV already appended; returns o [n_tokens, n_qo_heads * head_dim] in the query dtype."""
+
+    def __init__(self, config: CausalGroupedQueryPageAttentionConfig):
+        super().__init__()
+        assert config.n_qo_heads % config.n_kv_heads == 0, f"n_qo_heads {config.n_qo_heads} is not divisible by n_kv_heads {config.n_kv_heads}"
+        self.n_qo_heads = config.n_qo_heads
+        self.n_kv_heads = config.n_kv_heads
+        self.head_dim = config.head_dim
+        self.next_handler: Optional[nn.Module] = None
+        self.path = 0  # HiAttnPath: 0 auto, 1 split-KV CUDA-core kernel, 2 tcgen05 tile kernel (tests force each)
+
+    def forward(self, query: Tensor, attention_params: AttentionParameters) -> CausalGroupedQueryPageAttentionOutput:
+        if query.device.type != "cuda":
+            if self.next_handler is not None:
+                return self.next_handler(query, attention_params)
+            raise RuntimeError("hydrainfer_b200: attention needs CUDA tensors; no CPU handler is linked")
+        key_cache, value_cache = attention_params.kv_cache.get_kv_cache()
+        output = torch.empty((query.shape[0], self.n_qo_heads, self.head_dim), dtype=query.dtype, device=query.device)
+        mha_varlen_fwd(
+            output, query, key_cache, value_cache,
+            attention_params.q_cu_seq_lens, attention_params.kv_cu_seq_lens,
+            attention_params.block_tables, attention_params.cu_blocks_lens,
+            None, attention_params.q_max_seq_len, attention_params.kv_max_seq_len,
+            1.0 / math.sqrt(self.head_dim), 0, -1, 0, 0, self.path,
+        )
+        return CausalGroupedQueryPageAttentionOutput(o=output.view(-1, self.n_qo_heads * self.head_dim))
+
+
+class CausalGroupedQueryPageAttention(nn.Module):
+    """forward(query [T, Hq*d], key [T, Hkv*d], value [T, Hkv*d], attention_params) -> Output(o [T, Hq*d]):
+    view, append K/V to the paged cache, attend (causal_attention.py:394-406)."""
+
+    def __init__(self, config: CausalGroupedQueryPageAttentionConfig):
+        super().__init__()
+        assert config.n_qo_heads % config.n_kv_heads == 0, f"n_qo_heads {config.n_qo_heads} is not divisible by n_kv_heads {config.n_kv_heads}"
+        self.n_qo_heads = config.n_qo_heads
+        self.n_kv_heads = config.n_kv_heads
+        self.head_dim = config.head_dim
+        self.handlers = [B200CausalGroupedQueryPageAttentionHandler(config)]
+        self.handler = self.handlers[0]
+
+    def forward(self, query: Tensor, key: Tensor, value: Tensor, attention_params: AttentionParameters) -> CausalGroupedQueryPageAttentionOutput:
+        n_tokens = query.shape[0]
+        query = query.view(n_tokens, self.n_qo_heads, self.head_dim)
+        key = key.view(n_tokens, self.n_kv_heads, self.head_dim)
+        value = value.view(n_tokens, self.n_kv_heads, self.head_dim)
+        attention_params.kv_cache.set_kv_cache(attention_params.new_cache_slots, key, value)
+        return self.handler(query, attention_params)

@@ -1,0 +1,176 @@
+/*
+ * hi_b200.h — C ABI of the B200-native paged-KV attention hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Each entry point names the
+ * reference interface it replaces (paths relative to the hydrainfer repository).  All functions
+ *   - return 0 on success or a negative HiStatus; hi_last_error() gives a human-readable message
+ *     for the calling thread (the reference instead aborts the process: glog CHECK in
+ *     csrc/kernel/kv_cache_kernels/kv_cache_kernels.cu:67-68, printf+exit in
+ *     csrc/data_transfer/block_migration.cpp:9-15);
+ *   - launch asynchronously on the cudaStream_t passed as `stream` (an opaque pointer here so the header
+ *     needs no CUDA include); the reference uses at::cuda::getCurrentCUDAStream()
+ *     (kv_cache_kernels.cu:83, flash_api.cpp:353, block_migration.cpp:201) — the host shim passes that;
+ *   - never allocate device memory: scratch comes from the caller-owned workspace.
+ *
+ * Device pointers are marked [dev]; everything else is host memory.
+ */
+#ifndef HI_B200_H_
+#define HI_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HI_B200_ABI_VERSION 1
+
+typedef enum HiStatus {
+  HI_OK = 0,
+  HI_ERR_INVALID_ARGUMENT = -1, /* layout / shape precondition violated */
+  HI_ERR_UNSUPPORTED = -2,      /* dtype / head_dim / block size outside what the kernels cover */
+  HI_ERR_CUDA = -3,             /* a CUDA runtime or driver call failed */
+  HI_ERR_WORKSPACE = -4,        /* workspace too small; see hi_attention_workspace_bytes */
+  HI_ERR_PEER_UNSUPPORTED = -5  /* peer access to the exporting GPU is not possible */
+} HiStatus;
+
+typedef enum HiDtype { HI_F32 = 0, HI_F16 = 1, HI_BF16 = 2 } HiDtype;
+
+/* Which attention kernel hi_paged_attention should run. AUTO is the production choice. */
+typedef enum HiAttnPath {
+  HI_ATTN_AUTO = 0,
+  HI_ATTN_SIMT = 1,   /* split-KV CUDA-core kernel (decode rows; also the generic any-shape path) */
+  HI_ATTN_TCGEN05 = 2 /* tcgen05/TMEM tile kernel (prefill, chunked prefill, GQA-packed decode) */
+} HiAttnPath;
+
+const char* hi_last_error(void);
+int hi_abi_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * KV append — replaces set_kv_cache (csrc/kernel/kv_cache_kernels/kv_cache_kernels.cu:60-95) and
+ * set_image_cache (csrc/kernel/cache_kernels/cache_kernels.cu:55-83).
+ *
+ *   cache[slot / block_size, slot % block_size, :, :] = rows[t, :, :]      (bit-exact copy)
+ *
+ * Caches are contiguous [n_blocks, block_size, n_heads, head_dim], so the destination of token t is
+ * the `row_elems`-long run starting at slot_ids[t] * row_elems.  Source rows are contiguous over
+ * (n_heads, head_dim) but may have a larger row stride (a slice of a fused qkv projection,
+ * kv_cache_kernels.cu:75-76).  hi_set_kv_cache scatters K and V in ONE launch.
+ * ------------------------------------------------------------------------------------------- */
+int hi_set_kv_cache(const int32_t* slot_ids /*[dev] [n_tokens]*/,
+                    const void* keys /*[dev]*/, const void* values /*[dev]*/,
+                    void* key_cache /*[dev]*/, void* value_cache /*[dev]*/,
+                    int64_t n_tokens, int64_t row_elems /* n_kv_heads*head_dim */,
+                    int64_t key_row_stride /*elements*/, int64_t value_row_stride /*elements*/,
+                    int dtype /*HiDtype*/, int device, void* stream);
+
+int hi_set_image_cache(const int32_t* slot_ids /*[dev] [n_tokens]*/,
+                       const void* image_tokens /*[dev]*/, void* image_cache /*[dev]*/,
+                       int64_t n_tokens, int64_t row_elems /* n_heads*head_dim */,
+                       int64_t token_row_stride /*elements*/,
+                       int dtype, int device, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Paged causal GQA attention — replaces mha_varlen_fwd (csrc/kernel/flash_attn/flash_api.cpp:216-355)
+ * as called by FlashAttentionCausalGroupedQueryPageAttentionHandler
+ * (hydrainfer/layer/causal_attention.py:262-294), the flashinfer run() of :235-249, and computes what
+ * TorchCausalGroupedQueryPageAttentionHandler (:307-374) computes:
+ *
+ *   for sequence b, query row i (0-based among its q_b new tokens), key j of its L_b cached tokens:
+ *       visible(i, j)  <=>  j <= i + L_b - q_b            (bottom-right aligned causal mask, :339-342)
+ *       o[i, h] = softmax_j(scale * q[i, h] . k[j, h / group]) @ v[:, h / group]
+ *
+ * KV has already been appended (causal_attention.py:402-403); L_b includes the new tokens.
+ * The metadata arrays are the int32 device tensors of AttentionParameters (:31-68):
+ * block_tables is the flattened CSR of per-sequence block ids, cu_blocks_lens its row pointer.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct HiAttnArgs {
+  /* tensors */
+  const void* q;             /* [dev] [n_tokens, n_qo_heads, head_dim], head stride == head_dim */
+  void* out;                 /* [dev] same shape; written in place like mha_varlen_fwd's `out` */
+  const void* key_cache;     /* [dev] [n_blocks, block_size, n_kv_heads, head_dim] contiguous */
+  const void* value_cache;   /* [dev] same geometry */
+  int64_t q_row_stride;      /* elements between consecutive tokens of q */
+  int64_t out_row_stride;    /* elements between consecutive tokens of out */
+  /* metadata (AttentionParameters) */
+  const int32_t* q_cu_seq_lens;  /* [dev] [n_seqs + 1] */
+  const int32_t* kv_cu_seq_lens; /* [dev] [n_seqs + 1] */
+  const int32_t* block_tables;   /* [dev] [sum ceil(L_b / block_size)] */
+  const int32_t* cu_blocks_lens; /* [dev] [n_seqs + 1] */
+  int32_t n_seqs;
+  int32_t n_tokens;
+  int32_t max_q_len;         /* AttentionParameters.q_max_seq_len */
+  int32_t max_kv_len;        /* AttentionParameters.kv_max_seq_len */
+  /* geometry */
+  int32_t n_qo_heads, n_kv_heads, head_dim, block_size;
+  int64_t n_blocks;          /* pool blocks (bounds the TMA tensor map) */
+  int32_t dtype;             /* HiDtype of q/out/caches */
+  float softmax_scale;       /* 1/sqrt(head_dim) in the reference */
+  /* scratch + control */
+  void* workspace;           /* [dev] >= hi_attention_workspace_bytes(...) bytes, 256-B aligned */
+  int64_t workspace_bytes;
+  int32_t path;              /* HiAttnPath */
+  int32_t device;
+  int32_t reserved[4];
+} HiAttnArgs;
+
+/* Upper bound of the scratch hi_paged_attention needs for a batch with these extents (split-KV partials). */
+int64_t hi_attention_workspace_bytes(int32_t n_tokens, int32_t n_qo_heads, int32_t head_dim, int32_t max_kv_len);
+
+int hi_paged_attention(const HiAttnArgs* args, void* stream);
+
+/* Number of kernels the last API call on this thread launched (bench bookkeeping). */
+int hi_last_launch_count(void);
+
+/* Measurement hooks (bench.py's roofline leg).  Events live in this library's CUDA runtime instance.
+ * hi_set_kernel_timing_events(start, stop): the NEXT hi_paged_attention call on this thread records `start`
+ * immediately before and `stop` immediately after its dominant kernel (the split-KV / tile kernel, excluding the
+ * split-merge kernel) on the launch stream; pass NULLs to disarm.  The pair is consumed by that call. */
+int hi_event_create(void** event_out);
+int hi_event_destroy(void* event);
+int hi_event_record(void* event, void* stream);
+int hi_event_elapsed_ms(void* start, void* stop, float* ms_out); /* synchronizes on `stop` */
+int hi_set_kernel_timing_events(void* start, void* stop);
+
+/* ---------------------------------------------------------------------------------------------
+ * KV-page migration — replaces csrc/data_transfer/block_migration.cpp.
+ *
+ * Pools are contiguous [n_layers, n_tokens, n_blocks, block_size, n_heads, head_size]
+ * (hydrainfer/memory/token_cache_manger.py:65).  For every (layer, kv, i) the run of
+ * run_bytes = block_size*n_heads*head_size*itemsize bytes of src block src_blocks[i] is copied to dst block
+ * dst_blocks[i] (block_migration.cpp:222-244); pools may differ in n_blocks only.
+ * The reference issues n_layers*n_tokens*n cudaMemcpyAsync calls; this is ONE gather kernel that reads
+ * the source through its (peer-mapped) pointer and writes local memory.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct HiPoolGeom {
+  int64_t n_layers, n_tokens, n_blocks, run_bytes;
+} HiPoolGeom;
+
+int hi_migrate_blocks(const int32_t* src_blocks /*[dev] [n]*/, const int32_t* dst_blocks /*[dev] [n]*/,
+                      int64_t n, const void* src_pool /*[dev] local or peer-mapped*/, void* dst_pool /*[dev]*/,
+                      HiPoolGeom src, HiPoolGeom dst, int device, void* stream);
+
+/* get_ipc_mem_handle (block_migration.cpp:55-59).  handle_out receives the 64 bytes of
+ * cudaIpcMemHandle_t of the ALLOCATION containing ptr; *offset_out the byte offset of ptr inside it
+ * (the reference silently assumes 0). */
+int hi_ipc_get_handle(const void* ptr /*[dev]*/, uint8_t handle_out[64], int64_t* offset_out, int device);
+
+/* register_ipc_mem_handle (block_migration.cpp:69-80) + the per-call cudaIpcOpenMemHandle of :213-215,
+ * cached per process: the same handle is mapped once.  *ptr_out = mapped base + offset. */
+int hi_ipc_open_handle(const uint8_t handle[64], int64_t offset, int device, void** ptr_out);
+
+/* Unmap every cached peer mapping (the reference never closes them). */
+int hi_ipc_close_all(void);
+
+/* cudaDeviceEnablePeerAccess(peer_device) on `device`, idempotent.  Needed only when source and destination pools
+ * live in the SAME process on different GPUs (IPC mappings enable peer access lazily by themselves). */
+int hi_enable_peer_access(int device, int peer_device);
+
+/* cudaMemcpyPeerAsync of one contiguous range — the NVLink roofline probe used by bench/tests. */
+int hi_peer_copy(void* dst, int dst_device, const void* src, int src_device, int64_t bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HI_B200_H_ */

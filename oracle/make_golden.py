@@ -1,0 +1,176 @@
+"""Generates tests/golden/*.npz by running the REAL reference (imported from /root/reference) on seeded inputs, and
+checks oracle/paged_kv_oracle.py against it on the way.  Run in the build container only:
+
+    python oracle/make_golden.py            # writes fixtures, prints the oracle-vs-reference report
+
+The reference's Python torch path runs on CPU once four plotting modules are stubbed (hydrainfer/utils/statistic.py:2-7
+imports matplotlib / seaborn, which this image lacks; nothing on the path uses them).  Functions exercised:
+  CausalGroupedQueryPageAttention.forward            hydrainfer/layer/causal_attention.py:394-406
+    -> KVCache.set_kv_cache (Python fallback)        hydrainfer/memory/kv_cache.py:44-50
+    -> TorchCausalGroupedQueryPageAttentionHandler   hydrainfer/layer/causal_attention.py:307-374
+  AttentionParametersBuilder                         hydrainfer/layer/causal_attention.py:110-210
+  TokenCache.set_caches (CPU path)                   hydrainfer/memory/token_cache.py:53-56
+  BlockAllocator                                     hydrainfer/memory/block_allocator.py:11-39
+  TokenCacheBlockManager.v2p                         hydrainfer/memory/token_cache_manger.py:126-133
+"""
+from __future__ import annotations
+
+import sys
+import types
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+GOLDEN = ROOT / "tests" / "golden"
+sys.path.insert(0, str(ROOT))
+
+from oracle import paged_kv_oracle as oracle  # noqa: E402
+from hydrainfer_b200.workloads import make_batch  # noqa: E402
+
+
+def import_reference():
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.colors", "seaborn"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["matplotlib.colors"].LogNorm = object
+    sys.path.insert(0, "/root/reference")
+    import hydrainfer.layer.causal_attention as ca
+    import hydrainfer.memory as mem
+    return ca, mem
+
+
+def to_np(t: torch.Tensor) -> np.ndarray:
+    if t.dtype in (torch.bfloat16, torch.float16):
+        return t.contiguous().view(torch.int16).numpy()
+    return t.contiguous().numpy()
+
+
+DTYPE_NAMES = {torch.float32: "float32", torch.float16: "float16", torch.bfloat16: "bfloat16"}
+
+# (name, seq_lens [(q, kv)], Hq, Hkv, d, block_size, dtype, fused_qkv)
+ATTENTION_CASES = [
+    # cfg-1 flavour: MHA fp32 decode-only, ragged context lengths
+    ("mha_fp32_decode", [(1, 1), (1, 16), (1, 17), (1, 100)], 4, 4, 64, 16, torch.float32, False),
+    # reference test grid (tests/layer/test_attention.py:42) scaled down: decode + square prefill + chunked prefill
+    ("gqa_bf16_mixed", [(1, 37), (15, 15), (21, 50), (1, 130)], 8, 2, 128, 16, torch.bfloat16, False),
+    # Qwen2-VL-7B head geometry (28 q heads, 4 kv heads): group size 7, q/k/v are slices of a fused qkv tensor
+    ("qwen_gqa7_bf16_fused", [(1, 40), (9, 33), (1, 16)], 28, 4, 128, 16, torch.bfloat16, True),
+    ("mha_fp16_prefill", [(33, 33), (5, 70)], 4, 4, 128, 16, torch.float16, False),
+    ("mqa_fp16_d256", [(1, 20), (7, 19)], 4, 1, 256, 16, torch.float16, False),
+    ("gqa_bf16_d64_bs8", [(1, 9), (12, 30)], 4, 2, 64, 8, torch.bfloat16, False),
+]
+
+
+def run_reference_layer(ca, mem, batch):
+    """Drive the reference layer exactly as its engine does: builder -> AttentionParameters -> layer.forward."""
+    device = torch.device("cpu")
+    kc, vc = batch.clone_caches()
+    builder = ca.AttentionParametersBuilder(batch.n_qo_heads, batch.n_kv_heads, batch.head_dim, batch.block_size, device)
+    for q_len, kv_len, slots, table in batch.requests():
+        builder.add_request(q_len, kv_len, slots, table)
+    builder.add_kv_cache(mem.KVCache(kc, vc))
+    params = builder.build_attention_parameters()[0]
+    layer = ca.CausalGroupedQueryPageAttention(ca.CausalGroupedQueryPageAttentionConfig(batch.n_qo_heads, batch.n_kv_heads, batch.head_dim))
+    with torch.inference_mode():
+        out = layer(batch.query, batch.key, batch.value, params).o
+    return out, kc, vc, params
+
+
+def main() -> None:
+    torch.manual_seed(0)
+    ca, mem = import_reference()
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    report = []
+
+    for idx, (name, seq_lens, hq, hkv, d, bs, dtype, fused) in enumerate(ATTENTION_CASES):
+        batch = make_batch(seq_lens, hq, hkv, d, bs, dtype=dtype, seed=100 + idx, fused_qkv=fused)
+        ref_out, ref_kc, ref_vc, params = run_reference_layer(ca, mem, batch)
+
+        # oracle on the same inputs
+        kc, vc = batch.clone_caches()
+        meta = oracle.build_metadata(batch.requests(), bs)
+        out = oracle.attention_layer_forward(batch.query, batch.key, batch.value, kc, vc,
+                                             torch.tensor(meta.new_cache_slots, dtype=torch.int32), meta.q_cu_seq_lens,
+                                             meta.kv_cu_seq_lens, torch.tensor(meta.block_tables, dtype=torch.int32),
+                                             meta.cu_blocks_lens, hq, hkv, d)
+        assert torch.equal(kc, ref_kc) and torch.equal(vc, ref_vc), f"{name}: oracle KV append differs from the reference"
+        assert torch.equal(out, ref_out), f"{name}: oracle attention differs from the reference"
+        for field in ("q_cu_seq_lens", "kv_cu_seq_lens", "paged_kv_last_page_len", "new_cache_slots", "block_tables", "cu_blocks_lens"):
+            assert getattr(params, field).tolist() == getattr(meta, field), f"{name}: metadata {field} differs"
+        assert params.num_sequences == meta.num_sequences and params.all_sequences_decode == meta.all_sequences_decode
+        assert params.q_max_seq_len == meta.q_max_seq_len and params.kv_max_seq_len == meta.kv_max_seq_len
+        fp32 = oracle.paged_attention_fp32(batch.query.view(-1, hq, d), kc, vc, meta.q_cu_seq_lens, meta.kv_cu_seq_lens,
+                                           torch.tensor(meta.block_tables, dtype=torch.int32), meta.cu_blocks_lens, hq, hkv, d)
+        report.append((name, float((ref_out.float() - fp32).abs().max())))
+
+        # touched-slot view of the caches keeps the fixture small: rows of the blocks this batch owns, after the append
+        blocks = torch.tensor(sorted(set(batch.block_tables)), dtype=torch.long)
+        np.savez_compressed(
+            GOLDEN / f"attn_{name}.npz",
+            dtype=DTYPE_NAMES[dtype], seq_lens=np.array(seq_lens, dtype=np.int64), geometry=np.array([hq, hkv, d, bs, batch.n_blocks]),
+            seed=100 + idx, fused_qkv=int(fused),
+            query=to_np(batch.query), key=to_np(batch.key), value=to_np(batch.value),
+            key_cache=to_np(batch.key_cache), value_cache=to_np(batch.value_cache),
+            q_cu_seq_lens=np.array(meta.q_cu_seq_lens), kv_cu_seq_lens=np.array(meta.kv_cu_seq_lens),
+            paged_kv_last_page_len=np.array(meta.paged_kv_last_page_len), new_cache_slots=np.array(meta.new_cache_slots),
+            block_tables=np.array(meta.block_tables), cu_blocks_lens=np.array(meta.cu_blocks_lens),
+            owned_blocks=blocks.numpy(), ref_key_cache_owned=to_np(ref_kc[blocks]), ref_value_cache_owned=to_np(ref_vc[blocks]),
+            ref_out=to_np(ref_out), ref_fp32=fp32.numpy())
+
+    # ---- set_image_cache via the reference's TokenCache CPU path ------------------------------------------------
+    g = torch.Generator().manual_seed(7)
+    n_blocks, bs, heads, d = 3, 576, 2, 64
+    cache = torch.randn(n_blocks, bs, heads, d, generator=g).to(torch.float16)
+    tokens = torch.randn(40, heads, d, generator=g).to(torch.float16)
+    slots = torch.randperm(n_blocks * bs, generator=g)[:40].to(torch.int32)
+    ref_cache = cache.clone()
+    mem.TokenCache([ref_cache]).set_caches(slots, [tokens])
+    mine = cache.clone()
+    oracle.set_image_cache(slots, tokens, mine)
+    assert torch.equal(mine, ref_cache), "oracle set_image_cache differs from the reference"
+    touched = torch.unique(slots.long() // bs)
+    np.savez_compressed(GOLDEN / "image_cache.npz", geometry=np.array([n_blocks, bs, heads, d]), slots=slots.numpy(),
+                        tokens=to_np(tokens), cache_seed=7, ref_rows=to_np(ref_cache.view(-1, heads, d)[slots.long()]),
+                        ref_checksum=np.array([int(ref_cache.view(torch.int16).to(torch.int64).sum())]),
+                        cache=to_np(cache), touched_blocks=touched.numpy())
+
+    # ---- allocator + v2p known answers -----------------------------------------------------------------------------
+    trace = []
+    ref_alloc, my_alloc = mem.BlockAllocator(40), oracle.BlockAllocator(40)
+    rng = np.random.default_rng(3)
+    held: list[int] = []
+    for _ in range(30):
+        if held and rng.random() < 0.4:
+            k = int(rng.integers(1, len(held) + 1))
+            give, held = held[:k], held[k:]
+            ref_alloc.free(list(give))
+            my_alloc.free(list(give))
+            trace.append(("free", give, []))
+        else:
+            n = int(rng.integers(0, 9))
+            a, b = ref_alloc.allocate(n), my_alloc.allocate(n)
+            assert a == b, "oracle BlockAllocator differs from the reference"
+            held += a
+            trace.append(("allocate", [n], a))
+    table = ref_alloc.allocate(5)
+    assert my_alloc.allocate(5) == table
+    vids = [0, 1, 15, 16, 17, 31, 47, 64, 79]
+    fake_self = types.SimpleNamespace(block_size=16)
+    fake_cache = types.SimpleNamespace(block_table=table)
+    ref_slots = mem.TokenCacheBlockManager.v2p(fake_self, fake_cache, vids)
+    assert oracle.v2p(table, 16, vids) == ref_slots
+    np.savez_compressed(GOLDEN / "allocator.npz",
+                        ops=np.array([t[0] for t in trace]), args=np.array([",".join(map(str, t[1])) for t in trace]),
+                        results=np.array([",".join(map(str, t[2])) for t in trace]),
+                        v2p_table=np.array(table), v2p_vids=np.array(vids), v2p_slots=np.array(ref_slots))
+
+    print("oracle == reference on every case (bit-exact outputs, caches, metadata, allocator, v2p)")
+    for name, err in report:
+        print(f"  {name:28s} max |reference(dtype) - fp32 recompute| = {err:.3e}")
+    total = sum(p.stat().st_size for p in GOLDEN.glob("*.npz"))
+    print(f"fixtures: {len(list(GOLDEN.glob('*.npz')))} files, {total / 1024:.0f} KiB in {GOLDEN}")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,178 @@
+"""CPU oracle for hydrainfer's paged-KV attention hot path.  TEST INFRASTRUCTURE ONLY.
+
+This module restates, in plain torch-on-CPU / Python, what the reference computes on this path.  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import it; nothing under
+hydrainfer_b200/ does (the product path has no CPU fallback).
+
+Parity pin: oracle/make_golden.py imports the REAL reference from /root/reference (Python torch path, runnable on CPU)
+and checks every function below against it on seeded inputs, then freezes the reference's outputs as fixtures in
+tests/golden/*.npz; tests/test_oracle_golden.py re-checks the oracle against those fixtures wherever the reference is
+absent (the GPU box).  Pinned this way: attention (Torch handler), set_kv_cache / set_image_cache (Python fallbacks),
+BlockAllocator, AttentionParametersBuilder metadata, v2p.  NOT pinned ("parity unpinned"): migrate_blocks — the
+reference implementation is CUDA-only C++ with no test or fixture anywhere in the reference tree; its
+index arithmetic is restated from the source alone.
+
+Every function cites the reference lines it follows (paths relative to /root/reference).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import torch
+from torch import Tensor
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# KV append
+# ---------------------------------------------------------------------------------------------------------------
+def set_kv_cache(slot_ids: Tensor, keys: Tensor, values: Tensor, key_cache: Tensor, value_cache: Tensor) -> None:
+    """hydrainfer/memory/kv_cache.py:44-50 (Python fallback of KVCache.set_kv_cache), same result as
+    csrc/kernel/kv_cache_kernels/kv_cache_kernels.cu:17-58:
+        cache[slot // block_size, slot % block_size, :, :] = rows[i, :, :]   for i in order
+    Written token by token so duplicate slots resolve the way the reference's loop resolves them (last write wins)."""
+    block_size = key_cache.shape[1]
+    for i in range(slot_ids.shape[0]):
+        slot = int(slot_ids[i])
+        block_id, block_offset = slot // block_size, slot % block_size
+        key_cache[block_id, block_offset, :, :] = keys[i, :, :]
+        value_cache[block_id, block_offset, :, :] = values[i, :, :]
+
+
+def set_image_cache(slot_ids: Tensor, image_tokens: Tensor, image_cache: Tensor) -> None:
+    """hydrainfer/memory/token_cache.py:53-56 (slot_view[slot_ids] = value) ==
+    csrc/kernel/cache_kernels/cache_kernels.cu:17-53."""
+    slot_view = image_cache.view(-1, image_cache.shape[-2], image_cache.shape[-1])
+    slot_view[slot_ids.long(), :, :] = image_tokens
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Attention
+# ---------------------------------------------------------------------------------------------------------------
+def paged_attention_fp32(query: Tensor, key_cache: Tensor, value_cache: Tensor, q_cu_seq_lens, kv_cu_seq_lens,
+                         block_tables: Tensor, cu_blocks_lens, n_qo_heads: int, n_kv_heads: int, head_dim: int) -> Tensor:
+    """fp32 result of TorchCausalGroupedQueryPageAttentionHandler.forward BEFORE the final cast
+    (hydrainfer/layer/causal_attention.py:307-374).  query [T, Hq, d]; caches [NB, bs, Hkv, d]; returns fp32 [T, Hq*d].
+
+    Per sequence (:314): gather pages by block table and flatten to [n_pages*bs, Hkv, d] (:315-317), keep the first
+    L rows (:318-319), cast q/k/v to fp32 (:318-320), repeat KV heads to Hq (:324-326), scores = q.k * 1/sqrt(d)
+    (:331-335), mask where (j - i) > (L - q) (:339-342), softmax over keys (:365), o = scores.v (:366)."""
+    q_cu = [int(x) for x in q_cu_seq_lens]
+    kv_cu = [int(x) for x in kv_cu_seq_lens]
+    cu_blocks = [int(x) for x in cu_blocks_lens]
+    block_tables = block_tables.long()
+    group = n_qo_heads // n_kv_heads
+    sm_scale = 1.0 / math.sqrt(head_dim)
+    outputs = []
+    for b in range(len(q_cu) - 1):
+        table = block_tables[cu_blocks[b]: cu_blocks[b + 1]]
+        kv_len = kv_cu[b + 1] - kv_cu[b]
+        k = key_cache[table].reshape(-1, n_kv_heads, head_dim)[:kv_len].to(torch.float)
+        v = value_cache[table].reshape(-1, n_kv_heads, head_dim)[:kv_len].to(torch.float)
+        q = query[q_cu[b]: q_cu[b + 1]].to(torch.float)
+        q_len = q.shape[0]
+        k = k.repeat_interleave(repeats=group, dim=1)
+        v = v.repeat_interleave(repeats=group, dim=1)
+        scores = torch.einsum("qhd,khd->hqk", q, k) * sm_scale
+        j = torch.arange(kv_len)[None, None, :]
+        i = torch.arange(q_len)[None, :, None]
+        scores = scores.masked_fill((j - i) > (kv_len - q_len), float("-inf"))
+        scores = torch.softmax(scores, dim=-1)
+        outputs.append(torch.einsum("hqk,khd->qhd", scores, v))
+    return torch.cat(outputs, dim=0).reshape(-1, n_qo_heads * head_dim)
+
+
+def paged_attention(query: Tensor, key_cache: Tensor, value_cache: Tensor, q_cu_seq_lens, kv_cu_seq_lens,
+                    block_tables: Tensor, cu_blocks_lens, n_qo_heads: int, n_kv_heads: int, head_dim: int) -> Tensor:
+    """The handler's return value: the fp32 result rounded to the query dtype (causal_attention.py:370-372)."""
+    return paged_attention_fp32(query, key_cache, value_cache, q_cu_seq_lens, kv_cu_seq_lens, block_tables,
+                                cu_blocks_lens, n_qo_heads, n_kv_heads, head_dim).to(query.dtype)
+
+
+def attention_layer_forward(query: Tensor, key: Tensor, value: Tensor, key_cache: Tensor, value_cache: Tensor,
+                            new_cache_slots: Tensor, q_cu_seq_lens, kv_cu_seq_lens, block_tables: Tensor, cu_blocks_lens,
+                            n_qo_heads: int, n_kv_heads: int, head_dim: int) -> Tensor:
+    """CausalGroupedQueryPageAttention.forward (causal_attention.py:394-406): view q/k/v to [T, H, d], append the new
+    K/V rows to the cache, then attend over old + new tokens."""
+    n_tokens = query.shape[0]
+    q = query.view(n_tokens, n_qo_heads, head_dim)
+    k = key.view(n_tokens, n_kv_heads, head_dim)
+    v = value.view(n_tokens, n_kv_heads, head_dim)
+    set_kv_cache(new_cache_slots, k, v, key_cache, value_cache)
+    return paged_attention(q, key_cache, value_cache, q_cu_seq_lens, kv_cu_seq_lens, block_tables, cu_blocks_lens,
+                           n_qo_heads, n_kv_heads, head_dim)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Allocator contract and per-step metadata
+# ---------------------------------------------------------------------------------------------------------------
+class BlockAllocator:
+    """hydrainfer/memory/block_allocator.py:11-39: free list [n-1 .. 0]; allocate(n) takes the LAST n entries in list
+    order (:25-32, at most what is left, [] for 0); free appends (:34-36)."""
+
+    def __init__(self, total_blocks: int):
+        self.total_blocks = total_blocks
+        self.free_blocks = [b for b in reversed(range(total_blocks))]
+
+    def allocate(self, n_blocks: int) -> list[int]:
+        if n_blocks == 0:
+            return []
+        n_blocks = min(n_blocks, len(self.free_blocks))
+        blocks, self.free_blocks = self.free_blocks[-n_blocks:], self.free_blocks[:-n_blocks]
+        return blocks
+
+    def free(self, blocks: list[int]) -> None:
+        self.free_blocks += blocks
+
+
+def v2p(block_table: list[int], block_size: int, virtual_cache_ids: list[int]) -> list[int]:
+    """hydrainfer/memory/token_cache_manger.py:126-133: slot = block_table[v // bs] * bs + v % bs."""
+    return [block_table[v // block_size] * block_size + v % block_size for v in virtual_cache_ids]
+
+
+@dataclass
+class Metadata:
+    """The lists AttentionParametersBuilder accumulates (causal_attention.py:135-157) before they become int32 tensors."""
+    q_cu_seq_lens: list[int] = field(default_factory=lambda: [0])
+    kv_cu_seq_lens: list[int] = field(default_factory=lambda: [0])
+    paged_kv_last_page_len: list[int] = field(default_factory=list)
+    new_cache_slots: list[int] = field(default_factory=list)
+    block_tables: list[int] = field(default_factory=list)
+    cu_blocks_lens: list[int] = field(default_factory=lambda: [0])
+    num_sequences: int = 0
+    all_sequences_decode: bool = True
+    q_max_seq_len: int = 0
+    kv_max_seq_len: int = 0
+
+
+def build_metadata(requests: list[tuple[int, int, list[int], list[int]]], block_size: int) -> Metadata:
+    """requests: (q_seq_len, kv_seq_len, new_cache_slots, block_table) per sequence, in batch order
+    (AttentionParametersBuilder.add_request, causal_attention.py:147-157)."""
+    m = Metadata()
+    for q_len, kv_len, slots, table in requests:
+        m.q_cu_seq_lens.append(m.q_cu_seq_lens[-1] + q_len)
+        m.kv_cu_seq_lens.append(m.kv_cu_seq_lens[-1] + kv_len)
+        m.paged_kv_last_page_len.append((kv_len + block_size - 1) % block_size + 1)
+        m.new_cache_slots += slots
+        m.block_tables += table
+        m.cu_blocks_lens.append(m.cu_blocks_lens[-1] + len(table))
+        m.num_sequences += 1
+        m.all_sequences_decode = m.all_sequences_decode and q_len == 1
+        m.q_max_seq_len = max(m.q_max_seq_len, q_len)
+        m.kv_max_seq_len = max(m.kv_max_seq_len, kv_len)
+    return m
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Migration (parity unpinned: restated from source only)
+# ---------------------------------------------------------------------------------------------------------------
+def migrate_blocks(src_block_table: list[int], dst_block_table: list[int], src_cache: Tensor, dst_cache: Tensor) -> None:
+    """csrc/data_transfer/block_migration.cpp:222-244: for every (layer, token/kv plane, i) copy the contiguous run
+    src[layer, plane, src_bt[i], :, :, :] -> dst[layer, plane, dst_bt[i], :, :, :] (INDEX_6D, :26-27).
+    Pools are 6-D (n_layers, n_tokens, n_blocks, block_size, n_heads, head_size) and may differ in n_blocks only."""
+    assert len(src_block_table) == len(dst_block_table)
+    n_layers, n_tokens = dst_cache.shape[0], dst_cache.shape[1]
+    for layer_id in range(n_layers):
+        for token_id in range(n_tokens):
+            for s, d in zip(src_block_table, dst_block_table):
+                dst_cache[layer_id, token_id, d].copy_(src_cache[layer_id, token_id, s])

@@ -1,0 +1,154 @@
+"""CPU: host-side mirrors of the reference interface (allocator contract, metadata builder, backend selection)."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from hydrainfer_b200.layer.causal_attention import (AttentionParametersBuilder, B200CausalGroupedQueryPageAttentionHandler,
+                                                    CausalGroupedQueryPageAttention, CausalGroupedQueryPageAttentionConfig)
+from hydrainfer_b200.memory import (BlockAllocator, CommunicationBackendManager, CommunicationBackendManagerConfig,
+                                    CommunicationBackendManagerContext, TokenCacheBlockManager, TokenCacheBlockManagerConfig,
+                                    TokenCacheBlockManagerContext, VirtualTokenCache)
+from hydrainfer_b200.memory.token_cache_manger import _PinnedBlocks
+
+
+def _ints(s) -> list[int]:
+    s = str(s)
+    return [int(v) for v in s.split(",")] if s else []
+
+
+def test_allocator_reference_trace():
+    z = np.load(GOLDEN / "allocator.npz")
+    alloc = BlockAllocator(40)
+    for op, args, result in zip(z["ops"], z["args"], z["results"]):
+        if str(op) == "free":
+            alloc.free(_ints(args))
+        else:
+            assert alloc.allocate(_ints(args)[0]) == _ints(result)
+
+
+def test_allocator_random_allocate():
+    # reference tests/memory/test_block_allocator.py:5-22
+    total = 100
+    alloc = BlockAllocator(total)
+    ref = list(reversed(range(total)))
+    rng = random.Random(0)
+    for _ in range(10):
+        n = rng.randint(1, 10)
+        expect = [ref.pop() for _ in range(n)]
+        expect.reverse()
+        assert alloc.allocate(n) == expect
+    assert alloc.allocate(0) == []
+
+
+def test_allocator_free_kat():
+    # reference tests/memory/test_block_allocator.py:34-38
+    alloc = BlockAllocator(10)
+    assert alloc.allocate(3) == [2, 1, 0]
+    alloc.free([1, 0])
+    assert alloc.allocate(3) == [3, 1, 0]
+
+
+def test_allocator_partial_when_dry():
+    # the current reference returns what is left (block_allocator.py:25-32); its stale test_out_of_memory expects []
+    alloc = BlockAllocator(4)
+    assert alloc.allocate(6) == [3, 2, 1, 0]
+    assert alloc.allocate(1) == []
+    assert alloc.get_num_avaiable_blocks() == 0
+    m = alloc.get_metrics()
+    assert (m.n_used_blocks, m.n_total_blocks, m.block_usage) == (4, 4, 1.0)
+
+
+def test_builder_metadata_matches_reference(golden_attention):
+    g = golden_attention
+    builder = AttentionParametersBuilder(g.n_qo_heads, g.n_kv_heads, g.head_dim, g.block_size, torch.device("cpu"))
+    for req in g.requests():
+        builder.add_request(*req)
+    builder.add_kv_cache(object())
+    builder.add_kv_cache(object())
+    params = builder.build_attention_parameters()
+    assert len(params) == 2 and params[0].block_tables is params[1].block_tables or torch.equal(params[0].block_tables, params[1].block_tables)
+    p = params[0]
+    for name in ("q_cu_seq_lens", "kv_cu_seq_lens", "paged_kv_last_page_len", "new_cache_slots", "block_tables", "cu_blocks_lens"):
+        t = getattr(p, name)
+        assert t.dtype == torch.int32 and t.tolist() == getattr(g, name), name
+        assert t.data_ptr() % 16 == 0, f"{name} slice is not 16-byte aligned"
+    assert p.num_sequences == len(g.seq_lens)
+    assert p.all_sequences_decode == all(q == 1 for q, _ in g.seq_lens)
+    assert p.q_max_seq_len == max(q for q, _ in g.seq_lens) and p.kv_max_seq_len == max(kv for _, kv in g.seq_lens)
+
+
+def test_handler_rejects_cpu_without_fallback():
+    cfg = CausalGroupedQueryPageAttentionConfig(4, 2, 64)
+    handler = B200CausalGroupedQueryPageAttentionHandler(cfg)
+    with pytest.raises(RuntimeError, match="no CPU handler"):
+        handler(torch.zeros(1, 4, 64), None)
+
+    class Next(torch.nn.Module):
+        def forward(self, q, p):
+            return "fell through"
+
+    handler.next_handler = Next()
+    assert handler(torch.zeros(1, 4, 64), None) == "fell through"
+    with pytest.raises(AssertionError):
+        CausalGroupedQueryPageAttention(CausalGroupedQueryPageAttentionConfig(6, 4, 64))
+
+
+def test_kernels_reject_cpu_tensors():
+    from hydrainfer_b200._C.kernel.kv_cache_kernels import set_kv_cache
+    from hydrainfer_b200._C.kernel.cache_kernels import set_image_cache
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        set_kv_cache(torch.zeros(1, dtype=torch.int32), torch.zeros(1, 1, 8), torch.zeros(1, 1, 8), torch.zeros(1, 4, 1, 8), torch.zeros(1, 4, 1, 8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        set_image_cache(torch.zeros(1, dtype=torch.int32), torch.zeros(1, 1, 8), torch.zeros(1, 4, 1, 8))
+
+
+def test_block_manager_has_no_cpu_pool():
+    cfg = TokenCacheBlockManagerConfig(CommunicationBackendManagerConfig(), n_layers=1, n_blocks=4, n_heads=1, head_size=8, device="cpu")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        TokenCacheBlockManager(cfg, TokenCacheBlockManagerContext(rank=0, rank2host={0: "a"}))
+
+
+def test_compute_n_blocks():
+    cfg = TokenCacheBlockManagerConfig(CommunicationBackendManagerConfig(), n_layers=32, n_tokens=2, block_size=16, n_heads=32, head_size=128, dtype="fp16")
+    per_block = 32 * 2 * 16 * 32 * 128 * 2  # 8 MiB
+    assert per_block == 8 << 20
+    assert TokenCacheBlockManager.compute_n_blocks(cfg, 10 * per_block + 5) == 10
+
+
+def test_pinned_blocks_reuse():
+    pool = _PinnedBlocks(6)
+    pool.pin([0, 1, 2])
+    pool.pin([1])
+    pool.unpin([0, 1, 2])
+    assert pool.get_num_avaiable_blocks() == 2 and sorted(pool.evictable) == [0, 2]
+    got = pool.allocate(5)
+    assert sorted(got) == [0, 2] and pool.get_num_avaiable_blocks() == 0
+    with pytest.raises(AssertionError):
+        pool.unpin([5])
+
+
+class _Recorder:
+    def __init__(self):
+        self.calls = []
+
+    def migrate_blocks(self, s, d, is_send):
+        self.calls.append((s.rank, d.rank, is_send))
+
+
+def test_backend_selection_by_host():
+    ctx = CommunicationBackendManagerContext(migrate_stream=None, cache=torch.zeros(1, 1, 1, 1, 1, 1), n_blocks=1,
+                                             rank2host={0: "hostA", 1: "hostA", 2: "hostB"})
+    mgr = CommunicationBackendManager(CommunicationBackendManagerConfig(), ctx)
+    mgr.intranode_backend, mgr.internode_backend = _Recorder(), _Recorder()
+    v = lambda rank, n=4: VirtualTokenCache(vid=1, n_blocks_of_cache_manager=8, n_cache_tokens=n, rank=rank)
+    mgr.migrate_blocks(v(0), v(1), False)
+    mgr.migrate_blocks(v(0), v(2), True)
+    mgr.migrate_blocks(v(0), v(7), False)  # unknown rank -> treated as another machine (communication.py:112-115)
+    assert mgr.intranode_backend.calls == [(0, 1, False)]
+    assert mgr.internode_backend.calls == [(0, 2, True), (0, 7, False)]
+    with pytest.raises(AssertionError):
+        mgr.migrate_blocks(v(0, 4), v(1, 5), False)
+    assert mgr.in_same_machine(0, 1) and not mgr.in_same_machine(1, 2)
