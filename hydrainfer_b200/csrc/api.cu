@@ -41,6 +41,7 @@ int launch_attn_simt(const HiAttnArgs& args, cudaStream_t stream);
 int launch_attn_tc(const HiAttnArgs& args, cudaStream_t stream);
 bool attn_tc_supported(const HiAttnArgs& args);
 int64_t simt_workspace_bytes(int head_dim);
+int64_t tc_workspace_bytes();
 
 }  // namespace hi
 
@@ -52,7 +53,8 @@ extern "C" int64_t hi_attention_workspace_bytes(int32_t n_tokens, int32_t n_qo_h
   (void)n_tokens;
   (void)n_qo_heads;
   (void)max_kv_len;
-  const int64_t need = hi::simt_workspace_bytes(head_dim > 0 ? head_dim : 128);
+  int64_t need = hi::simt_workspace_bytes(head_dim > 0 ? head_dim : 128);
+  if (hi::tc_workspace_bytes() > need) need = hi::tc_workspace_bytes();
   return (need + 255) / 256 * 256;
 }
 
@@ -90,7 +92,10 @@ extern "C" int hi_paged_attention(const HiAttnArgs* p, void* stream_) {
   if (path == HI_ATTN_AUTO) {
     // Rows with q_len > 1 are dense contractions: tensor pipe.  Pure decode batches stream KV once per row: the
     // split-KV kernel keeps more bytes in flight and balances ragged lengths.
-    path = (a.max_q_len > 1 && attn_tc_supported(a)) ? HI_ATTN_TCGEN05 : HI_ATTN_SIMT;
+    // Grouped models (>= 4 query heads per KV head) also decode on the tile kernel: the heads of a group are packed
+    // into the MMA M dimension, which the CUDA-core kernel can only emulate with G FMAs per KV element.
+    const int group = a.n_qo_heads / a.n_kv_heads;
+    path = ((a.max_q_len > 1 || group >= 4) && attn_tc_supported(a)) ? HI_ATTN_TCGEN05 : HI_ATTN_SIMT;
   }
   if (path == HI_ATTN_TCGEN05) return launch_attn_tc(a, stream);
   if (path == HI_ATTN_SIMT) return launch_attn_simt(a, stream);

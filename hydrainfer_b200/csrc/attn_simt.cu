@@ -23,27 +23,10 @@
 #include <cfloat>
 
 #include "common.cuh"
+#include "attn_common.cuh"
 
 namespace hi {
 
-struct SimtArgs {
-  const void* q;
-  void* out;
-  const void* kc;
-  const void* vc;
-  int64_t q_row_stride, out_row_stride;  // elements
-  int64_t tok_stride;                    // elements between consecutive slots of the cache: Hkv * D
-  const int32_t* q_cu;
-  const int32_t* kv_cu;
-  const int32_t* block_tables;
-  const int32_t* cu_blocks;
-  int n_seqs, n_tokens, n_qo_heads, n_kv_heads, group, block_size;
-  int chunk_tiles;  // 16-token tiles per chunk
-  int n_chunks;
-  float scale_log2;  // softmax_scale * log2(e)
-  float* part_o;     // [n_tokens * Hq * n_chunks][D]
-  float* part_ml;    // [n_tokens * Hq * n_chunks][2]
-};
 
 constexpr int kSimtThreads = 128;
 constexpr int kHalfWarps = kSimtThreads / 16;
@@ -110,6 +93,60 @@ __device__ __forceinline__ void transpose_reduce16(float (&v)[16], int lane) {
       v[i] = keep + __shfl_xor_sync(kFull, send, H);
     }
     transpose_reduce16<H>(v, lane);
+  }
+}
+
+// Merge the 8 half-warp (m, l, o) states of a CTA through shared memory and write the row (or its split-KV partial).
+// `scratch` holds kHalfWarps * G * (D + 2) floats.
+template <typename T, int D, int G>
+__device__ __forceinline__ void merge_half_warps_and_store(const SimtArgs& a, float* scratch, const float (&m)[G],
+                                                           const float (&lsum)[G], const float (&o)[G][D / 16], int t, int qh0,
+                                                           int chunk) {
+  constexpr int E = D / 16;
+  const int l16 = threadIdx.x & 15;
+  const int hw = threadIdx.x >> 4;
+  float* sm_o = scratch;                          // [kHalfWarps][G][D]
+  float* sm_m = scratch + kHalfWarps * G * D;     // [kHalfWarps][G]
+  float* sm_l = sm_m + kHalfWarps * G;            // [kHalfWarps][G]
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    float l = lsum[g];
+#pragma unroll
+    for (int off = 8; off >= 1; off >>= 1) l += __shfl_xor_sync(kFull, l, off);
+    if (l16 == 0) {
+      sm_m[hw * G + g] = m[g];
+      sm_l[hw * G + g] = l;
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) sm_o[(hw * G + g) * D + l16 * E + e] = o[g][e];
+  }
+  __syncthreads();
+
+  for (int idx = threadIdx.x; idx < G * D; idx += kSimtThreads) {
+    const int g = idx / D;
+    const int d = idx - g * D;
+    float mm = -INFINITY;
+#pragma unroll
+    for (int h = 0; h < kHalfWarps; ++h) mm = fmaxf(mm, sm_m[h * G + g]);
+    float osum = 0.f, l = 0.f;
+#pragma unroll
+    for (int h = 0; h < kHalfWarps; ++h) {
+      const float w = fast_exp2(sm_m[h * G + g] - mm);  // mm is finite: the chunk has at least one visible key
+      osum = fmaf(w, sm_o[(h * G + g) * D + d], osum);
+      l = fmaf(w, sm_l[h * G + g], l);
+    }
+    const int head = qh0 + g;
+    if (a.n_chunks == 1) {
+      T* orow = static_cast<T*>(a.out) + static_cast<int64_t>(t) * a.out_row_stride + head * D;
+      orow[d] = Elem<T>::from_f32(osum / l);
+    } else {
+      const int64_t pidx = (static_cast<int64_t>(t) * a.n_qo_heads + head) * a.n_chunks + chunk;
+      a.part_o[pidx * D + d] = osum;
+      if (d == 0) {
+        a.part_ml[pidx * 2 + 0] = mm;
+        a.part_ml[pidx * 2 + 1] = l;
+      }
+    }
   }
 }
 
@@ -246,50 +283,202 @@ __global__ void __launch_bounds__(kSimtThreads) paged_attn_simt_kernel(const Sim
     }
   }
 
-  // ---- merge the 8 half-warp states ----------------------------------------------------------------------------
-  __shared__ float sm_o[kHalfWarps][G][D];
-  __shared__ float sm_m[kHalfWarps][G];
-  __shared__ float sm_l[kHalfWarps][G];
+  __shared__ float scratch[kHalfWarps * G * (D + 2)];
+  merge_half_warps_and_store<T, D, G>(a, scratch, m, lsum, o, t, qh0, chunk);
+}
+
+
+// ---- streaming variant: KV pages staged through shared memory with cp.async -------------------------------------------
+//
+// Same algorithm and thread mapping as paged_attn_simt_kernel, but a lane never holds raw KV in registers: for every
+// token of a tile it issues a 16-byte (8-byte for D=64) cp.async from the page straight into a private shared-memory
+// slot and later reads that slot back with one LDS.  Each lane only ever reads the bytes it copied itself, so
+// cp.async.wait_group is the only synchronisation needed (no barrier, no producer warp).  A half-warp owns one K buffer
+// and one V buffer of one tile each; K of tile i+1 is in flight while P.V of tile i is computed, V of tile i while
+// Q.K^T of tile i is computed, so every half-warp keeps 4 KiB (d=128) of HBM requests outstanding at all times:
+// 64 KiB of shared memory per CTA, 3 CTAs per SM, ~96 KiB in flight per SM against the ~45 KiB Little's law asks for.
+template <int BYTES>
+__device__ __forceinline__ void cp_async_lane(uint32_t smem_dst, const void* gmem_src, bool pred) {
+  const int src_bytes = pred ? BYTES : 0;  // src-size 0: nothing is read, the destination is zero-filled
+  if constexpr (BYTES == 16) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_bytes) : "memory");
+  } else {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_bytes) : "memory");
+  }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <typename T, int E>
+__device__ __forceinline__ void lds_lane_row(const uint8_t* p, float (&f)[E]) {
+  constexpr int W = E * static_cast<int>(sizeof(T)) / 4;
+  uint32_t w[W];
+  if constexpr (W == 2) {
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    w[0] = v.x;
+    w[1] = v.y;
+  } else {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    w[0] = v.x;
+    w[1] = v.y;
+    w[2] = v.z;
+    w[3] = v.w;
+  }
+#pragma unroll
+  for (int i = 0; i < W; ++i) unpack2<T>(w[i], f[2 * i], f[2 * i + 1]);
+}
+
+template <typename T, int D>
+constexpr int stream_smem_bytes() {
+  return kHalfWarps * 2 * 16 * 16 * (D / 16) * static_cast<int>(sizeof(T));
+}
+
+template <typename T, int D, int G>
+__global__ void __launch_bounds__(kSimtThreads) paged_attn_stream_kernel(const SimtArgs a) {
+  constexpr int E = D / 16;                               // head dims per lane
+  constexpr int EB = E * static_cast<int>(sizeof(T));     // bytes per lane per token row: 16 (d=128) or 8 (d=64)
+  static_assert(sizeof(T) == 2 && (EB == 16 || EB == 8), "streaming kernel covers 16-bit dtypes with head_dim 64 / 128");
+  constexpr int kRowBytes = 16 * EB;                      // one token row of one KV head
+  constexpr int kTileBytes = 16 * kRowBytes;              // one 16-token tile
+  static_assert(stream_smem_bytes<T, D>() >= static_cast<int>(kHalfWarps * G * (D + 2) * sizeof(float)),
+                "the merge scratch aliases the staging buffers");
+
+  extern __shared__ __align__(16) uint8_t stage[];
+
+  const int t = blockIdx.x;
+  const int groups_per_kv = a.group / G;
+  const int kvh = blockIdx.y / groups_per_kv;
+  const int qh0 = kvh * a.group + (blockIdx.y % groups_per_kv) * G;
+  const int chunk = blockIdx.z;
+
+  const int b = find_seq(a.q_cu, a.n_seqs, t);
+  const int q_start = __ldg(a.q_cu + b);
+  const int q_len = __ldg(a.q_cu + b + 1) - q_start;
+  const int kv_len = __ldg(a.kv_cu + b + 1) - __ldg(a.kv_cu + b);
+  const int vis = kv_len - q_len + (t - q_start) + 1;
+  const int tiles_total = (vis + 15) >> 4;
+  const int tile_begin = chunk * a.chunk_tiles;
+  if (tile_begin >= tiles_total) return;
+  const int tile_end = min(tiles_total, tile_begin + a.chunk_tiles);
+  const int n_iters = (tile_end - tile_begin + kHalfWarps - 1) / kHalfWarps;
+  const int32_t* __restrict__ bt = a.block_tables + __ldg(a.cu_blocks + b);
+
+  const int l16 = threadIdx.x & 15;
+  const int hw = threadIdx.x >> 4;
+  const uint8_t* kbase = reinterpret_cast<const uint8_t*>(static_cast<const T*>(a.kc) + kvh * D + l16 * E);
+  const uint8_t* vbase = reinterpret_cast<const uint8_t*>(static_cast<const T*>(a.vc) + kvh * D + l16 * E);
+  const int64_t tok_stride_bytes = a.tok_stride * static_cast<int64_t>(sizeof(T));
+
+  uint8_t* k_buf = stage + hw * 2 * kTileBytes + l16 * EB;  // this lane's column of the half-warp's K tile
+  uint8_t* v_buf = k_buf + kTileBytes;
+  const uint32_t k_buf_s = static_cast<uint32_t>(__cvta_generic_to_shared(k_buf));
+  const uint32_t v_buf_s = k_buf_s + kTileBytes;
+
+  // physical slot of this lane's token in iteration `it` (-1: masked / beyond the chunk)
+  auto slot_of = [&](int it) -> int {
+    const int tile = tile_begin + it * kHalfWarps + hw;
+    const int pos = tile * 16 + l16;
+    if (it >= n_iters || tile >= tile_end || pos >= vis) return -1;
+    const int pg = pos / a.block_size;
+    return __ldg(bt + pg) * a.block_size + (pos - pg * a.block_size);
+  };
+  auto issue_tile = [&](const uint8_t* base, uint32_t buf_s, int slot_lane) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int sk = __shfl_sync(kFull, slot_lane, k, 16);
+      cp_async_lane<EB>(buf_s + k * kRowBytes, base + static_cast<int64_t>(sk < 0 ? 0 : sk) * tok_stride_bytes, sk >= 0);
+    }
+    cp_async_commit();
+  };
+
+  int slot = slot_of(0);
+  issue_tile(kbase, k_buf_s, slot);
+  issue_tile(vbase, v_buf_s, slot);
+
+  float qf[G][E];
+  {
+    const T* qrow = static_cast<const T*>(a.q) + static_cast<int64_t>(t) * a.q_row_stride + qh0 * D + l16 * E;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      LaneRow<T, E> r;
+      r.load(qrow + g * D);
+      r.to_f32(qf[g]);
+#pragma unroll
+      for (int e = 0; e < E; ++e) qf[g][e] *= a.scale_log2;
+    }
+  }
+  float m[G], lsum[G], o[G][E];
 #pragma unroll
   for (int g = 0; g < G; ++g) {
-    float l = lsum[g];
+    m[g] = -INFINITY;
+    lsum[g] = 0.f;
 #pragma unroll
-    for (int off = 8; off >= 1; off >>= 1) l += __shfl_xor_sync(kFull, l, off);
-    if (l16 == 0) {
-      sm_m[hw][g] = m[g];
-      sm_l[hw][g] = l;
-    }
-#pragma unroll
-    for (int e = 0; e < E; ++e) sm_o[hw][g][l16 * E + e] = o[g][e];
+    for (int e = 0; e < E; ++e) o[g][e] = 0.f;
   }
-  __syncthreads();
 
-  for (int idx = threadIdx.x; idx < G * D; idx += kSimtThreads) {
-    const int g = idx / D;
-    const int d = idx - g * D;
-    float mm = -INFINITY;
+  for (int it = 0; it < n_iters; ++it) {
+    const bool valid = slot >= 0;
+    const int slot_next = slot_of(it + 1);
+
+    // ---- S = q . K^T ----------------------------------------------------------------------------------------------
+    cp_async_wait<1>();  // K(it) has landed; V(it) may still be in flight
+    float acc[G][16];
 #pragma unroll
-    for (int h = 0; h < kHalfWarps; ++h) mm = fmaxf(mm, sm_m[h][g]);
-    float osum = 0.f, l = 0.f;
+    for (int k = 0; k < 16; ++k) {
+      float kf[E];
+      lds_lane_row<T, E>(k_buf + k * kRowBytes, kf);
 #pragma unroll
-    for (int h = 0; h < kHalfWarps; ++h) {
-      const float w = fast_exp2(sm_m[h][g] - mm);  // mm is finite: the chunk has at least one visible key
-      osum = fmaf(w, sm_o[h][g][d], osum);
-      l = fmaf(w, sm_l[h][g], l);
-    }
-    const int head = qh0 + g;
-    if (a.n_chunks == 1) {
-      T* orow = static_cast<T*>(a.out) + static_cast<int64_t>(t) * a.out_row_stride + head * D;
-      orow[d] = Elem<T>::from_f32(osum / l);
-    } else {
-      const int64_t pidx = (static_cast<int64_t>(t) * a.n_qo_heads + head) * a.n_chunks + chunk;
-      a.part_o[pidx * D + d] = osum;
-      if (d == 0) {
-        a.part_ml[pidx * 2 + 0] = mm;
-        a.part_ml[pidx * 2 + 1] = l;
+      for (int g = 0; g < G; ++g) {
+        float s = 0.f;
+#pragma unroll
+        for (int e = 0; e < E; ++e) s = fmaf(qf[g][e], kf[e], s);
+        acc[g][k] = s;
       }
     }
+    issue_tile(kbase, k_buf_s, slot_next);  // K(it+1) streams in behind the softmax and P.V of this tile
+
+    // ---- online softmax; lane k owns token k ------------------------------------------------------------------------
+    float p[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      transpose_reduce16<16>(acc[g], l16);
+      const float s = valid ? acc[g][0] : -INFINITY;
+      float mx = s;
+#pragma unroll
+      for (int off = 8; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, off));
+      const float m_new = fmaxf(m[g], mx);
+      const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
+      const float alpha = fast_exp2(m[g] - m_safe);
+      p[g] = fast_exp2(s - m_safe);
+      lsum[g] = lsum[g] * alpha + p[g];
+      m[g] = m_new;
+#pragma unroll
+      for (int e = 0; e < E; ++e) o[g][e] *= alpha;
+    }
+
+    // ---- O += P . V ----------------------------------------------------------------------------------------------------
+    cp_async_wait<1>();  // V(it) has landed; K(it+1) may still be in flight
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float vf[E];
+      lds_lane_row<T, E>(v_buf + k * kRowBytes, vf);
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const float pk = __shfl_sync(kFull, p[g], k, 16);
+#pragma unroll
+        for (int e = 0; e < E; ++e) o[g][e] = fmaf(pk, vf[e], o[g][e]);
+      }
+    }
+    issue_tile(vbase, v_buf_s, slot_next);  // V(it+1) streams in behind Q.K^T of the next tile
+    slot = slot_next;
   }
+
+  cp_async_wait<0>();
+  __syncthreads();  // every lane is done with the staging buffers; reuse them as the merge scratch
+  merge_half_warps_and_store<T, D, G>(a, reinterpret_cast<float*>(stage), m, lsum, o, t, qh0, chunk);
 }
 
 // LSE-weighted reduction of the per-chunk partials of one (row, head): the split-merge step.
@@ -339,11 +528,39 @@ int64_t simt_workspace_bytes(int head_dim) {
   return static_cast<int64_t>(8) * kTargetCtas * (head_dim + 2) * 4;
 }
 
+// Split-merge launch shared with the tile kernel's split-KV mode (a.n_tokens rows, a.n_chunks partials per row and head).
+int launch_merge_partials(const SimtArgs& a, int dtype, int head_dim, cudaStream_t stream) {
+  const dim3 grid(a.n_tokens, a.n_qo_heads);
+  if (head_dim == 128 && dtype == HI_BF16) {
+    merge_partials_kernel<__nv_bfloat16, 128><<<grid, 32, 0, stream>>>(a);
+  } else if (head_dim == 128 && dtype == HI_F16) {
+    merge_partials_kernel<__half, 128><<<grid, 32, 0, stream>>>(a);
+  } else {
+    set_error("merge_partials: unsupported head_dim %d / dtype %d", head_dim, dtype);
+    return HI_ERR_UNSUPPORTED;
+  }
+  note_launch();
+  HI_CUDA(cudaGetLastError());
+  return HI_OK;
+}
+
 template <typename T, int D, int G>
 static int launch_simt_g(const SimtArgs& a, cudaStream_t stream) {
   const dim3 grid(a.n_tokens, a.n_kv_heads * (a.group / G), a.n_chunks);
-  timing_mark_start(stream);
-  paged_attn_simt_kernel<T, D, G><<<grid, kSimtThreads, 0, stream>>>(a);
+  constexpr bool kStream = sizeof(T) == 2 && D <= 128;  // 8- or 16-byte lane rows: staged through cp.async
+  if constexpr (kStream) {
+    constexpr int smem = stream_smem_bytes<T, D>();
+    static bool configured = false;
+    if (!configured) {
+      HI_CUDA(cudaFuncSetAttribute(paged_attn_stream_kernel<T, D, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      configured = true;
+    }
+    timing_mark_start(stream);
+    paged_attn_stream_kernel<T, D, G><<<grid, kSimtThreads, smem, stream>>>(a);
+  } else {
+    timing_mark_start(stream);
+    paged_attn_simt_kernel<T, D, G><<<grid, kSimtThreads, 0, stream>>>(a);
+  }
   timing_mark_stop(stream);
   note_launch();
   HI_CUDA(cudaGetLastError());

@@ -32,6 +32,7 @@
 #include <type_traits>
 #include <unordered_map>
 
+#include "attn_common.cuh"
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 
@@ -59,6 +60,12 @@ struct TcArgs {
   int tq;            // query tokens per tile: 128 / group
   float scale_log2;  // softmax_scale * log2(e)
   int serialize;     // debug: wait for P.V to finish before the next Q.K^T is issued (HI_TC_SERIALIZE=1)
+  // split-KV mode (n_splits > 1): CTA `sp` of a tile covers KV tiles [sp*tiles_per_split, (sp+1)*tiles_per_split) and
+  // writes an fp32 partial (o, m, l) per row; merge_partials_kernel reduces them.
+  int n_splits;
+  int tiles_per_split;  // in 128-token tiles
+  float* part_o;        // [n_tokens * Hq * n_splits][128]
+  float* part_ml;       // [n_tokens * Hq * n_splits][2]
 };
 
 template <int NST>
@@ -97,12 +104,16 @@ paged_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   const int kv_len = __ldg(a.kv_cu + b + 1) - __ldg(a.kv_cu + b);
   const int n_q_tiles = (q_len + a.tq - 1) / a.tq;
   // Heaviest tiles (the end of the sequence sees the most keys) are scheduled first.
-  const int q_tile = n_q_tiles - 1 - static_cast<int>(blockIdx.x);
+  const int sp = static_cast<int>(blockIdx.x) % a.n_splits;
+  const int q_tile = n_q_tiles - 1 - static_cast<int>(blockIdx.x) / a.n_splits;
   if (q_tile < 0) return;
   const int i0 = q_tile * a.tq;                                   // first query position of the tile
   const int i_last = min(q_len, i0 + a.tq) - 1;                   // last valid query position
   const int kv_end = i_last + (kv_len - q_len) + 1;               // keys [0, kv_end) are visible to the tile
-  const int n_kv_tiles = (kv_end + kTileN - 1) / kTileN;
+  const int n_kv_tiles_all = (kv_end + kTileN - 1) / kTileN;
+  const int j_begin = sp * a.tiles_per_split;
+  if (j_begin >= n_kv_tiles_all) return;  // this split has no visible key for the tile; the merge skips it too
+  const int n_kv_tiles = min(n_kv_tiles_all - j_begin, a.tiles_per_split);  // tiles this CTA walks
   const int blk0 = __ldg(a.cu_blocks + b);
   const int n_pages = __ldg(a.cu_blocks + b + 1) - blk0;
   const int pages_per_tile = kTileN / a.block_size;
@@ -157,7 +168,7 @@ paged_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     for (int j = 0; j < n_kv_tiles; ++j) {
       const int st = j % NST;
       const uint32_t ph = static_cast<uint32_t>(j / NST) & 1u;
-      const int page0 = j * pages_per_tile;
+      const int page0 = (j_begin + j) * pages_per_tile;
       const int n_valid = min(pages_per_tile, n_pages - page0);
       // lane p stages page p of the tile
       int blk = 0;
@@ -238,28 +249,38 @@ paged_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     const int lim = i + (kv_len - q_len);            // last visible key index for this row
     float m_used = 0.f;                              // exponent reference, scaled log2 domain
     float l = 0.f;
+    // Rows past the tile's valid (token, head) pairs are padding: a warp that owns only padding rows skips the softmax
+    // math (decode tiles of grouped models have <= 16 real rows).  Its rows of P keep stale bits; MMA rows are independent.
+    const int rows_real = (min(q_len, i0 + a.tq) - i0) * a.group;
+    const bool warp_active = warp * 32 < rows_real;
 
     for (int j = 0; j < n_kv_tiles; ++j) {
-      const int kv0 = j * kTileN;
+      const int kv0 = (j_begin + j) * kTileN;
       const int col_lim = lim - kv0;                 // columns [0, col_lim] are visible
       const bool need_mask = col_lim < kTileN - 1;
       ptx::mbar_wait(bar(L::bSFull), static_cast<uint32_t>(j) & 1u);
       ptx::tc_fence_after_sync();
+      if (warp_active) {
 
-      // pass 1: row max of the raw scores
-      float mx = -INFINITY;
+      // The row's 128 scores live in registers for the whole step (one TMEM read), the mask is only evaluated on tiles
+      // that touch the causal diagonal or the end of the sequence, and the arithmetic uses the 3-input max and the
+      // packed fp32x2 FMA/ADD of sm_100 so that MUFU.EX2 (16 lanes/clk/SM) is the only saturated pipe.
+      uint32_t sv[128];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        ptx::tmem_ld_x32(tmem_s + c * 32, v);
-        ptx::tmem_wait_ld();
+      for (int c = 0; c < 4; ++c) ptx::tmem_ld_x32(tmem_s + c * 32, reinterpret_cast<uint32_t(&)[32]>(sv[32 * c]));
+      ptx::tmem_wait_ld();
+      if (__any_sync(0xffffffffu, need_mask)) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          float s = __uint_as_float(v[e]);
-          if (need_mask && (c * 32 + e > col_lim)) s = -INFINITY;
-          mx = fmaxf(mx, s);
-        }
+        for (int e = 0; e < 128; ++e)
+          if (e > col_lim) sv[e] = 0xff800000u;  // -inf
       }
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int e = 0; e < 128; e += 8) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) mx4[u] = fmax3(mx4[u], __uint_as_float(sv[e + 2 * u]), __uint_as_float(sv[e + 2 * u + 1]));
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float mxs = mx * a.scale_log2;
       if (j == 0) {
         m_used = (mxs == -INFINITY) ? 0.f : mxs;
@@ -280,30 +301,25 @@ paged_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         }
       }
 
-      // pass 2: P = exp2(S * scale - m) as 16-bit pairs, written over S
-      float lsum = 0.f;
+      // P = exp2(S * scale - m) as 16-bit pairs, written over S
+      const float2 sc2 = make_float2(a.scale_log2, a.scale_log2);
+      const float2 nm2 = make_float2(-m_used, -m_used);
+      float2 ls2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        ptx::tmem_ld_x32(tmem_s + c * 32, v);
-        ptx::tmem_wait_ld();
         uint32_t pk[16];
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
-          float s0 = __uint_as_float(v[e]);
-          float s1 = __uint_as_float(v[e + 1]);
-          if (need_mask) {
-            if (c * 32 + e > col_lim) s0 = -INFINITY;
-            if (c * 32 + e + 1 > col_lim) s1 = -INFINITY;
-          }
-          const float p0 = fast_exp2(fmaf(s0, a.scale_log2, -m_used));
-          const float p1 = fast_exp2(fmaf(s1, a.scale_log2, -m_used));
-          lsum += p0 + p1;
-          pk[e >> 1] = pack2<T>(p0, p1);
+          const float2 t2 = ffma2(make_float2(__uint_as_float(sv[c * 32 + e]), __uint_as_float(sv[c * 32 + e + 1])), sc2, nm2);
+          const float2 p2 = make_float2(fast_exp2(t2.x), fast_exp2(t2.y));
+          ls2[(e >> 1) & 1] = fadd2(ls2[(e >> 1) & 1], p2);
+          pk[e >> 1] = pack2<T>(p2.x, p2.y);
         }
         ptx::tmem_st_x16(tmem_s + c * 16, pk);
       }
+      const float lsum = (ls2[0].x + ls2[0].y) + (ls2[1].x + ls2[1].y);
       l += lsum;
+      }  // warp_active
 
       // Keys at or beyond kv_len (tail of the last page, pages that do not exist) carry P == 0, but their V rows are
       // whatever the pool / stale shared memory holds; zero them so 0 * NaN cannot reach O.
@@ -333,12 +349,24 @@ paged_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     const float inv_l = 1.f / l;
     T* orow = static_cast<T*>(a.out) + static_cast<int64_t>(q_start + i) * a.out_row_stride +
               (kvh * a.group + g) * kHeadDim;
+    const int64_t pidx = (static_cast<int64_t>(q_start + i) * a.n_qo_heads + (kvh * a.group + g)) * a.n_splits + sp;
+    if (a.n_splits > 1 && row_valid) {
+      a.part_ml[pidx * 2 + 0] = m_used;
+      a.part_ml[pidx * 2 + 1] = l;
+    }
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       uint32_t v[32];
       ptx::tmem_ld_x32(tmem_o + c * 32, v);
       ptx::tmem_wait_ld();
-      if (row_valid) {
+      if (a.n_splits > 1) {
+        if (row_valid) {
+          float4* dst = reinterpret_cast<float4*>(a.part_o + pidx * kHeadDim + c * 32);
+#pragma unroll
+          for (int e = 0; e < 32; e += 4)
+            dst[e >> 2] = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+        }
+      } else if (row_valid) {
 #pragma unroll
         for (int e = 0; e < 32; e += 8) {
           uint4 w;
@@ -458,13 +486,19 @@ static int launch_tc_t(const HiAttnArgs& args, const TcArgs& a, const CUtensorMa
     configured = true;
   }
   const int q_tiles = (args.max_q_len + a.tq - 1) / a.tq;
-  const dim3 grid(q_tiles, args.n_kv_heads, args.n_seqs);
+  const dim3 grid(q_tiles * a.n_splits, args.n_kv_heads, args.n_seqs);
   timing_mark_start(stream);
   paged_attn_tc_kernel<T, NST><<<grid, kTcThreads, L::kDynamicBytes, stream>>>(mq, mk, mv, a);
   timing_mark_stop(stream);
   note_launch();
   HI_CUDA(cudaGetLastError());
   return HI_OK;
+}
+
+int64_t tc_workspace_bytes() {
+  // split-KV partials: rows * heads * n_splits entries of (128 + 2) floats; splits are only used while the launch has
+  // fewer than kSplitTargetCtas CTAs, which bounds rows*heads*n_splits by about 2 * 128 * kSplitTargetCtas.
+  return static_cast<int64_t>(2) * 128 * 600 * (kHeadDim + 2) * 4;
 }
 
 int launch_attn_tc(const HiAttnArgs& args, cudaStream_t stream) {
@@ -490,6 +524,31 @@ int launch_attn_tc(const HiAttnArgs& args, cudaStream_t stream) {
     a.serialize = (env != nullptr && env[0] == '1') ? 1 : 0;
   }
 
+  // ---- split-KV: only for launches too small to fill the machine (decode batches, a few long prompts) ---------------
+  constexpr int kSplitTargetCtas = 592;  // 148 SMs x 4
+  constexpr int kMinTilesPerSplit = 2;   // never finer than 256 tokens
+  const int q_tiles = (args.max_q_len + a.tq - 1) / a.tq;
+  const int64_t base_ctas = static_cast<int64_t>(q_tiles) * args.n_kv_heads * args.n_seqs;
+  const int max_kv_tiles = (args.max_kv_len + kTileN - 1) / kTileN;
+  int n_splits = 1;
+  if (base_ctas < kSplitTargetCtas) {
+    n_splits = static_cast<int>((kSplitTargetCtas + base_ctas - 1) / base_ctas);
+    const int max_splits = (max_kv_tiles + kMinTilesPerSplit - 1) / kMinTilesPerSplit;
+    if (n_splits > max_splits) n_splits = max_splits;
+    if (const char* env = getenv("HI_TC_SPLITS")) n_splits = atoi(env);  // tuning override
+    if (n_splits < 1) n_splits = 1;
+    // shrink to what the workspace can hold
+    const int64_t per_split = static_cast<int64_t>(args.n_tokens) * args.n_qo_heads * (kHeadDim + 2) * 4;
+    while (n_splits > 1 && (args.workspace == nullptr || per_split * n_splits > args.workspace_bytes)) --n_splits;
+  }
+  a.tiles_per_split = (max_kv_tiles + n_splits - 1) / n_splits;
+  a.n_splits = (max_kv_tiles + a.tiles_per_split - 1) / a.tiles_per_split;
+  if (a.n_splits > 1) {
+    const int64_t entries = static_cast<int64_t>(args.n_tokens) * args.n_qo_heads * a.n_splits;
+    a.part_o = static_cast<float*>(args.workspace);
+    a.part_ml = a.part_o + entries * kHeadDim;
+  }
+
   CUtensorMap mq, mk, mv;
   int rc = make_map(&mq, args.dtype, args.q, args.n_tokens, args.n_qo_heads, args.q_row_stride, a.group, a.tq);
   if (rc != HI_OK) return rc;
@@ -499,8 +558,34 @@ int launch_attn_tc(const HiAttnArgs& args, cudaStream_t stream) {
   rc = pool_map(&mv, args.dtype, args.value_cache, n_slots, args.n_kv_heads, args.block_size);
   if (rc != HI_OK) return rc;
 
-  if (args.dtype == HI_BF16) return launch_tc_t<__nv_bfloat16, 1>(args, a, mq, mk, mv, stream);
-  return launch_tc_t<__half, 1>(args, a, mq, mk, mv, stream);
+  // Decode-only batches stream KV once per CTA: one CTA per SM with a 3-deep K/V ring keeps ~190 KiB of TMA loads in
+  // flight.  Batches with prefill rows are MMA/softmax bound: two CTAs per SM overlap each other's phases.
+  int stages = (args.max_q_len == 1) ? 3 : 1;
+  if (const char* env = getenv("HI_TC_STAGES")) stages = atoi(env);
+  if (args.dtype == HI_BF16) {
+    rc = stages == 3 ? launch_tc_t<__nv_bfloat16, 3>(args, a, mq, mk, mv, stream)
+       : stages == 2 ? launch_tc_t<__nv_bfloat16, 2>(args, a, mq, mk, mv, stream)
+                     : launch_tc_t<__nv_bfloat16, 1>(args, a, mq, mk, mv, stream);
+  } else {
+    rc = stages == 3 ? launch_tc_t<__half, 3>(args, a, mq, mk, mv, stream)
+       : stages == 2 ? launch_tc_t<__half, 2>(args, a, mq, mk, mv, stream)
+                     : launch_tc_t<__half, 1>(args, a, mq, mk, mv, stream);
+  }
+  if (rc != HI_OK || a.n_splits == 1) return rc;
+
+  SimtArgs m{};
+  m.out = args.out;
+  m.out_row_stride = args.out_row_stride;
+  m.q_cu = args.q_cu_seq_lens;
+  m.kv_cu = args.kv_cu_seq_lens;
+  m.n_seqs = args.n_seqs;
+  m.n_tokens = args.n_tokens;
+  m.n_qo_heads = args.n_qo_heads;
+  m.n_chunks = a.n_splits;
+  m.chunk_tiles = a.tiles_per_split * (kTileN / 16);
+  m.part_o = a.part_o;
+  m.part_ml = a.part_ml;
+  return launch_merge_partials(m, args.dtype, kHeadDim, stream);
 }
 
 }  // namespace hi

@@ -205,6 +205,18 @@ def test_large_score_magnitudes_stay_finite():
     check_batch(batch, paths_for(128, torch.bfloat16), "large scores")
 
 
+@pytest.mark.parametrize("stages", ["1", "2", "3"])
+@pytest.mark.parametrize("splits", ["1", "2", "3", "8"])
+def test_tile_kernel_split_kv_and_ring_depth_variants(monkeypatch, splits, stages):
+    """Split-KV partials + merge and every K/V ring depth of the tile kernel give the same answer (tuning overrides)."""
+    monkeypatch.setenv("HI_TC_SPLITS", splits)
+    monkeypatch.setenv("HI_TC_STAGES", stages)
+    seq_lens = [(1, 1300), (1, 17), (1, 128), (1, 129), (1, 640), (3, 700), (1, 2049)]
+    for heads in ((28, 4), (8, 8)):
+        batch = make_batch(seq_lens, heads[0], heads[1], 128, 16, dtype=torch.bfloat16, seed=40)
+        check_batch(batch, [TC], f"splits={splits} stages={stages} heads={heads}")
+
+
 # ---- full-size configs: sampled oracle rows + size-independent properties -------------------------------------------------
 def _sampled_check(batch_dev, sample_seqs, path, what):
     """Oracle on a subset of sequences (copied to CPU); the kernels ran on the whole batch."""
