@@ -63,10 +63,15 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=self.file, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
+            return
+        # nvidia-smi needs a moment to attach; wait for its first line so the timed region is covered
+        t0 = time.time()
+        while time.time() - t0 < 3.0 and os.path.getsize(self.file.name) == 0:
+            time.sleep(0.05)
 
     def stop(self) -> dict:
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
@@ -253,6 +258,13 @@ def run_ours(args) -> None:
     h2d = q_host.numel() * 2 + k_host.numel() * 2 + v_host.numel() * 2 + 4 * (
         len(batch.q_cu_seq_lens) + len(batch.kv_cu_seq_lens) + BATCH + len(batch.new_cache_slots) + len(batch.block_tables) + len(batch.cu_blocks_lens))
     d2h = o_host.numel() * 2
+    # the timed region is ~10 ms; keep the identical step running for ~1.5 s so nvidia-smi (100 ms period) sees the clocks
+    # the kernels actually run at (same kernels, same inputs; not part of any reported time)
+    t_end = time.time() + 1.5
+    while time.time() < t_end:
+        for _ in range(50):
+            step()
+        torch.cuda.synchronize(dev)
     clocks = sampler.stop() if rank == 0 else {}
 
     # ---- migration extra: KV-migrate GB/s (same metric family, BASELINE.json) -----------------------------------------------
@@ -274,7 +286,7 @@ def run_ours(args) -> None:
         tp = ROOT / "profiles" / "traffic.json"
         if tp.exists():
             try:
-                traffic = json.loads(tp.read_text()).get("paged_attn_simt_kernel_dram_bytes_per_launch")
+                traffic = json.loads(tp.read_text()).get("paged_attn_stream_kernel_dram_bytes_per_launch")
             except Exception:
                 traffic = None
         cpu = cpu_reference_run(8, 5, 2)
@@ -283,7 +295,7 @@ def run_ours(args) -> None:
             "ms_per_step": ms_total_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "tokens_per_step_per_gpu": BATCH, "l2": "inputs_larger_than_l2 (2.1 GB of KV per step vs 126 MB L2)",
-                       "parallelism": f"sequences sharded, {world} independent rank(s), no collective", "kernel": "paged_attn_simt_kernel<bf16,128,1> + merge_partials_kernel + scatter_rows_kernel"},
+                       "parallelism": f"sequences sharded, {world} independent rank(s), no collective", "kernel": "scatter_rows_kernel + paged_attn_stream_kernel<bf16,128,1> (cp.async split-KV) + merge_partials_kernel"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0, "kernel_ms": kernel_ms_max,
                          "algorithmic_bytes_per_launch": BATCH * ALGO_BYTES_PER_TOKEN},

@@ -18,8 +18,8 @@ CSRC = PKG_DIR / "csrc"
 LIB_DIR = PKG_DIR / "lib"
 LIB_PATH = LIB_DIR / "libhi_b200.so"
 OBJ_DIR = CSRC / "build"
-SOURCES = ["api.cu", "scatter.cu", "attn_simt.cu", "attn_tc.cu", "migrate.cu"]
-HEADERS = ["common.cuh", "ptx_sm100.cuh", "attn_common.cuh", "../../include/hi_b200.h"]
+SOURCES = ["api.cu", "scatter.cu", "attn_simt.cu", "attn_tc.cu", "attn_decode_tc.cu", "migrate.cu"]
+HEADERS = ["common.cuh", "ptx_sm100.cuh", "attn_common.cuh", "tma_maps.h", "../../include/hi_b200.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -40,6 +40,8 @@ void reset_launch_count() { g_launches = 0; }
 int launch_attn_simt(const HiAttnArgs& args, cudaStream_t stream);
 int launch_attn_tc(const HiAttnArgs& args, cudaStream_t stream);
 bool attn_tc_supported(const HiAttnArgs& args);
+int launch_attn_decode_tc(const HiAttnArgs& args, cudaStream_t stream);
+bool attn_decode_tc_supported(const HiAttnArgs& args);
 int64_t simt_workspace_bytes(int head_dim);
 int64_t tc_workspace_bytes();
 
@@ -88,16 +90,27 @@ extern "C" int hi_paged_attention(const HiAttnArgs* p, void* stream_) {
   if (const char* env = getenv("HI_ATTN_PATH")) {  // test / profiling override: "simt" or "tc"
     if (env[0] == 's') path = HI_ATTN_SIMT;
     if (env[0] == 't') path = HI_ATTN_TCGEN05;
+    if (env[0] == 'd') path = HI_ATTN_TCGEN05_DECODE;
   }
   if (path == HI_ATTN_AUTO) {
     // Rows with q_len > 1 are dense contractions: tensor pipe.  Pure decode batches stream KV once per row: the
     // split-KV kernel keeps more bytes in flight and balances ragged lengths.
-    // Grouped models (>= 4 query heads per KV head) also decode on the tile kernel: the heads of a group are packed
-    // into the MMA M dimension, which the CUDA-core kernel can only emulate with G FMAs per KV element.
+    // Grouped models (>= 4 query heads per KV head) decode on tensor cores too: the CUDA-core kernel needs G FMAs per KV
+    // element and stops being memory-bound.  Decode-only batches take the swapped-operand kernel (tokens on the MMA M
+    // side, one row per CTA); batches with prefill rows take the tile kernel for every row.
     const int group = a.n_qo_heads / a.n_kv_heads;
-    path = ((a.max_q_len > 1 || group >= 4) && attn_tc_supported(a)) ? HI_ATTN_TCGEN05 : HI_ATTN_SIMT;
+    if (a.max_q_len > 1) {
+      path = attn_tc_supported(a) ? HI_ATTN_TCGEN05 : HI_ATTN_SIMT;
+    } else if (group >= 4 && attn_decode_tc_supported(a)) {
+      path = HI_ATTN_TCGEN05_DECODE;
+    } else if (group >= 4 && attn_tc_supported(a)) {
+      path = HI_ATTN_TCGEN05;
+    } else {
+      path = HI_ATTN_SIMT;
+    }
   }
   if (path == HI_ATTN_TCGEN05) return launch_attn_tc(a, stream);
+  if (path == HI_ATTN_TCGEN05_DECODE) return launch_attn_decode_tc(a, stream);
   if (path == HI_ATTN_SIMT) return launch_attn_simt(a, stream);
   set_error("paged_attention: unknown path %d", path);
   return HI_ERR_INVALID_ARGUMENT;

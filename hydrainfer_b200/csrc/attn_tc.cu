@@ -35,6 +35,7 @@
 #include "attn_common.cuh"
 #include "common.cuh"
 #include "ptx_sm100.cuh"
+#include "tma_maps.h"
 
 namespace hi {
 
@@ -262,23 +263,32 @@ paged_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       ptx::tc_fence_after_sync();
       if (warp_active) {
 
-      // The row's 128 scores live in registers for the whole step (one TMEM read), the mask is only evaluated on tiles
-      // that touch the causal diagonal or the end of the sequence, and the arithmetic uses the 3-input max and the
-      // packed fp32x2 FMA/ADD of sm_100 so that MUFU.EX2 (16 lanes/clk/SM) is the only saturated pipe.
-      uint32_t sv[128];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) ptx::tmem_ld_x32(tmem_s + c * 32, reinterpret_cast<uint32_t(&)[32]>(sv[32 * c]));
-      ptx::tmem_wait_ld();
-      if (__any_sync(0xffffffffu, need_mask)) {
-#pragma unroll
-        for (int e = 0; e < 128; ++e)
-          if (e > col_lim) sv[e] = 0xff800000u;  // -inf
-      }
+      // Two sweeps over the row's 128 scores, 64 columns per TMEM round trip.  The mask is only evaluated on tiles that
+      // touch the causal diagonal or the end of the sequence, and the arithmetic uses the 3-input max and the packed
+      // fp32x2 FMA/ADD of sm_100, so that MUFU.EX2 (16 lanes/clk/SM) is the only saturated pipe.
+      const bool mask_tile = __any_sync(0xffffffffu, need_mask);
+      uint32_t va[32], vb[32];
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int e = 0; e < 128; e += 8) {
+      for (int h = 0; h < 2; ++h) {
+        ptx::tmem_ld_x32(tmem_s + h * 64, va);
+        ptx::tmem_ld_x32(tmem_s + h * 64 + 32, vb);
+        ptx::tmem_wait_ld();
+        if (mask_tile) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) mx4[u] = fmax3(mx4[u], __uint_as_float(sv[e + 2 * u]), __uint_as_float(sv[e + 2 * u + 1]));
+          for (int e = 0; e < 32; ++e) {
+            if (h * 64 + e > col_lim) va[e] = 0xff800000u;  // -inf
+            if (h * 64 + 32 + e > col_lim) vb[e] = 0xff800000u;
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 32; e += 8) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            mx4[u] = fmax3(mx4[u], __uint_as_float(va[e + 2 * u]), __uint_as_float(va[e + 2 * u + 1]));
+            mx4[u] = fmax3(mx4[u], __uint_as_float(vb[e + 2 * u]), __uint_as_float(vb[e + 2 * u + 1]));
+          }
+        }
       }
       const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float mxs = mx * a.scale_log2;
@@ -292,30 +302,41 @@ paged_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         m_used = m_new;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          uint32_t v[32];
-          ptx::tmem_ld_x32(tmem_o + c * 32, v);
+          ptx::tmem_ld_x32(tmem_o + c * 32, va);
           ptx::tmem_wait_ld();
 #pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
-          ptx::tmem_st_x32(tmem_o + c * 32, v);
+          for (int e = 0; e < 32; ++e) va[e] = __float_as_uint(__uint_as_float(va[e]) * alpha);
+          ptx::tmem_st_x32(tmem_o + c * 32, va);
         }
       }
 
-      // P = exp2(S * scale - m) as 16-bit pairs, written over S
+      // P = exp2(S * scale - m) as 16-bit pairs, written over S (P columns [16c, 16c+16) only cover S columns already read)
       const float2 sc2 = make_float2(a.scale_log2, a.scale_log2);
       const float2 nm2 = make_float2(-m_used, -m_used);
       float2 ls2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      auto exp_pack_store = [&](uint32_t (&v)[32], int c) {
         uint32_t pk[16];
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
-          const float2 t2 = ffma2(make_float2(__uint_as_float(sv[c * 32 + e]), __uint_as_float(sv[c * 32 + e + 1])), sc2, nm2);
+          float s0 = __uint_as_float(v[e]), s1 = __uint_as_float(v[e + 1]);
+          if (mask_tile) {
+            if (c * 32 + e > col_lim) s0 = -INFINITY;
+            if (c * 32 + e + 1 > col_lim) s1 = -INFINITY;
+          }
+          const float2 t2 = ffma2(make_float2(s0, s1), sc2, nm2);
           const float2 p2 = make_float2(fast_exp2(t2.x), fast_exp2(t2.y));
           ls2[(e >> 1) & 1] = fadd2(ls2[(e >> 1) & 1], p2);
           pk[e >> 1] = pack2<T>(p2.x, p2.y);
         }
         ptx::tmem_st_x16(tmem_s + c * 16, pk);
+      };
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        ptx::tmem_ld_x32(tmem_s + h * 64, va);
+        ptx::tmem_ld_x32(tmem_s + h * 64 + 32, vb);
+        ptx::tmem_wait_ld();
+        exp_pack_store(va, 2 * h);
+        exp_pack_store(vb, 2 * h + 1);
       }
       const float lsum = (ls2[0].x + ls2[0].y) + (ls2[1].x + ls2[1].y);
       l += lsum;
@@ -411,7 +432,7 @@ static int get_encode_fn(EncodeTiledFn* out) {
 }
 
 // 3-D map over [rows, heads, 128] 16-bit elements; box = {64 dims, box_heads, box_rows}, 128B swizzle.
-static int make_map(CUtensorMap* map, int dtype, const void* base, int64_t rows, int64_t heads, int64_t row_stride_elems,
+int make_map(CUtensorMap* map, int dtype, const void* base, int64_t rows, int64_t heads, int64_t row_stride_elems,
                     int box_heads, int box_rows) {
   EncodeTiledFn encode = nullptr;
   const int rc = get_encode_fn(&encode);
@@ -450,7 +471,7 @@ struct MapKeyHash {
 static std::mutex g_map_mu;
 static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_pool_maps;
 
-static int pool_map(CUtensorMap* out, int dtype, const void* base, int64_t n_slots, int heads, int block_size) {
+int pool_map(CUtensorMap* out, int dtype, const void* base, int64_t n_slots, int heads, int block_size) {
   const MapKey key{base, n_slots, heads, dtype, block_size};
   std::lock_guard<std::mutex> lock(g_map_mu);
   auto it = g_pool_maps.find(key);
@@ -558,9 +579,9 @@ int launch_attn_tc(const HiAttnArgs& args, cudaStream_t stream) {
   rc = pool_map(&mv, args.dtype, args.value_cache, n_slots, args.n_kv_heads, args.block_size);
   if (rc != HI_OK) return rc;
 
-  // Decode-only batches stream KV once per CTA: one CTA per SM with a 3-deep K/V ring keeps ~190 KiB of TMA loads in
-  // flight.  Batches with prefill rows are MMA/softmax bound: two CTAs per SM overlap each other's phases.
-  int stages = (args.max_q_len == 1) ? 3 : 1;
+  // Ring depth 1 = two co-resident CTAs per SM whose QK / softmax / PV phases overlap each other; measured better than
+  // one CTA per SM with a 2- or 3-deep ring for both prefill and decode tiles (profiles/r01_notes.md).
+  int stages = 1;
   if (const char* env = getenv("HI_TC_STAGES")) stages = atoi(env);
   if (args.dtype == HI_BF16) {
     rc = stages == 3 ? launch_tc_t<__nv_bfloat16, 3>(args, a, mq, mk, mv, stream)

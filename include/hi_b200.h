@@ -41,7 +41,8 @@ typedef enum HiDtype { HI_F32 = 0, HI_F16 = 1, HI_BF16 = 2 } HiDtype;
 typedef enum HiAttnPath {
   HI_ATTN_AUTO = 0,
   HI_ATTN_SIMT = 1,   /* split-KV CUDA-core kernel (decode rows; also the generic any-shape path) */
-  HI_ATTN_TCGEN05 = 2 /* tcgen05/TMEM tile kernel (prefill, chunked prefill, GQA-packed decode) */
+  HI_ATTN_TCGEN05 = 2, /* tcgen05/TMEM tile kernel (prefill, chunked prefill, GQA-packed decode) */
+  HI_ATTN_TCGEN05_DECODE = 3 /* tcgen05 swapped-operand kernel: one query row x one KV head per CTA (grouped decode) */
 } HiAttnPath;
 
 const char* hi_last_error(void);

@@ -12,7 +12,7 @@ from oracle import paged_kv_oracle as oracle
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-SIMT, TC = 1, 2
+SIMT, TC, DEC = 1, 2, 3
 
 
 def tolerances(dtype):
@@ -72,11 +72,18 @@ def check_batch(batch, paths, what=""):
     return fp32
 
 
-def paths_for(head_dim, dtype, block_size=16):
+def paths_for(head_dim, dtype, block_size=16, group=1):
+    """Every kernel path that covers the shape: 1 split-KV CUDA-core, 2 tcgen05 tile, 3 tcgen05 swapped-operand decode, 0 auto."""
     import os
     if os.environ.get("HI_TEST_SKIP_TC") == "1":  # dev switch: validate the split-KV kernel alone
         return [SIMT]
-    return [SIMT, TC, 0] if tc_supported(head_dim, dtype, block_size) else [SIMT, 0]
+    if not tc_supported(head_dim, dtype, block_size):
+        return [SIMT, 0]
+    return [SIMT, TC, DEC, 0] if group <= 16 else [SIMT, TC, 0]
+
+
+def paths_of(batch):
+    return paths_for(batch.head_dim, batch.dtype, batch.block_size, batch.n_qo_heads // batch.n_kv_heads)
 
 
 # ---- golden fixtures: the reference's own outputs ---------------------------------------------------------------------
@@ -85,7 +92,7 @@ def test_golden_layer_forward(golden_attention):
     from hydrainfer_b200.layer import AttentionParametersBuilder, CausalGroupedQueryPageAttention, CausalGroupedQueryPageAttentionConfig
     from hydrainfer_b200.memory import KVCache
     g = golden_attention
-    for path in paths_for(g.head_dim, g.dtype, g.block_size):
+    for path in paths_for(g.head_dim, g.dtype, g.block_size, g.n_qo_heads // g.n_kv_heads):
         kc, vc = g.key_cache.to(DEV), g.value_cache.to(DEV)
         builder = AttentionParametersBuilder(g.n_qo_heads, g.n_kv_heads, g.head_dim, g.block_size, torch.device(DEV))
         for req in g.requests():
@@ -118,7 +125,7 @@ def test_golden_layer_forward(golden_attention):
 def test_reference_grid(num_heads, head_size, dtype):
     seq_lens = [(1, 100), (15, 15), (111, 234), (1, 1024)]  # tests/layer/test_attention.py:42
     batch = make_batch(seq_lens, num_heads[0], num_heads[1], head_size, 16, n_blocks=120, dtype=dtype, seed=42)
-    check_batch(batch, paths_for(head_size, dtype), f"grid heads={num_heads} d={head_size}")
+    check_batch(batch, paths_of(batch), f"grid heads={num_heads} d={head_size}")
 
 
 @pytest.mark.parametrize("dtype", [torch.float32])
@@ -135,7 +142,7 @@ def test_ragged_decode(heads):
     lens = [1, 2, 15, 16, 17, 31, 32, 33, 127, 128, 129, 255, 256, 257, 600, 1025]
     lens += torch.randint(1, 900, (8,), generator=g).tolist()
     batch = make_batch([(1, L) for L in lens], heads[0], heads[1], 128, 16, dtype=torch.bfloat16, seed=7)
-    check_batch(batch, paths_for(128, torch.bfloat16), f"ragged decode heads={heads}")
+    check_batch(batch, paths_of(batch), f"ragged decode heads={heads}")
 
 
 @pytest.mark.parametrize("heads", [(8, 8), (28, 4), (16, 2)])
@@ -143,21 +150,21 @@ def test_chunked_prefill_shapes(heads):
     # q < kv: the bottom-right aligned mask; q tiles that start mid-sequence; kv not a multiple of the 128-token tile
     seq_lens = [(128, 128), (129, 300), (64, 1000), (200, 200), (1, 77), (37, 165), (256, 513)]
     batch = make_batch(seq_lens, heads[0], heads[1], 128, 16, dtype=torch.bfloat16, seed=9)
-    check_batch(batch, paths_for(128, torch.bfloat16), f"chunked prefill heads={heads}")
+    check_batch(batch, paths_of(batch), f"chunked prefill heads={heads}")
 
 
 def test_mixed_batch_qwen_geometry_fp16_fused():
     # config 3 flavour (28 q / 4 kv heads): decode rows + chunked prefill rows in one call, q a strided qkv slice
     seq_lens = [(1, 300), (1, 45), (512, 2048), (1, 1999), (300, 300), (1, 16)]
     batch = make_batch(seq_lens, 28, 4, 128, 16, dtype=torch.float16, seed=13, fused_qkv=True)
-    check_batch(batch, paths_for(128, torch.float16), "mixed qwen fp16")
+    check_batch(batch, paths_of(batch), "mixed qwen fp16")
 
 
 @pytest.mark.parametrize("block_size", [8, 32, 64])
 def test_other_block_sizes(block_size):
     seq_lens = [(1, 70), (50, 131), (1, 5), (130, 130)]
     batch = make_batch(seq_lens, 8, 2, 128, block_size, dtype=torch.bfloat16, seed=21)
-    check_batch(batch, paths_for(128, torch.bfloat16, block_size), f"block_size={block_size}")
+    check_batch(batch, paths_of(batch), f"block_size={block_size}")
 
 
 def test_small_block_size_simt_only():
@@ -167,7 +174,7 @@ def test_small_block_size_simt_only():
 
 def test_single_token_single_sequence():
     batch = make_batch([(1, 1)], 8, 8, 128, 16, dtype=torch.bfloat16, seed=2)
-    fp32 = check_batch(batch, paths_for(128, torch.bfloat16), "one token")
+    fp32 = check_batch(batch, paths_of(batch), "one token")
     # softmax over one key is 1: the output is the value row itself
     t = 0
     v_row = batch.value.view(1, 8, 128).float().reshape(1, -1)
@@ -190,7 +197,7 @@ def test_garbage_in_unused_slots_does_not_leak():
     poison_k.view(-1, 2, 128)[~used] = float("nan")
     poison_v.view(-1, 2, 128)[~used] = float("inf")
     q3 = batch.query.to(DEV).view(t, 8, 128)
-    for path in paths_for(128, torch.bfloat16):
+    for path in paths_of(batch):
         out = run_attention(q3, poison_k.to(DEV), poison_v.to(DEV), batch.q_cu_seq_lens, batch.kv_cu_seq_lens, batch.block_tables,
                             batch.cu_blocks_lens, batch.q_max, batch.kv_max, 128, path)
         assert_close_to_fp32(out.reshape(t, -1), fp32, torch.bfloat16, f"poisoned pool path={path}")
@@ -202,7 +209,7 @@ def test_large_score_magnitudes_stay_finite():
     batch.query.mul_(6.0)
     batch.key_cache.mul_(4.0)
     batch.key.mul_(4.0)
-    check_batch(batch, paths_for(128, torch.bfloat16), "large scores")
+    check_batch(batch, paths_of(batch), "large scores")
 
 
 @pytest.mark.parametrize("stages", ["1", "2", "3"])
@@ -211,10 +218,11 @@ def test_tile_kernel_split_kv_and_ring_depth_variants(monkeypatch, splits, stage
     """Split-KV partials + merge and every K/V ring depth of the tile kernel give the same answer (tuning overrides)."""
     monkeypatch.setenv("HI_TC_SPLITS", splits)
     monkeypatch.setenv("HI_TC_STAGES", stages)
+    monkeypatch.setenv("HI_DEC_SPLITS", splits)
     seq_lens = [(1, 1300), (1, 17), (1, 128), (1, 129), (1, 640), (3, 700), (1, 2049)]
     for heads in ((28, 4), (8, 8)):
         batch = make_batch(seq_lens, heads[0], heads[1], 128, 16, dtype=torch.bfloat16, seed=40)
-        check_batch(batch, [TC], f"splits={splits} stages={stages} heads={heads}")
+        check_batch(batch, [TC, DEC], f"splits={splits} stages={stages} heads={heads}")
 
 
 # ---- full-size configs: sampled oracle rows + size-independent properties -------------------------------------------------
@@ -255,14 +263,14 @@ def test_config3_qwen_mixed_full_size():
     lens = torch.randint(256, 8193, (48,), generator=g).tolist()
     seq_lens = [(1, L) for L in lens] + [(512, 512), (512, 2048), (512, 4096), (512, 8192)]
     batch = make_batch(seq_lens, 28, 4, 128, 16, dtype=torch.bfloat16, device=DEV, gen_device=DEV, seed=3)
-    for path in paths_for(128, torch.bfloat16):
+    for path in paths_of(batch):
         _sampled_check(batch, [0, 17, 48, 49, 51], path, "cfg3")
 
 
 def test_config4_qwen72b_shape_decode():
     # BASELINE config 4 per-GPU shard at N=8: 64/8 heads, 32 sequences of ctx 4096
     batch = make_batch([(1, 4096)] * 32, 64, 8, 128, 16, dtype=torch.bfloat16, device=DEV, gen_device=DEV, seed=4)
-    for path in paths_for(128, torch.bfloat16):
+    for path in paths_of(batch):
         _sampled_check(batch, [0, 15, 31], path, "cfg4")
 
 
@@ -274,7 +282,7 @@ def test_duplicate_sequences_give_identical_rows():
     q = batch.query.clone()
     q[1] = q[0]
     q3 = q.to(DEV).view(2, 32, 128)
-    for path in paths_for(128, torch.bfloat16):
+    for path in paths_of(batch):
         out = run_attention(q3, batch.key_cache.to(DEV), batch.value_cache.to(DEV), [0, 1, 2], [0, 900, 1800], tables,
                             [0, len(table), 2 * len(table)], 1, 900, 128, path)
         assert torch.equal(out[0], out[1]), f"path={path}"

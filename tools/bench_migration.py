@@ -105,7 +105,7 @@ def main():
                 ok = True
                 if receiver:
                     if world == 1:
-                        ok = bool(torch.equal(dst_pool[:, :, dst_bt], pool[:, :, src_bt]))
+                        ok = bool(torch.equal(dst_pool[:, :, dst_bt].view(torch.int16), pool[:, :, src_bt].view(torch.int16)))
                     else:
                         # the source pool content is reproducible only on its owner: fetch it over NCCL for the check
                         pass
@@ -116,7 +116,7 @@ def main():
                         if receiver:
                             buf = torch.empty_like(pool[:, :, :chk])
                             dist.recv(buf, src=src_rank)
-                            ok = bool(torch.equal(dst_pool[:, :, dst_bt[:chk]], buf))
+                            ok = bool(torch.equal(dst_pool[:, :, dst_bt[:chk]].view(torch.int16), buf.view(torch.int16)))
                         elif rank + 1 < world:
                             dist.send(pool[:, :, src_bt[:chk]].contiguous(), dst=rank + 1)
                     else:
@@ -127,7 +127,7 @@ def main():
                         else:
                             buf = torch.empty_like(pool[:, :, :chk])
                             dist.recv(buf, src=0)
-                            ok = bool(torch.equal(dst_pool[:, :, dst_bt[:chk]], buf))
+                            ok = bool(torch.equal(dst_pool[:, :, dst_bt[:chk]].view(torch.int16), buf.view(torch.int16)))
                 okt = torch.tensor([1 if ok else 0], device=dev)
                 if world > 1:
                     dist.all_reduce(okt, op=dist.ReduceOp.MIN)

@@ -23,6 +23,15 @@ GROUPS = {
         ("1 head q16 kv40", [(16, 40)], 1, 1),
         ("1 head q300 kv300", [(300, 300)], 1, 1),
     ]),
+    "dec": dict(path=3, cases=[
+        ("gqa8 one row kv128", [(1, 128)], 8, 1),
+        ("gqa8 one row kv16", [(1, 16)], 8, 1),
+        ("gqa8 one row kv300", [(1, 300)], 8, 1),
+        ("gqa4 ragged", [(1, 100), (1, 15), (1, 234), (1, 1024)], 8, 2),
+        ("gqa7 qwen mixed", [(1, 300), (40, 170), (1, 17)], 28, 4),
+        ("gqa16", [(1, 2000)] * 2, 32, 2),
+        ("mha", [(1, 500), (3, 140)], 4, 4),
+    ]),
     "tc_gqa": dict(path=2, cases=[
         ("mha 8 heads mixed", [(1, 100), (15, 15), (111, 234), (1, 1024)], 8, 8),
         ("gqa4", [(1, 100), (15, 15), (111, 234), (1, 1024)], 8, 2),
@@ -74,7 +83,7 @@ if __name__ == "__main__":
         run_group(sys.argv[1])
     else:
         for g in GROUPS:
-            for env_extra in ({},) if not g.startswith("tc") else ({}, {"HI_TC_SERIALIZE": "1"}):
+            for env_extra in ({},):
                 tag = g + ("+serialize" if env_extra else "")
                 print(f"===== {tag}", flush=True)
                 try:
