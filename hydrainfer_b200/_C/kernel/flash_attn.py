@@ -63,7 +63,8 @@ def mha_varlen_fwd(out: Tensor, q: Tensor, k: Tensor, v: Tensor, cu_seqlens_q: T
         n_seqs=n_seqs, n_tokens=n_tokens, max_q_len=int(max_seqlen_q), max_kv_len=int(max_seqlen_k),
         n_qo_heads=n_qo_heads, n_kv_heads=n_kv_heads, head_dim=head_dim, block_size=block_size, n_blocks=n_blocks,
         dtype=_lib.dtype_code(q.dtype), softmax_scale=float(softmax_scale),
-        workspace=ws.data_ptr(), workspace_bytes=ws.numel(), path=int(path), device=dev.index or 0)
+        workspace=ws.data_ptr(), workspace_bytes=ws.numel(), path=int(path), device=dev.index or 0,
+        kv_blocks_hint=int(block_table_.numel()))
     _lib.check(_lib.lib.hi_paged_attention(args, _lib.current_stream_ptr(dev)))
 
 

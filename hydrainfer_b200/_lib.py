@@ -31,7 +31,7 @@ class HiAttnArgs(Structure):
         ("n_blocks", c_int64),
         ("dtype", c_int32), ("softmax_scale", c_float),
         ("workspace", c_void_p), ("workspace_bytes", c_int64),
-        ("path", c_int32), ("device", c_int32), ("reserved", c_int32 * 4),
+        ("path", c_int32), ("device", c_int32), ("kv_blocks_hint", c_int32), ("reserved", c_int32 * 3),
     ]
 
 

@@ -396,12 +396,24 @@ int launch_attn_decode_tc(const HiAttnArgs& args, cudaStream_t stream) {
   a.block_size = args.block_size;
   a.scale_log2 = args.softmax_scale * 1.4426950408889634f;
 
-  // split-KV: enough CTAs to fill 148 SMs x 3 resident CTAs a few times over, never finer than 256 tokens
-  constexpr int kTargetCtas = 148 * 3 * 4;
-  constexpr int kMinTilesPerSplit = 2;
+  // split-KV.  Measured on B200 (profiles/r01_notes.md): with >= 1 CTA per SM and sequences of similar length the kernel
+  // already streams at the HBM roofline and splitting only adds tail waves and merge traffic; ragged batches (longest
+  // sequence well above the mean) and launches with fewer CTAs than SMs want ~600 CTAs of equal work.
+  constexpr int kMinTilesPerSplit = 2;  // never finer than 256 tokens
   const int64_t base_ctas = static_cast<int64_t>(args.n_tokens) * args.n_kv_heads;
   const int max_tiles = (args.max_kv_len + kDecTile - 1) / kDecTile;
-  int n_splits = static_cast<int>((kTargetCtas + base_ctas - 1) / base_ctas);
+  // mean tiles per row from the block-table size (rows of one sequence share its blocks: exact for decode batches)
+  double mean_tiles = static_cast<double>(max_tiles);
+  if (args.kv_blocks_hint > 0 && args.n_seqs > 0)
+    mean_tiles = static_cast<double>(args.kv_blocks_hint) * args.block_size / kDecTile / args.n_seqs;
+  if (mean_tiles < 1.0) mean_tiles = 1.0;
+  int n_splits = 1;
+  if (base_ctas < 148 || max_tiles > 1.3 * mean_tiles) {
+    const double total_work = mean_tiles * static_cast<double>(base_ctas);  // tile-CTA units
+    int tps = static_cast<int>(total_work / 600.0 + 0.999);
+    if (tps < kMinTilesPerSplit) tps = kMinTilesPerSplit;
+    n_splits = (max_tiles + tps - 1) / tps;
+  }
   const int max_splits = (max_tiles + kMinTilesPerSplit - 1) / kMinTilesPerSplit;
   if (n_splits > max_splits) n_splits = max_splits;
   if (const char* env = getenv("HI_DEC_SPLITS")) n_splits = atoi(env);

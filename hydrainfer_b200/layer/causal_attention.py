@@ -11,6 +11,7 @@ package ships no CPU implementation (the fp32 restatement lives in oracle/ and i
 from __future__ import annotations
 
 import math
+from array import array
 from dataclasses import dataclass
 from typing import Optional
 
@@ -44,6 +45,42 @@ class AttentionParameters:
             t = getattr(self, name)
             if t is not None:
                 setattr(self, name, t.to(device))
+
+
+class _PinnedStaging:
+    """Per-device ring of pinned int32 staging buffers for the per-step metadata upload.  pin_memory() on a fresh tensor
+    costs a cudaHostAlloc per step; the ring allocates once and an event per slot guards reuse while a copy is in flight."""
+
+    _rings: dict = {}
+
+    def __init__(self, device: torch.device, slots: int = 4):
+        self.device = device
+        self.buffers = [torch.empty(0, dtype=torch.int32) for _ in range(slots)]
+        self.events = [None] * slots
+        self.cursor = 0
+
+    @classmethod
+    def get(cls, device: torch.device) -> "_PinnedStaging":
+        ring = cls._rings.get(device)
+        if ring is None:
+            ring = cls._rings[device] = cls(device)
+        return ring
+
+    def upload(self, flat: array) -> Tensor:
+        i = self.cursor
+        self.cursor = (i + 1) % len(self.buffers)
+        if self.events[i] is not None:
+            self.events[i].synchronize()  # the copy that last used this slot has finished
+        n = len(flat)
+        if self.buffers[i].numel() < n:
+            self.buffers[i] = torch.empty(max(n, 4096, 2 * self.buffers[i].numel()), dtype=torch.int32).pin_memory()
+        host = self.buffers[i][:n]
+        host.copy_(torch.frombuffer(flat, dtype=torch.int32))
+        dev = host.to(self.device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.events[i] = ev
+        return dev
 
 
 class AttentionParametersBuilder:
@@ -89,15 +126,16 @@ class AttentionParametersBuilder:
         parts = [self.q_cu_seq_lens, self.kv_cu_seq_lens, self.paged_kv_last_page_len, self.new_cache_slots,
                  self.block_tables, self.cu_blocks_lens]
         # each slice starts on a 16-byte boundary (4 int32) so the kernels' vector paths never see a misaligned table
-        offsets, flat = [], []
+        offsets, flat_list = [], []
         for part in parts:
-            offsets.append(len(flat))
-            flat += part
-            flat += [0] * (-len(flat) % 4)
-        host = torch.tensor(flat, dtype=torch.int32)
+            offsets.append(len(flat_list))
+            flat_list += part
+            flat_list += [0] * (-len(flat_list) % 4)
+        flat = array("i", flat_list)  # one C-speed conversion (about 5x faster than torch.tensor(list))
         if self.device.type == "cuda":
-            host = host.pin_memory()
-        dev = host.to(self.device, non_blocking=True)
+            dev = _PinnedStaging.get(self.device).upload(flat)
+        else:
+            dev = torch.frombuffer(flat, dtype=torch.int32).clone() if len(flat) else torch.empty(0, dtype=torch.int32)
         views = [dev[o:o + len(part)] for o, part in zip(offsets, parts)]
         return [AttentionParameters(
             kv_cache=kv_cache,

@@ -113,7 +113,9 @@ typedef struct HiAttnArgs {
   int64_t workspace_bytes;
   int32_t path;              /* HiAttnPath */
   int32_t device;
-  int32_t reserved[4];
+  int32_t kv_blocks_hint;    /* entries of block_tables (sum of ceil(L_b / block_size)); 0 = unknown.  Only steers the
+                                split-KV heuristics (ragged batches are split finer); never affects results. */
+  int32_t reserved[3];
 } HiAttnArgs;
 
 /* Upper bound of the scratch hi_paged_attention needs for a batch with these extents (split-KV partials). */
