@@ -16,7 +16,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "lib" / "libhi_b200.so"
 
 HI_F32, HI_F16, HI_BF16 = 0, 1, 2
-HI_ATTN_AUTO, HI_ATTN_SIMT, HI_ATTN_TCGEN05, HI_ATTN_TCGEN05_DECODE = 0, 1, 2, 3
+HI_ATTN_AUTO, HI_ATTN_SIMT, HI_ATTN_TCGEN05, HI_ATTN_TCGEN05_DECODE, HI_ATTN_TCGEN05_PAIR = 0, 1, 2, 3, 4
 
 _DTYPES = {torch.float32: HI_F32, torch.float16: HI_F16, torch.bfloat16: HI_BF16}
 

@@ -42,6 +42,8 @@ int launch_attn_tc(const HiAttnArgs& args, cudaStream_t stream);
 bool attn_tc_supported(const HiAttnArgs& args);
 int launch_attn_decode_tc(const HiAttnArgs& args, cudaStream_t stream);
 bool attn_decode_tc_supported(const HiAttnArgs& args);
+int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream);
+bool attn_pair_supported(const HiAttnArgs& args);
 int64_t simt_workspace_bytes(int head_dim);
 int64_t tc_workspace_bytes();
 
@@ -91,6 +93,7 @@ extern "C" int hi_paged_attention(const HiAttnArgs* p, void* stream_) {
     if (env[0] == 's') path = HI_ATTN_SIMT;
     if (env[0] == 't') path = HI_ATTN_TCGEN05;
     if (env[0] == 'd') path = HI_ATTN_TCGEN05_DECODE;
+    if (env[0] == 'p') path = HI_ATTN_TCGEN05_PAIR;
   }
   if (path == HI_ATTN_AUTO) {
     // Rows with q_len > 1 are dense contractions: tensor pipe.  Pure decode batches stream KV once per row: the
@@ -100,7 +103,7 @@ extern "C" int hi_paged_attention(const HiAttnArgs* p, void* stream_) {
     // side, one row per CTA); batches with prefill rows take the tile kernel for every row.
     const int group = a.n_qo_heads / a.n_kv_heads;
     if (a.max_q_len > 1) {
-      path = attn_tc_supported(a) ? HI_ATTN_TCGEN05 : HI_ATTN_SIMT;
+      path = attn_pair_supported(a) ? HI_ATTN_TCGEN05_PAIR : attn_tc_supported(a) ? HI_ATTN_TCGEN05 : HI_ATTN_SIMT;
     } else if (group >= 4 && attn_decode_tc_supported(a)) {
       path = HI_ATTN_TCGEN05_DECODE;
     } else if (group >= 4 && attn_tc_supported(a)) {
@@ -111,6 +114,7 @@ extern "C" int hi_paged_attention(const HiAttnArgs* p, void* stream_) {
   }
   if (path == HI_ATTN_TCGEN05) return launch_attn_tc(a, stream);
   if (path == HI_ATTN_TCGEN05_DECODE) return launch_attn_decode_tc(a, stream);
+  if (path == HI_ATTN_TCGEN05_PAIR) return launch_attn_pair(a, stream);
   if (path == HI_ATTN_SIMT) return launch_attn_simt(a, stream);
   set_error("paged_attention: unknown path %d", path);
   return HI_ERR_INVALID_ARGUMENT;

@@ -1,0 +1,536 @@
+// Paged causal attention on tcgen05 — the prefill / chunked-prefill kernel: two query tiles per CTA, ping-ponged.
+//
+// Same function as TorchCausalGroupedQueryPageAttentionHandler.forward (reference
+// hydrainfer/layer/causal_attention.py:307-374) and the same operand staging as attn_tc.cu (TMA boxes per page written
+// 128B-swizzled = canonical UMMA layouts, S and O in TMEM, P fed to the second product straight from TMEM).  What changes
+// is the schedule, built around the two facts that bound attention on this part (B300_MICROARCH.md, tcgen05 / pipe rates):
+// a 128x128 score tile costs 1024 tensor-pipe cycles (Q.K^T + P.V) and 1024 MUFU cycles (16 ex2/clk/SM), and every K/V
+// tile costs 64 KiB of L2 -> shared-memory traffic.
+//
+//   * One CTA owns TWO 128-row query tiles of the same (sequence, KV head) and ONE K/V ring: every staged K/V byte feeds
+//     both tiles (half the L2 -> SM traffic of one tile per CTA).  One CTA per SM: 512 TMEM columns = S0 | S1 | O0 | O1.
+//   * Two softmax warpgroups (thread = row = TMEM lane).  The single MMA-issuing thread interleaves the tiles
+//         ... P0.V(j)  Q0.K(j+1)  P1.V(j)  Q1.K(j+1)  P0.V(j+1) ...
+//     so while warpgroup 0 turns S0(j+1) into P0(j+1) the tensor pipe runs tile 1's products, and vice versa.
+//   * A softmax thread reads its 128 scores from TMEM ONCE and keeps them in registers (setmaxnreg moves registers from
+//     the producer / MMA warpgroup to the softmax warpgroups: 208 vs 72): max, exp2, row sum and the 16-bit pack all run
+//     from registers; P overwrites S.
+//   * O is rescaled lazily (only when a row max grows by more than 2^8) by the softmax thread itself: S_t(j) complete
+//     implies P_t.V(j-1) complete because the tensor pipe executes one thread's MMAs in order.
+//   * The TMA producer zeroes V rows at or beyond kv_len of the last tile (P is 0 there, the pool bytes are arbitrary).
+// Rows are (token, head-in-group) pairs, so GQA groups share the staged K/V exactly as in attn_tc.cu.
+#include <cuda.h>
+
+#include <cstdlib>
+#include <type_traits>
+
+#include "attn_common.cuh"
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+#include "tma_maps.h"
+
+namespace hi {
+
+constexpr int kP2Threads = 384;               // warps 0-3 / 4-7: softmax of tile 0 / 1; warp 8: TMA; warp 9: MMA; 10-11 idle
+constexpr int kP2TileM = 128;
+constexpr int kP2TileN = 128;
+constexpr int kP2D = 128;
+constexpr int kP2Half = kP2TileM * 128;       // one 64-dim half of a 128-row tile: 16 KiB
+constexpr int kP2Tile = 2 * kP2Half;          // 32 KiB
+constexpr uint32_t kP2TmemCols = 512;
+constexpr uint32_t kP2ColS = 0;               // S_t at columns [128 t, 128 t + 128); P_t aliases its first 64 columns
+constexpr uint32_t kP2ColO = 256;             // O_t at columns [256 + 128 t, ...)
+constexpr float kP2Rescale = 8.0f;
+
+struct P2Args {
+  void* out;
+  int64_t out_row_stride;
+  const int32_t* q_cu;
+  const int32_t* kv_cu;
+  const int32_t* block_tables;
+  const int32_t* cu_blocks;
+  int n_qo_heads, n_kv_heads, group, block_size;
+  int tq;            // query tokens per 128-row tile: 128 / group
+  float scale_log2;
+  int n_splits;
+  int tiles_per_split;
+  float* part_o;
+  float* part_ml;
+};
+
+template <int NK, int NV>
+struct P2Smem {
+  static constexpr int kQ = 0;                          // two tiles
+  static constexpr int kK = 2 * kP2Tile;
+  static constexpr int kV = kK + NK * kP2Tile;
+  static constexpr int kBars = kV + NV * kP2Tile;
+  static constexpr int bQFull = 0;                      // [2]
+  static constexpr int bKFull = 2;                      // [NK]
+  static constexpr int bKEmpty = bKFull + NK;
+  static constexpr int bVFull = bKEmpty + NK;           // [NV]
+  static constexpr int bVEmpty = bVFull + NV;
+  static constexpr int bSFull = bVEmpty + NV;           // [2]
+  static constexpr int bPFull = bSFull + 2;             // [2]
+  static constexpr int bOFull = bPFull + 2;             // [2]
+  static constexpr int bVTail = bOFull + 2;
+  static constexpr int kNumBars = bVTail + 1;
+  static constexpr int kTmemPtr = kBars + kNumBars * 8;
+  static constexpr int kTotal = kTmemPtr + 16;
+  static constexpr int kDynamicBytes = kTotal + 1024;   // slack to align the base to 1024 B (128B-swizzle atoms)
+};
+
+template <typename T, int NK, int NV>
+__global__ void __launch_bounds__(kP2Threads, 1)
+paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                       const __grid_constant__ CUtensorMap tm_v, const P2Args a) {
+  using L = P2Smem<NK, NV>;
+  constexpr bool kBf16 = !std::is_same<T, __half>::value;
+
+  // ---- which pair of query tiles -----------------------------------------------------------------------------------
+  const int b = blockIdx.z;
+  const int kvh = blockIdx.y;
+  const int q_start = __ldg(a.q_cu + b);
+  const int q_len = __ldg(a.q_cu + b + 1) - q_start;
+  const int kv_len = __ldg(a.kv_cu + b + 1) - __ldg(a.kv_cu + b);
+  const int pair_tokens = 2 * a.tq;
+  const int n_pairs = (q_len + pair_tokens - 1) / pair_tokens;
+  const int sp = static_cast<int>(blockIdx.x) % a.n_splits;
+  const int pair = n_pairs - 1 - static_cast<int>(blockIdx.x) / a.n_splits;  // heaviest (latest) tiles first
+  if (pair < 0) return;
+  const int i0 = pair * pair_tokens;
+  const int j_begin = sp * a.tiles_per_split;
+  // nt[t]: KV tiles walked for query tile t (local tile index j = 0 .. nt[t]-1 is global tile j_begin + j)
+  int nt[2];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int first = i0 + t * a.tq;
+    if (first >= q_len) {
+      nt[t] = 0;
+    } else {
+      const int i_last = min(q_len, first + a.tq) - 1;
+      const int kv_end = i_last + (kv_len - q_len) + 1;  // keys [0, kv_end) are visible to the tile
+      const int n_all = (kv_end + kP2TileN - 1) / kP2TileN;
+      nt[t] = max(0, min(n_all - j_begin, a.tiles_per_split));
+    }
+  }
+  const int n_all = max(nt[0], nt[1]);
+  if (n_all == 0) return;  // this split sees no key of the pair; the merge skips it too
+  const int blk0 = __ldg(a.cu_blocks + b);
+  const int n_pages = __ldg(a.cu_blocks + b + 1) - blk0;
+  const int pages_per_tile = kP2TileN / a.block_size;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  auto bar = [&](int idx) -> uint32_t { return smem_base + L::kBars + idx * 8; };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + L::kTmemPtr);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- one-time setup ------------------------------------------------------------------------------------------------
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < L::kNumBars; ++i) ptx::mbar_init(bar(i), 1);
+    ptx::mbar_init(bar(L::bPFull + 0), kP2TileM);  // every softmax thread of the tile arrives
+    ptx::mbar_init(bar(L::bPFull + 1), kP2TileM);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 8) {
+    if (lane == 0) {
+      ptx::prefetch_tensormap(&tm_q);
+      ptx::prefetch_tensormap(&tm_k);
+      ptx::prefetch_tensormap(&tm_v);
+    }
+    __syncwarp();
+    ptx::tmem_alloc(smem_base + L::kTmemPtr, kP2TmemCols);
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp >= 8) {
+    // ===================================== producer / MMA warpgroup (warps 10-11 idle) ================================
+    ptx::setmaxnreg_dec<72>();
+  if (warp == 8) {
+    // ================================================ TMA producer ================================================
+    if (lane == 0) {
+      const uint32_t q_bytes = 2u * static_cast<uint32_t>(a.group * a.tq) * 128u;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (nt[t] > 0) {
+          const uint32_t dst = smem_base + L::kQ + t * kP2Tile;
+          ptx::mbar_arrive_expect_tx(bar(L::bQFull + t), q_bytes);
+          ptx::tma_load_3d(dst, &tm_q, bar(L::bQFull + t), 0, kvh * a.group, q_start + i0 + t * a.tq);
+          ptx::tma_load_3d(dst + kP2Half, &tm_q, bar(L::bQFull + t), 64, kvh * a.group, q_start + i0 + t * a.tq);
+        }
+      }
+    }
+    const uint32_t page_half_bytes = static_cast<uint32_t>(a.block_size) * 128u;
+    for (int j = 0; j < n_all; ++j) {
+      const int page0 = (j_begin + j) * pages_per_tile;
+      const int n_valid = max(0, min(pages_per_tile, n_pages - page0));
+      int blk = 0;
+      if (lane < n_valid) blk = __ldg(a.block_tables + blk0 + page0 + lane);  // lane p stages page p of the tile
+      const uint32_t tx = static_cast<uint32_t>(n_valid) * 2u * page_half_bytes;
+      {  // K(j)
+        const int st = j % NK;
+        const uint32_t ph = static_cast<uint32_t>(j / NK) & 1u;
+        if (lane == 0) {
+          ptx::mbar_wait(bar(L::bKEmpty + st), ph ^ 1u);
+          ptx::mbar_arrive_expect_tx(bar(L::bKFull + st), tx);
+        }
+        __syncwarp();
+        if (lane < n_valid) {
+          const uint32_t dst = smem_base + L::kK + st * kP2Tile + lane * page_half_bytes;
+          ptx::tma_load_3d(dst, &tm_k, bar(L::bKFull + st), 0, kvh, blk * a.block_size);
+          ptx::tma_load_3d(dst + kP2Half, &tm_k, bar(L::bKFull + st), 64, kvh, blk * a.block_size);
+        }
+      }
+      {  // V(j)
+        const int st = j % NV;
+        const uint32_t ph = static_cast<uint32_t>(j / NV) & 1u;
+        const int kv0 = (j_begin + j) * kP2TileN;
+        const bool tail = kv0 + kP2TileN > kv_len;  // at most one such tile per sequence
+        const uint32_t full_bar = tail ? bar(L::bVTail) : bar(L::bVFull + st);
+        if (lane == 0) {
+          ptx::mbar_wait(bar(L::bVEmpty + st), ph ^ 1u);
+          ptx::mbar_arrive_expect_tx(full_bar, tx);
+        }
+        __syncwarp();
+        const uint32_t dst0 = smem_base + L::kV + st * kP2Tile;
+        if (lane < n_valid) {
+          const uint32_t dst = dst0 + lane * page_half_bytes;
+          ptx::tma_load_3d(dst, &tm_v, full_bar, 0, kvh, blk * a.block_size);
+          ptx::tma_load_3d(dst + kP2Half, &tm_v, full_bar, 64, kvh, blk * a.block_size);
+        }
+        if (tail) {
+          // Keys at or beyond kv_len carry P == 0, but their V rows are whatever the pool / stale shared memory holds:
+          // zero them (0 * NaN must not reach O), then publish the tile.
+          ptx::mbar_wait(bar(L::bVTail), 0);
+          uint8_t* vt = smem_gen + L::kV + st * kP2Tile;
+          const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+          for (int r = max(0, kv_len - kv0) + lane; r < kP2TileN; r += 32) {
+            uint4* row0 = reinterpret_cast<uint4*>(vt + r * 128);
+            uint4* row1 = reinterpret_cast<uint4*>(vt + kP2Half + r * 128);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              row0[e] = z;
+              row1[e] = z;
+            }
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(bar(L::bVFull + st));
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ================================================ MMA issuer ==================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = ptx::make_idesc_f16(kBf16, false, false, kP2TileM, kP2TileN);
+      constexpr uint32_t idesc_pv = ptx::make_idesc_f16(kBf16, false, true, kP2TileM, kP2D);
+      auto issue_qk = [&](int t, int st) {
+        const uint32_t q_addr = smem_base + L::kQ + t * kP2Tile;
+        const uint32_t k_addr = smem_base + L::kK + st * kP2Tile;
+        const uint32_t tmem_s = tmem_base + kP2ColS + t * 128;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {  // 2 halves x 4 k-steps of 16 dims; both operands K-major, 8-row groups 1024 B apart
+          const uint32_t off = (kk >> 2) * kP2Half + (kk & 3) * 32;
+          ptx::mma_f16_ss(tmem_s, ptx::make_smem_desc_sw128(q_addr + off, 16, 1024),
+                          ptx::make_smem_desc_sw128(k_addr + off, 16, 1024), idesc_qk, kk > 0);
+        }
+        ptx::mma_commit(bar(L::bSFull + t));
+      };
+      auto issue_pv = [&](int t, int st, bool accumulate) {
+        const uint32_t v_addr = smem_base + L::kV + st * kP2Tile;
+        const uint32_t tmem_p = tmem_base + kP2ColS + t * 128;
+        const uint32_t tmem_o = tmem_base + kP2ColO + t * 128;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {  // 8 k-steps of 16 tokens; A = P in TMEM (8 columns per step), B = V MN-major
+          ptx::mma_f16_ts(tmem_o, tmem_p + kk * 8, ptx::make_smem_desc_sw128(v_addr + kk * 2048, kP2Half, 1024), idesc_pv,
+                          accumulate || (kk > 0));
+        }
+      };
+      // prologue: S_t(0)
+      ptx::mbar_wait(bar(L::bKFull + 0), 0);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (nt[t] > 0) {
+          ptx::mbar_wait(bar(L::bQFull + t), 0);
+          ptx::tc_fence_after_sync();
+          issue_qk(t, 0);
+        }
+      }
+      ptx::mma_commit(bar(L::bKEmpty + 0));
+      for (int j = 0; j < n_all; ++j) {
+        const int stv = j % NV;
+        const int stk = (j + 1) % NK;
+        const uint32_t phk = static_cast<uint32_t>((j + 1) / NK) & 1u;
+        ptx::mbar_wait(bar(L::bVFull + stv), static_cast<uint32_t>(j / NV) & 1u);
+        bool k_waited = false;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (j < nt[t]) {
+            ptx::mbar_wait(bar(L::bPFull + t), static_cast<uint32_t>(j) & 1u);
+            ptx::tc_fence_after_sync();
+            issue_pv(t, stv, j > 0);
+            if (j == nt[t] - 1) ptx::mma_commit(bar(L::bOFull + t));
+          }
+          if (t == 1) ptx::mma_commit(bar(L::bVEmpty + stv));  // V(j) reusable once both tiles' P.V have read it
+          if (j + 1 < nt[t]) {
+            if (!k_waited) {
+              ptx::mbar_wait(bar(L::bKFull + stk), phk);
+              ptx::tc_fence_after_sync();
+              k_waited = true;
+            }
+            issue_qk(t, stk);
+          }
+        }
+        if (j + 1 < n_all) ptx::mma_commit(bar(L::bKEmpty + stk));
+      }
+    }
+  }
+  } else {
+    // ================================================ softmax + epilogue ===========================================
+    ptx::setmaxnreg_inc<208>();
+    const int t = warp >> 2;                         // query tile of this warpgroup
+    const int r = threadIdx.x & 127;                 // tile row == TMEM lane
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tmem_s = tmem_base + lane_base + kP2ColS + t * 128;
+    const uint32_t tmem_o = tmem_base + lane_base + kP2ColO + t * 128;
+    const int tok = r / a.group;
+    const int g = r - tok * a.group;
+    const int first = i0 + t * a.tq;
+    const int i = first + tok;                       // query position within the sequence
+    const bool row_valid = (tok < a.tq) && (i < q_len);
+    const int lim = i + (kv_len - q_len);            // last visible key index of this row
+    const int n_mine = t ? nt[1] : nt[0];
+    float m_used = 0.f;                              // exponent reference (scaled log2 domain)
+    float l = 0.f;
+    // Rows past the tile's valid (token, head) pairs are padding; a warp that owns only padding rows skips the math.
+    const int rows_real = (min(q_len, first + a.tq) - first) * a.group;
+    const bool warp_active = (warp & 3) * 32 < rows_real;
+
+    for (int j = 0; j < n_mine; ++j) {
+      const int kv0 = (j_begin + j) * kP2TileN;
+      const int col_lim = lim - kv0;                 // columns [0, col_lim] are visible
+      ptx::mbar_wait(bar(L::bSFull + t), static_cast<uint32_t>(j) & 1u);
+      ptx::tc_fence_after_sync();
+      if (warp_active) {
+        uint32_t s[4][32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) ptx::tmem_ld_x32(tmem_s + c * 32, s[c]);
+        ptx::tmem_wait_ld();
+        if (__any_sync(0xffffffffu, col_lim < kP2TileN - 1)) {  // tile touches the causal diagonal / end of the sequence
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (c * 32 + e > col_lim) s[c][e] = 0xff800000u;  // -inf
+          }
+        }
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 8) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              mx4[u] = fmax3(mx4[u], __uint_as_float(s[c][e + 2 * u]), __uint_as_float(s[c][e + 2 * u + 1]));
+          }
+        }
+        const float mxs = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * a.scale_log2;
+        if (j == 0) {
+          m_used = (mxs == -INFINITY) ? 0.f : mxs;
+        } else if (__any_sync(0xffffffffu, mxs > m_used + kP2Rescale)) {
+          // Lazy rescale: the warp pays the TMEM round trip only when some row's max grew by more than 2^8.
+          const float m_new = fmaxf(m_used, mxs);
+          const float alpha = fast_exp2(m_used - m_new);
+          l *= alpha;
+          m_used = m_new;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t o[32];
+            ptx::tmem_ld_x32(tmem_o + c * 32, o);
+            ptx::tmem_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+            ptx::tmem_st_x32(tmem_o + c * 32, o);
+          }
+        }
+        // P = exp2(S * scale - m) as 16-bit pairs, written over S (every S column is already in registers)
+        const float2 sc2 = make_float2(a.scale_log2, a.scale_log2);
+        const float2 nm2 = make_float2(-m_used, -m_used);
+        float2 ls2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const float2 x2 = ffma2(make_float2(__uint_as_float(s[c][e]), __uint_as_float(s[c][e + 1])), sc2, nm2);
+            const float2 p2 = make_float2(fast_exp2(x2.x), fast_exp2(x2.y));
+            ls2[(e >> 1) & 1] = fadd2(ls2[(e >> 1) & 1], p2);
+            pk[e >> 1] = pack2<T>(p2.x, p2.y);
+          }
+          ptx::tmem_st_x16(tmem_s + c * 16, pk);
+        }
+        l += (ls2[0].x + ls2[0].y) + (ls2[1].x + ls2[1].y);
+      }
+      ptx::tmem_wait_st();
+      ptx::tc_fence_before_sync();
+      ptx::mbar_arrive(bar(L::bPFull + t));
+    }
+
+    // ---- epilogue: O / l -> out (or the fp32 split-KV partial) ---------------------------------------------------------
+    if (n_mine > 0) {
+      ptx::mbar_wait(bar(L::bOFull + t), 0);
+      ptx::tc_fence_after_sync();
+      const float inv_l = 1.f / l;
+      const int head = kvh * a.group + g;
+      T* orow = static_cast<T*>(a.out) + static_cast<int64_t>(q_start + i) * a.out_row_stride + head * kP2D;
+      const int64_t pidx = (static_cast<int64_t>(q_start + i) * a.n_qo_heads + head) * a.n_splits + sp;
+      if (a.n_splits > 1 && row_valid) {
+        a.part_ml[pidx * 2 + 0] = m_used;
+        a.part_ml[pidx * 2 + 1] = l;
+      }
+      if (warp_active) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          ptx::tmem_ld_x32(tmem_o + c * 32, v);
+          ptx::tmem_wait_ld();
+          if (!row_valid) continue;
+          if (a.n_splits > 1) {
+            float4* dst = reinterpret_cast<float4*>(a.part_o + pidx * kP2D + c * 32);
+#pragma unroll
+            for (int e = 0; e < 32; e += 4)
+              dst[e >> 2] = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; e += 8) {
+              uint4 w;
+              w.x = pack2<T>(__uint_as_float(v[e + 0]) * inv_l, __uint_as_float(v[e + 1]) * inv_l);
+              w.y = pack2<T>(__uint_as_float(v[e + 2]) * inv_l, __uint_as_float(v[e + 3]) * inv_l);
+              w.z = pack2<T>(__uint_as_float(v[e + 4]) * inv_l, __uint_as_float(v[e + 5]) * inv_l);
+              w.w = pack2<T>(__uint_as_float(v[e + 6]) * inv_l, __uint_as_float(v[e + 7]) * inv_l);
+              *reinterpret_cast<uint4*>(orow + c * 32 + e) = w;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ---- teardown ----------------------------------------------------------------------------------------------------
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 8) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, kP2TmemCols);
+  }
+}
+
+bool attn_pair_supported(const HiAttnArgs& args) {
+  const int group = args.n_kv_heads > 0 ? args.n_qo_heads / args.n_kv_heads : 0;
+  return (args.dtype == HI_F16 || args.dtype == HI_BF16) && args.head_dim == kP2D && group >= 1 && group <= kP2TileM &&
+         args.block_size >= 8 && args.block_size <= kP2TileN && (kP2TileN % args.block_size) == 0 &&
+         (args.q_row_stride % 8) == 0 && (args.out_row_stride % 8) == 0 && aligned_to(args.q, 16) &&
+         aligned_to(args.out, 16) && aligned_to(args.key_cache, 16) && aligned_to(args.value_cache, 16) &&
+         args.n_blocks > 0;
+}
+
+template <typename T>
+static int launch_pair_t(const HiAttnArgs& args, const P2Args& a, const CUtensorMap& mq, const CUtensorMap& mk,
+                         const CUtensorMap& mv, cudaStream_t stream) {
+  constexpr int NK = 2, NV = 2;
+  using L = P2Smem<NK, NV>;
+  static bool configured = false;
+  if (!configured) {
+    HI_CUDA(cudaFuncSetAttribute(paged_attn_pair_kernel<T, NK, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamicBytes));
+    configured = true;
+  }
+  const int n_pairs = (args.max_q_len + 2 * a.tq - 1) / (2 * a.tq);
+  const dim3 grid(n_pairs * a.n_splits, args.n_kv_heads, args.n_seqs);
+  timing_mark_start(stream);
+  paged_attn_pair_kernel<T, NK, NV><<<grid, kP2Threads, L::kDynamicBytes, stream>>>(mq, mk, mv, a);
+  timing_mark_stop(stream);
+  note_launch();
+  HI_CUDA(cudaGetLastError());
+  return HI_OK;
+}
+
+int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
+  if (!attn_pair_supported(args)) {
+    set_error("paged_attention: the tcgen05 pair-tile path needs fp16/bf16, head_dim 128, block_size in {8,16,32,64,128} and 16-byte aligned rows");
+    return HI_ERR_UNSUPPORTED;
+  }
+  P2Args a{};
+  a.out = args.out;
+  a.out_row_stride = args.out_row_stride;
+  a.q_cu = args.q_cu_seq_lens;
+  a.kv_cu = args.kv_cu_seq_lens;
+  a.block_tables = args.block_tables;
+  a.cu_blocks = args.cu_blocks_lens;
+  a.n_qo_heads = args.n_qo_heads;
+  a.n_kv_heads = args.n_kv_heads;
+  a.group = args.n_qo_heads / args.n_kv_heads;
+  a.block_size = args.block_size;
+  a.tq = kP2TileM / a.group;
+  a.scale_log2 = args.softmax_scale * 1.4426950408889634f;
+
+  // ---- split-KV: only for launches too small to fill the machine (one CTA per SM) ---------------------------------------
+  constexpr int kSplitTargetCtas = 296;  // 148 SMs x 2
+  constexpr int kMinTilesPerSplit = 2;   // never finer than 256 tokens
+  const int n_pairs = (args.max_q_len + 2 * a.tq - 1) / (2 * a.tq);
+  const int64_t base_ctas = static_cast<int64_t>(n_pairs) * args.n_kv_heads * args.n_seqs;
+  const int max_kv_tiles = (args.max_kv_len + kP2TileN - 1) / kP2TileN;
+  int n_splits = 1;
+  if (base_ctas < kSplitTargetCtas) {
+    n_splits = static_cast<int>((kSplitTargetCtas + base_ctas - 1) / base_ctas);
+    const int max_splits = (max_kv_tiles + kMinTilesPerSplit - 1) / kMinTilesPerSplit;
+    if (n_splits > max_splits) n_splits = max_splits;
+  }
+  if (const char* env = getenv("HI_TC_SPLITS")) n_splits = atoi(env);  // tuning / test override
+  if (n_splits < 1) n_splits = 1;
+  {
+    const int64_t per_split = static_cast<int64_t>(args.n_tokens) * args.n_qo_heads * (kP2D + 2) * 4;
+    while (n_splits > 1 && (args.workspace == nullptr || per_split * n_splits > args.workspace_bytes)) --n_splits;
+  }
+  a.tiles_per_split = (max_kv_tiles + n_splits - 1) / n_splits;
+  a.n_splits = (max_kv_tiles + a.tiles_per_split - 1) / a.tiles_per_split;
+  if (a.n_splits > 1) {
+    const int64_t entries = static_cast<int64_t>(args.n_tokens) * args.n_qo_heads * a.n_splits;
+    a.part_o = static_cast<float*>(args.workspace);
+    a.part_ml = a.part_o + entries * kP2D;
+  }
+
+  CUtensorMap mq, mk, mv;
+  int rc = make_map(&mq, args.dtype, args.q, args.n_tokens, args.n_qo_heads, args.q_row_stride, a.group, a.tq);
+  if (rc != HI_OK) return rc;
+  const int64_t n_slots = args.n_blocks * args.block_size;
+  rc = pool_map(&mk, args.dtype, args.key_cache, n_slots, args.n_kv_heads, args.block_size);
+  if (rc != HI_OK) return rc;
+  rc = pool_map(&mv, args.dtype, args.value_cache, n_slots, args.n_kv_heads, args.block_size);
+  if (rc != HI_OK) return rc;
+
+  rc = args.dtype == HI_BF16 ? launch_pair_t<__nv_bfloat16>(args, a, mq, mk, mv, stream)
+                             : launch_pair_t<__half>(args, a, mq, mk, mv, stream);
+  if (rc != HI_OK || a.n_splits == 1) return rc;
+
+  SimtArgs m{};
+  m.out = args.out;
+  m.out_row_stride = args.out_row_stride;
+  m.q_cu = args.q_cu_seq_lens;
+  m.kv_cu = args.kv_cu_seq_lens;
+  m.n_seqs = args.n_seqs;
+  m.n_tokens = args.n_tokens;
+  m.n_qo_heads = args.n_qo_heads;
+  m.n_chunks = a.n_splits;
+  m.chunk_tiles = a.tiles_per_split * (kP2TileN / 16);
+  m.part_o = a.part_o;
+  m.part_ml = a.part_ml;
+  return launch_merge_partials(m, args.dtype, kP2D, stream);
+}
+
+}  // namespace hi

@@ -138,6 +138,16 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t n_threads) 
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
 }
 
+// Warpgroup register re-allocation: every warp of a warpgroup (4 consecutive warps) must execute the same instruction.
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 // ---- TMEM <-> registers (32x32b: thread i of the warp owns TMEM lane base+i; registers are consecutive columns) ----
 __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(

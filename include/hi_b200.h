@@ -42,7 +42,8 @@ typedef enum HiAttnPath {
   HI_ATTN_AUTO = 0,
   HI_ATTN_SIMT = 1,   /* split-KV CUDA-core kernel (decode rows; also the generic any-shape path) */
   HI_ATTN_TCGEN05 = 2, /* tcgen05/TMEM tile kernel (prefill, chunked prefill, GQA-packed decode) */
-  HI_ATTN_TCGEN05_DECODE = 3 /* tcgen05 swapped-operand kernel: one query row x one KV head per CTA (grouped decode) */
+  HI_ATTN_TCGEN05_DECODE = 3, /* tcgen05 swapped-operand kernel: one query row x one KV head per CTA (grouped decode) */
+  HI_ATTN_TCGEN05_PAIR = 4 /* tcgen05 pair-tile kernel: two ping-ponged 128-row query tiles per CTA (prefill, chunked prefill) */
 } HiAttnPath;
 
 const char* hi_last_error(void);

@@ -12,7 +12,7 @@ from oracle import paged_kv_oracle as oracle
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-SIMT, TC, DEC = 1, 2, 3
+SIMT, TC, DEC, PAIR = 1, 2, 3, 4
 
 
 def tolerances(dtype):
@@ -73,13 +73,14 @@ def check_batch(batch, paths, what=""):
 
 
 def paths_for(head_dim, dtype, block_size=16, group=1):
-    """Every kernel path that covers the shape: 1 split-KV CUDA-core, 2 tcgen05 tile, 3 tcgen05 swapped-operand decode, 0 auto."""
+    """Every kernel path that covers the shape: 1 split-KV CUDA-core, 2 tcgen05 tile, 3 tcgen05 swapped-operand decode,
+    4 tcgen05 pair-tile (prefill), 0 auto."""
     import os
     if os.environ.get("HI_TEST_SKIP_TC") == "1":  # dev switch: validate the split-KV kernel alone
         return [SIMT]
     if not tc_supported(head_dim, dtype, block_size):
         return [SIMT, 0]
-    return [SIMT, TC, DEC, 0] if group <= 16 else [SIMT, TC, 0]
+    return [SIMT, TC, DEC, PAIR, 0] if group <= 16 else [SIMT, TC, PAIR, 0]
 
 
 def paths_of(batch):
@@ -222,7 +223,7 @@ def test_tile_kernel_split_kv_and_ring_depth_variants(monkeypatch, splits, stage
     seq_lens = [(1, 1300), (1, 17), (1, 128), (1, 129), (1, 640), (3, 700), (1, 2049)]
     for heads in ((28, 4), (8, 8)):
         batch = make_batch(seq_lens, heads[0], heads[1], 128, 16, dtype=torch.bfloat16, seed=40)
-        check_batch(batch, [TC, DEC], f"splits={splits} stages={stages} heads={heads}")
+        check_batch(batch, [TC, DEC, PAIR], f"splits={splits} stages={stages} heads={heads}")
 
 
 # ---- full-size configs: sampled oracle rows + size-independent properties -------------------------------------------------

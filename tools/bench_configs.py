@@ -116,7 +116,7 @@ def main():
     ap.add_argument("--flashinfer", action="store_true")
     args = ap.parse_args()
     only = set(args.only.split(",")) if args.only else None
-    SIMT, TC, AUTO, DEC = ("simt", 1), ("tc", 2), ("auto", 0), ("dec", 3)
+    SIMT, TC, AUTO, DEC, PAIR = ("simt", 1), ("tc", 2), ("auto", 0), ("dec", 3), ("pair", 4)
     g = torch.Generator().manual_seed(0)
     cfg3_dec = [(1, int(L)) for L in torch.randint(256, 8193, (48,), generator=g).tolist()]
     cfg3_pre = [(512, 512), (512, 2048), (512, 4096), (512, 8192)]
@@ -125,14 +125,14 @@ def main():
         ("cfg2_b8", [(1, 2048)] * 8, 32, 32, [SIMT, TC]),
         ("cfg2_ctx8k", [(1, 8192)] * 16, 32, 32, [SIMT, TC]),
         ("cfg3d", cfg3_dec, 28, 4, [SIMT, TC, DEC]),
-        ("cfg3p", cfg3_pre, 28, 4, [TC]),
-        ("cfg3mix", cfg3_dec + cfg3_pre, 28, 4, [AUTO, TC]),
-        ("pre256", [(256, 256)] * 32, 28, 4, [TC]),
-        ("pre1k", [(1024, 1024)] * 8, 28, 4, [TC]),
-        ("pre4k", [(4096, 4096)] * 2, 28, 4, [TC]),
-        ("pre8k", [(8192, 8192)] * 1, 28, 4, [TC]),
-        ("pre_mha2k", [(2048, 2048)] * 4, 32, 32, [TC]),
-        ("pre_mha8k", [(8192, 8192)] * 1, 32, 32, [TC]),
+        ("cfg3p", cfg3_pre, 28, 4, [TC, PAIR]),
+        ("cfg3mix", cfg3_dec + cfg3_pre, 28, 4, [AUTO, TC, PAIR]),
+        ("pre256", [(256, 256)] * 32, 28, 4, [TC, PAIR]),
+        ("pre1k", [(1024, 1024)] * 8, 28, 4, [TC, PAIR]),
+        ("pre4k", [(4096, 4096)] * 2, 28, 4, [TC, PAIR]),
+        ("pre8k", [(8192, 8192)] * 1, 28, 4, [TC, PAIR]),
+        ("pre_mha2k", [(2048, 2048)] * 4, 32, 32, [TC, PAIR]),
+        ("pre_mha8k", [(8192, 8192)] * 1, 32, 32, [TC, PAIR]),
         ("cfg4_2k", [(1, 2048)] * 256, 64, 8, [SIMT, TC, DEC]),
         ("cfg4_4k", [(1, 4096)] * 256, 64, 8, [SIMT, TC, DEC]),
         ("cfg4_shard8", [(1, 4096)] * 32, 64, 8, [SIMT, TC, DEC]),

@@ -32,6 +32,17 @@ GROUPS = {
         ("gqa16", [(1, 2000)] * 2, 32, 2),
         ("mha", [(1, 500), (3, 140)], 4, 4),
     ]),
+    "pair": dict(path=4, cases=[
+        ("1 head q128 kv128", [(128, 128)], 1, 1),
+        ("1 head q256 kv256", [(256, 256)], 1, 1),
+        ("1 head q1 kv16", [(1, 16)], 1, 1),
+        ("1 head q16 kv40", [(16, 40)], 1, 1),
+        ("1 head q300 kv300", [(300, 300)], 1, 1),
+        ("1 head q700 kv1500", [(700, 1500)], 1, 1),
+        ("mha 8 heads mixed", [(1, 100), (15, 15), (111, 234), (1, 1024)], 8, 8),
+        ("gqa4", [(1, 100), (15, 15), (111, 234), (1, 1024)], 8, 2),
+        ("gqa7 qwen", [(1, 300), (40, 170), (1, 17), (200, 513)], 28, 4),
+    ]),
     "tc_gqa": dict(path=2, cases=[
         ("mha 8 heads mixed", [(1, 100), (15, 15), (111, 234), (1, 1024)], 8, 8),
         ("gqa4", [(1, 100), (15, 15), (111, 234), (1, 1024)], 8, 2),
