@@ -79,7 +79,8 @@ struct P2Smem {
   static constexpr int kDynamicBytes = kTotal + 1024;   // slack to align the base to 1024 B (128B-swizzle atoms)
 };
 
-template <typename T, int NK, int NV>
+// PF = how many of every 4 (pairs of) exponentials run on the FMA pipes (exp2_poly2) instead of MUFU.EX2.
+template <typename T, int NK, int NV, int PF>
 __global__ void __launch_bounds__(kP2Threads, 1)
 paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                        const __grid_constant__ CUtensorMap tm_v, const P2Args a) {
@@ -151,105 +152,113 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
 
   if (warp >= 8) {
     // ===================================== producer / MMA warpgroup (warps 10-11 idle) ================================
+    // Both roles keep the whole warp converged (every lane waits on the barriers) and issue the asynchronous
+    // instructions from one elected lane: warp-uniform control flow lets the compiler keep descriptors, barrier
+    // addresses and loop state in uniform registers instead of emulating them per lane.
     ptx::setmaxnreg_dec<72>();
-  if (warp == 8) {
-    // ================================================ TMA producer ================================================
-    if (lane == 0) {
-      const uint32_t q_bytes = 2u * static_cast<uint32_t>(a.group * a.tq) * 128u;
+    if (warp == 8) {
+      // ================================================ TMA producer ================================================
+      if (ptx::elect_one()) {
+        const uint32_t q_bytes = 2u * static_cast<uint32_t>(a.group * a.tq) * 128u;
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        if (nt[t] > 0) {
-          const uint32_t dst = smem_base + L::kQ + t * kP2Tile;
-          ptx::mbar_arrive_expect_tx(bar(L::bQFull + t), q_bytes);
-          ptx::tma_load_3d(dst, &tm_q, bar(L::bQFull + t), 0, kvh * a.group, q_start + i0 + t * a.tq);
-          ptx::tma_load_3d(dst + kP2Half, &tm_q, bar(L::bQFull + t), 64, kvh * a.group, q_start + i0 + t * a.tq);
-        }
-      }
-    }
-    const uint32_t page_half_bytes = static_cast<uint32_t>(a.block_size) * 128u;
-    for (int j = 0; j < n_all; ++j) {
-      const int page0 = (j_begin + j) * pages_per_tile;
-      const int n_valid = max(0, min(pages_per_tile, n_pages - page0));
-      int blk = 0;
-      if (lane < n_valid) blk = __ldg(a.block_tables + blk0 + page0 + lane);  // lane p stages page p of the tile
-      const uint32_t tx = static_cast<uint32_t>(n_valid) * 2u * page_half_bytes;
-      {  // K(j)
-        const int st = j % NK;
-        const uint32_t ph = static_cast<uint32_t>(j / NK) & 1u;
-        if (lane == 0) {
-          ptx::mbar_wait(bar(L::bKEmpty + st), ph ^ 1u);
-          ptx::mbar_arrive_expect_tx(bar(L::bKFull + st), tx);
-        }
-        __syncwarp();
-        if (lane < n_valid) {
-          const uint32_t dst = smem_base + L::kK + st * kP2Tile + lane * page_half_bytes;
-          ptx::tma_load_3d(dst, &tm_k, bar(L::bKFull + st), 0, kvh, blk * a.block_size);
-          ptx::tma_load_3d(dst + kP2Half, &tm_k, bar(L::bKFull + st), 64, kvh, blk * a.block_size);
-        }
-      }
-      {  // V(j)
-        const int st = j % NV;
-        const uint32_t ph = static_cast<uint32_t>(j / NV) & 1u;
-        const int kv0 = (j_begin + j) * kP2TileN;
-        const bool tail = kv0 + kP2TileN > kv_len;  // at most one such tile per sequence
-        const uint32_t full_bar = tail ? bar(L::bVTail) : bar(L::bVFull + st);
-        if (lane == 0) {
-          ptx::mbar_wait(bar(L::bVEmpty + st), ph ^ 1u);
-          ptx::mbar_arrive_expect_tx(full_bar, tx);
-        }
-        __syncwarp();
-        const uint32_t dst0 = smem_base + L::kV + st * kP2Tile;
-        if (lane < n_valid) {
-          const uint32_t dst = dst0 + lane * page_half_bytes;
-          ptx::tma_load_3d(dst, &tm_v, full_bar, 0, kvh, blk * a.block_size);
-          ptx::tma_load_3d(dst + kP2Half, &tm_v, full_bar, 64, kvh, blk * a.block_size);
-        }
-        if (tail) {
-          // Keys at or beyond kv_len carry P == 0, but their V rows are whatever the pool / stale shared memory holds:
-          // zero them (0 * NaN must not reach O), then publish the tile.
-          ptx::mbar_wait(bar(L::bVTail), 0);
-          uint8_t* vt = smem_gen + L::kV + st * kP2Tile;
-          const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-          for (int r = max(0, kv_len - kv0) + lane; r < kP2TileN; r += 32) {
-            uint4* row0 = reinterpret_cast<uint4*>(vt + r * 128);
-            uint4* row1 = reinterpret_cast<uint4*>(vt + kP2Half + r * 128);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              row0[e] = z;
-              row1[e] = z;
-            }
+        for (int t = 0; t < 2; ++t) {
+          if (nt[t] > 0) {
+            const uint32_t dst = smem_base + L::kQ + t * kP2Tile;
+            ptx::mbar_arrive_expect_tx(bar(L::bQFull + t), q_bytes);
+            ptx::tma_load_3d(dst, &tm_q, bar(L::bQFull + t), 0, kvh * a.group, q_start + i0 + t * a.tq);
+            ptx::tma_load_3d(dst + kP2Half, &tm_q, bar(L::bQFull + t), 64, kvh * a.group, q_start + i0 + t * a.tq);
           }
-          ptx::fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(bar(L::bVFull + st));
         }
       }
-    }
-  } else if (warp == 9) {
-    // ================================================ MMA issuer ==================================================
-    if (lane == 0) {
+      __syncwarp();
+      const uint32_t page_half_bytes = static_cast<uint32_t>(a.block_size) * 128u;
+      for (int j = 0; j < n_all; ++j) {
+        const int page0 = (j_begin + j) * pages_per_tile;
+        const int n_valid = max(0, min(pages_per_tile, n_pages - page0));
+        int blk_lane = 0;
+        if (lane < n_valid) blk_lane = __ldg(a.block_tables + blk0 + page0 + lane);  // lane p holds page p of the tile
+        const uint32_t tx = static_cast<uint32_t>(n_valid) * 2u * page_half_bytes;
+        {  // K(j)
+          const int st = j % NK;
+          ptx::mbar_wait(bar(L::bKEmpty + st), (static_cast<uint32_t>(j / NK) & 1u) ^ 1u);
+          const uint32_t full_bar = bar(L::bKFull + st);
+          uint32_t dst = smem_base + L::kK + st * kP2Tile;
+          if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(full_bar, tx);
+          __syncwarp();
+          for (int p = 0; p < n_valid; ++p, dst += page_half_bytes) {
+            const int slot0 = __shfl_sync(0xffffffffu, blk_lane, p) * a.block_size;
+            if (ptx::elect_one()) {
+              ptx::tma_load_3d(dst, &tm_k, full_bar, 0, kvh, slot0);
+              ptx::tma_load_3d(dst + kP2Half, &tm_k, full_bar, 64, kvh, slot0);
+            }
+            __syncwarp();
+          }
+        }
+        {  // V(j)
+          const int st = j % NV;
+          const int kv0 = (j_begin + j) * kP2TileN;
+          const bool tail = kv0 + kP2TileN > kv_len;  // at most one such tile per sequence
+          ptx::mbar_wait(bar(L::bVEmpty + st), (static_cast<uint32_t>(j / NV) & 1u) ^ 1u);
+          const uint32_t full_bar = tail ? bar(L::bVTail) : bar(L::bVFull + st);
+          uint32_t dst = smem_base + L::kV + st * kP2Tile;
+          if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(full_bar, tx);
+          __syncwarp();
+          for (int p = 0; p < n_valid; ++p, dst += page_half_bytes) {
+            const int slot0 = __shfl_sync(0xffffffffu, blk_lane, p) * a.block_size;
+            if (ptx::elect_one()) {
+              ptx::tma_load_3d(dst, &tm_v, full_bar, 0, kvh, slot0);
+              ptx::tma_load_3d(dst + kP2Half, &tm_v, full_bar, 64, kvh, slot0);
+            }
+            __syncwarp();
+          }
+          if (tail) {
+            // Keys at or beyond kv_len carry P == 0, but their V rows are whatever the pool / stale shared memory holds:
+            // zero them (0 * NaN must not reach O), then publish the tile.
+            ptx::mbar_wait(bar(L::bVTail), 0);
+            uint8_t* vt = smem_gen + L::kV + st * kP2Tile;
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+            for (int r = max(0, kv_len - kv0) + lane; r < kP2TileN; r += 32) {
+              uint4* row0 = reinterpret_cast<uint4*>(vt + r * 128);
+              uint4* row1 = reinterpret_cast<uint4*>(vt + kP2Half + r * 128);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                row0[e] = z;
+                row1[e] = z;
+              }
+            }
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (ptx::elect_one()) ptx::mbar_arrive(bar(L::bVFull + st));
+            __syncwarp();
+          }
+        }
+      }
+    } else if (warp == 9) {
+      // ================================================ MMA issuer ==================================================
       constexpr uint32_t idesc_qk = ptx::make_idesc_f16(kBf16, false, false, kP2TileM, kP2TileN);
       constexpr uint32_t idesc_pv = ptx::make_idesc_f16(kBf16, false, true, kP2TileM, kP2D);
-      auto issue_qk = [&](int t, int st) {
-        const uint32_t q_addr = smem_base + L::kQ + t * kP2Tile;
-        const uint32_t k_addr = smem_base + L::kK + st * kP2Tile;
+      // Descriptors of the operand bases, built once; a k-step only adds a constant to the 14-bit start-address field.
+      const uint64_t desc_q0 = ptx::make_smem_desc_sw128(smem_base + L::kQ, 16, 1024);
+      const uint64_t desc_k0 = ptx::make_smem_desc_sw128(smem_base + L::kK, 16, 1024);
+      const uint64_t desc_v0 = ptx::make_smem_desc_sw128(smem_base + L::kV, kP2Half, 1024);
+      auto issue_qk = [&](int t, int st) {  // S_t = Q_t . K(st)^T
+        const uint64_t dq = desc_q0 + static_cast<uint64_t>((t * kP2Tile) >> 4);
+        const uint64_t dk = desc_k0 + static_cast<uint64_t>((st * kP2Tile) >> 4);
         const uint32_t tmem_s = tmem_base + kP2ColS + t * 128;
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {  // 2 halves x 4 k-steps of 16 dims; both operands K-major, 8-row groups 1024 B apart
-          const uint32_t off = (kk >> 2) * kP2Half + (kk & 3) * 32;
-          ptx::mma_f16_ss(tmem_s, ptx::make_smem_desc_sw128(q_addr + off, 16, 1024),
-                          ptx::make_smem_desc_sw128(k_addr + off, 16, 1024), idesc_qk, kk > 0);
+          const uint64_t off = static_cast<uint64_t>(((kk >> 2) * kP2Half + (kk & 3) * 32) >> 4);
+          ptx::mma_f16_ss(tmem_s, dq + off, dk + off, idesc_qk, kk > 0);
         }
         ptx::mma_commit(bar(L::bSFull + t));
       };
-      auto issue_pv = [&](int t, int st, bool accumulate) {
-        const uint32_t v_addr = smem_base + L::kV + st * kP2Tile;
+      auto issue_pv = [&](int t, int st, bool accumulate) {  // O_t (+)= P_t . V(st)
+        const uint64_t dv = desc_v0 + static_cast<uint64_t>((st * kP2Tile) >> 4);
         const uint32_t tmem_p = tmem_base + kP2ColS + t * 128;
         const uint32_t tmem_o = tmem_base + kP2ColO + t * 128;
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {  // 8 k-steps of 16 tokens; A = P in TMEM (8 columns per step), B = V MN-major
-          ptx::mma_f16_ts(tmem_o, tmem_p + kk * 8, ptx::make_smem_desc_sw128(v_addr + kk * 2048, kP2Half, 1024), idesc_pv,
-                          accumulate || (kk > 0));
+          ptx::mma_f16_ts(tmem_o, tmem_p + kk * 8, dv + static_cast<uint64_t>((kk * 2048) >> 4), idesc_pv, accumulate || (kk > 0));
         }
       };
       // prologue: S_t(0)
@@ -259,38 +268,36 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         if (nt[t] > 0) {
           ptx::mbar_wait(bar(L::bQFull + t), 0);
           ptx::tc_fence_after_sync();
-          issue_qk(t, 0);
+          if (ptx::elect_one()) issue_qk(t, 0);
+          __syncwarp();
         }
       }
-      ptx::mma_commit(bar(L::bKEmpty + 0));
+      if (ptx::elect_one()) ptx::mma_commit(bar(L::bKEmpty + 0));
+      __syncwarp();
       for (int j = 0; j < n_all; ++j) {
         const int stv = j % NV;
         const int stk = (j + 1) % NK;
-        const uint32_t phk = static_cast<uint32_t>((j + 1) / NK) & 1u;
         ptx::mbar_wait(bar(L::bVFull + stv), static_cast<uint32_t>(j / NV) & 1u);
-        bool k_waited = false;
+        if (j + 1 < n_all) ptx::mbar_wait(bar(L::bKFull + stk), static_cast<uint32_t>((j + 1) / NK) & 1u);
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
-          if (j < nt[t]) {
-            ptx::mbar_wait(bar(L::bPFull + t), static_cast<uint32_t>(j) & 1u);
-            ptx::tc_fence_after_sync();
-            issue_pv(t, stv, j > 0);
-            if (j == nt[t] - 1) ptx::mma_commit(bar(L::bOFull + t));
-          }
-          if (t == 1) ptx::mma_commit(bar(L::bVEmpty + stv));  // V(j) reusable once both tiles' P.V have read it
-          if (j + 1 < nt[t]) {
-            if (!k_waited) {
-              ptx::mbar_wait(bar(L::bKFull + stk), phk);
-              ptx::tc_fence_after_sync();
-              k_waited = true;
+          const bool has_pv = j < nt[t];
+          const bool has_qk = j + 1 < nt[t];
+          if (has_pv) ptx::mbar_wait(bar(L::bPFull + t), static_cast<uint32_t>(j) & 1u);
+          ptx::tc_fence_after_sync();
+          if (ptx::elect_one()) {
+            if (has_pv) {
+              issue_pv(t, stv, j > 0);
+              if (j == nt[t] - 1) ptx::mma_commit(bar(L::bOFull + t));
             }
-            issue_qk(t, stk);
+            if (t == 1) ptx::mma_commit(bar(L::bVEmpty + stv));  // V(j) reusable once both tiles' P.V have read it
+            if (has_qk) issue_qk(t, stk);
+            if (t == 1 && j + 1 < n_all) ptx::mma_commit(bar(L::bKEmpty + stk));
           }
+          __syncwarp();
         }
-        if (j + 1 < n_all) ptx::mma_commit(bar(L::bKEmpty + stk));
       }
     }
-  }
   } else {
     // ================================================ softmax + epilogue ===========================================
     ptx::setmaxnreg_inc<208>();
@@ -369,7 +376,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
             const float2 x2 = ffma2(make_float2(__uint_as_float(s[c][e]), __uint_as_float(s[c][e + 1])), sc2, nm2);
-            const float2 p2 = make_float2(fast_exp2(x2.x), fast_exp2(x2.y));
+            const float2 p2 = (((e >> 1) & 3) >= 4 - PF) ? exp2_poly2(x2) : make_float2(fast_exp2(x2.x), fast_exp2(x2.y));
             ls2[(e >> 1) & 1] = fadd2(ls2[(e >> 1) & 1], p2);
             pk[e >> 1] = pack2<T>(p2.x, p2.y);
           }
@@ -440,20 +447,20 @@ bool attn_pair_supported(const HiAttnArgs& args) {
          args.n_blocks > 0;
 }
 
-template <typename T>
+template <typename T, int PF>
 static int launch_pair_t(const HiAttnArgs& args, const P2Args& a, const CUtensorMap& mq, const CUtensorMap& mk,
                          const CUtensorMap& mv, cudaStream_t stream) {
   constexpr int NK = 2, NV = 2;
   using L = P2Smem<NK, NV>;
   static bool configured = false;
   if (!configured) {
-    HI_CUDA(cudaFuncSetAttribute(paged_attn_pair_kernel<T, NK, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamicBytes));
+    HI_CUDA(cudaFuncSetAttribute(paged_attn_pair_kernel<T, NK, NV, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamicBytes));
     configured = true;
   }
   const int n_pairs = (args.max_q_len + 2 * a.tq - 1) / (2 * a.tq);
   const dim3 grid(n_pairs * a.n_splits, args.n_kv_heads, args.n_seqs);
   timing_mark_start(stream);
-  paged_attn_pair_kernel<T, NK, NV><<<grid, kP2Threads, L::kDynamicBytes, stream>>>(mq, mk, mv, a);
+  paged_attn_pair_kernel<T, NK, NV, PF><<<grid, kP2Threads, L::kDynamicBytes, stream>>>(mq, mk, mv, a);
   timing_mark_stop(stream);
   note_launch();
   HI_CUDA(cudaGetLastError());
@@ -514,8 +521,17 @@ int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
   rc = pool_map(&mv, args.dtype, args.value_cache, n_slots, args.n_kv_heads, args.block_size);
   if (rc != HI_OK) return rc;
 
-  rc = args.dtype == HI_BF16 ? launch_pair_t<__nv_bfloat16>(args, a, mq, mk, mv, stream)
-                             : launch_pair_t<__half>(args, a, mq, mk, mv, stream);
+  int poly = 1;  // exponentials per 4 moved from MUFU to the FMA pipes
+  if (const char* env = getenv("HI_PAIR_POLY")) poly = atoi(env);  // tuning override
+  if (args.dtype == HI_BF16) {
+    rc = poly <= 0 ? launch_pair_t<__nv_bfloat16, 0>(args, a, mq, mk, mv, stream)
+       : poly == 1 ? launch_pair_t<__nv_bfloat16, 1>(args, a, mq, mk, mv, stream)
+                   : launch_pair_t<__nv_bfloat16, 2>(args, a, mq, mk, mv, stream);
+  } else {
+    rc = poly <= 0 ? launch_pair_t<__half, 0>(args, a, mq, mk, mv, stream)
+       : poly == 1 ? launch_pair_t<__half, 1>(args, a, mq, mk, mv, stream)
+                   : launch_pair_t<__half, 2>(args, a, mq, mk, mv, stream);
+  }
   if (rc != HI_OK || a.n_splits == 1) return rc;
 
   SimtArgs m{};

@@ -165,4 +165,23 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
   return d;
 }
 
+// exp2 on the FMA / ALU pipes for two values at once (Cody-Waite range reduction + degree-3 minimax polynomial, max
+// relative error 7.5e-5 - far below the 16-bit rounding P gets anyway).  Used for a fraction of the softmax exponentials
+// so that MUFU.EX2 (16 lanes/clk/SM) stops being the only pipe that limits the softmax warps.  x <= ~100; x -> -inf gives
+// 2^-126 (~1e-38) instead of 0.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -126.f);
+  x.y = fmaxf(x.y, -126.f);
+  const float2 r = fadd2(x, make_float2(12582912.f, 12582912.f));     // 1.5 * 2^23: low mantissa bits of r = round(x)
+  const float2 n = fadd2(r, make_float2(-12582912.f, -12582912.f));
+  const float2 f = ffma2(n, make_float2(-1.f, -1.f), x);               // f in [-0.5, 0.5]
+  float2 p = ffma2(f, make_float2(0.0551716685f, 0.0551716685f), make_float2(0.2426111400f, 0.2426111400f));
+  p = ffma2(p, f, make_float2(0.6932609677f, 0.6932609677f));
+  p = ffma2(p, f, make_float2(0.9999280572f, 0.9999280572f));
+  float2 y;
+  y.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(r.x) << 23));  // add round(x) to the exponent field
+  y.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(r.y) << 23));
+  return y;
+}
+
 }  // namespace hi
