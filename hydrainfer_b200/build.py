@@ -30,6 +30,10 @@ NVCC_FLAGS = [
 ]
 
 
+# Extra -D flags for debug builds, e.g. HI_BUILD_DEFINES="-DHI_MBAR_DEBUG" (part of the build stamp).
+NVCC_FLAGS += [f for f in os.environ.get("HI_BUILD_DEFINES", "").split() if f]
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and Path(cand).exists():

@@ -1,23 +1,29 @@
-// Paged causal attention on tcgen05 — the prefill / chunked-prefill kernel: two query tiles per CTA, ping-ponged.
+// Paged causal attention on tcgen05 — the prefill / chunked-prefill kernel: two query tiles per CTA, S double-buffered.
 //
 // Same function as TorchCausalGroupedQueryPageAttentionHandler.forward (reference
 // hydrainfer/layer/causal_attention.py:307-374) and the same operand staging as attn_tc.cu (TMA boxes per page written
 // 128B-swizzled = canonical UMMA layouts, S and O in TMEM, P fed to the second product straight from TMEM).  What changes
 // is the schedule, built around the two facts that bound attention on this part (B300_MICROARCH.md, tcgen05 / pipe rates):
-// a 128x128 score tile costs 1024 tensor-pipe cycles (Q.K^T + P.V) and 1024 MUFU cycles (16 ex2/clk/SM), and every K/V
-// tile costs 64 KiB of L2 -> shared-memory traffic.
+// a 128-row x 64-key score tile costs 512 tensor-pipe cycles (Q.K^T + P.V) and 512 MUFU cycles (16 ex2/clk/SM), and
+// every staged K/V byte costs L2 -> shared-memory bandwidth.
 //
 //   * One CTA owns TWO 128-row query tiles of the same (sequence, KV head) and ONE K/V ring: every staged K/V byte feeds
-//     both tiles (half the L2 -> SM traffic of one tile per CTA).  One CTA per SM: 512 TMEM columns = S0 | S1 | O0 | O1.
-//   * Two softmax warpgroups (thread = row = TMEM lane).  The single MMA-issuing thread interleaves the tiles
-//         ... P0.V(j)  Q0.K(j+1)  P1.V(j)  Q1.K(j+1)  P0.V(j+1) ...
-//     so while warpgroup 0 turns S0(j+1) into P0(j+1) the tensor pipe runs tile 1's products, and vice versa.
-//   * A softmax thread reads its 128 scores from TMEM ONCE and keeps them in registers (setmaxnreg moves registers from
-//     the producer / MMA warpgroup to the softmax warpgroups: 208 vs 72): max, exp2, row sum and the 16-bit pack all run
-//     from registers; P overwrites S.
-//   * O is rescaled lazily (only when a row max grows by more than 2^8) by the softmax thread itself: S_t(j) complete
-//     implies P_t.V(j-1) complete because the tensor pipe executes one thread's MMAs in order.
-//   * The TMA producer zeroes V rows at or beyond kv_len of the last tile (P is 0 there, the pool bytes are arbitrary).
+//     both tiles.  One CTA per SM; 512 TMEM columns = per tile { S[0] (64) | S[1] (64) | O (128) }.
+//   * KV is walked in 64-key steps and S is DOUBLE-BUFFERED: the MMA lane of tile t issues
+//         ... P_t.V(j)  Q_t.K(j+2)  P_t.V(j+1)  Q_t.K(j+3) ...
+//     so S_t(j+1) is already complete when the softmax warpgroup of tile t finishes P_t(j): the softmax warps never wait for
+//     the tensor pipe, and the tensor pipe only waits for P.  (With a single S buffer the chain
+//     softmax -> P.V -> Q.K -> softmax is serial per tile and both pipes idle ~45 % of the time: measured.)
+//   * Issue bandwidth is a first-class resource: a tcgen05.mma of these shapes runs in 32-64 cycles (tools/probes/
+//     mma_probe.cu), and every extra instruction the issuing lane executes between two MMAs costs ~10 cycles.  So each tile
+//     has its OWN MMA-issuing warp (9 and 10), K and V have their own TMA warps (8 and 11), and a step costs each MMA warp
+//     3 waits + 3 commits; those warps stay converged and elect the issuing lane so that descriptors live in uniform
+//     registers.
+//   * Two softmax warpgroups (thread = row = TMEM lane): a thread reads its 64 scores from TMEM once, keeps them in
+//     registers for max / exp2 / row sum / 16-bit pack, and writes P over the S buffer it came from.
+//   * O is rescaled lazily (only when a row max grows by more than 2^8) by the softmax thread itself, after waiting for
+//     P_t.V(j-1) (its own commit barrier; S_t(j) no longer implies it).
+//   * The TMA producer zeroes V rows at or beyond kv_len of the last step (P is 0 there, the pool bytes are arbitrary).
 // Rows are (token, head-in-group) pairs, so GQA groups share the staged K/V exactly as in attn_tc.cu.
 #include <cuda.h>
 
@@ -31,15 +37,17 @@
 
 namespace hi {
 
-constexpr int kP2Threads = 384;               // warps 0-3 / 4-7: softmax of tile 0 / 1; warp 8: TMA; warp 9: MMA; 10-11 idle
+constexpr int kP2Threads = 384;               // warps 0-3 / 4-7: softmax of tile 0 / 1; 8: K TMA; 9 / 10: MMA of tile 0 / 1; 11: V TMA
 constexpr int kP2TileM = 128;
-constexpr int kP2TileN = 128;
+constexpr int kP2TileN = 64;                  // keys per step
 constexpr int kP2D = 128;
-constexpr int kP2Half = kP2TileM * 128;       // one 64-dim half of a 128-row tile: 16 KiB
-constexpr int kP2Tile = 2 * kP2Half;          // 32 KiB
+constexpr int kP2QHalf = kP2TileM * 128;      // one 64-dim half of a 128-row Q tile: 16 KiB
+constexpr int kP2QTile = 2 * kP2QHalf;        // 32 KiB
+constexpr int kP2Half = kP2TileN * 128;       // one 64-dim half of a 64-key K or V step: 8 KiB
+constexpr int kP2Tile = 2 * kP2Half;          // 16 KiB
 constexpr uint32_t kP2TmemCols = 512;
-constexpr uint32_t kP2ColS = 0;               // S_t at columns [128 t, 128 t + 128); P_t aliases its first 64 columns
-constexpr uint32_t kP2ColO = 256;             // O_t at columns [256 + 128 t, ...)
+constexpr uint32_t kP2ColTile = 256;          // columns per query tile: S[0] at +0, S[1] at +64, O at +128
+constexpr uint32_t kP2ColO = 128;
 constexpr float kP2Rescale = 8.0f;
 
 struct P2Args {
@@ -53,15 +61,17 @@ struct P2Args {
   int tq;            // query tokens per 128-row tile: 128 / group
   float scale_log2;
   int n_splits;
-  int tiles_per_split;
+  int tiles_per_split;  // in 64-key steps
   float* part_o;
   float* part_ml;
+  int debug;  // timing experiments only (HI_PAIR_DEBUG): bit 0 = softmax warps skip their math, bit 1 = no MMA is issued,
+              // bit 2 = K/V tiles are not loaded (barriers only)
 };
 
 template <int NK, int NV>
 struct P2Smem {
   static constexpr int kQ = 0;                          // two tiles
-  static constexpr int kK = 2 * kP2Tile;
+  static constexpr int kK = 2 * kP2QTile;
   static constexpr int kV = kK + NK * kP2Tile;
   static constexpr int kBars = kV + NV * kP2Tile;
   static constexpr int bQFull = 0;                      // [2]
@@ -69,9 +79,10 @@ struct P2Smem {
   static constexpr int bKEmpty = bKFull + NK;
   static constexpr int bVFull = bKEmpty + NK;           // [NV]
   static constexpr int bVEmpty = bVFull + NV;
-  static constexpr int bSFull = bVEmpty + NV;           // [2]
-  static constexpr int bPFull = bSFull + 2;             // [2]
-  static constexpr int bOFull = bPFull + 2;             // [2]
+  static constexpr int bSFull = bVEmpty + NV;           // [tile][buffer]
+  static constexpr int bPFull = bSFull + 4;             // [tile][buffer]: a warpgroup may run two steps ahead of the MMA lane
+  static constexpr int bPvDone = bPFull + 4;            // [2] P_t.V(n_t - 2) complete (lazy rescale in the last step)
+  static constexpr int bOFull = bPvDone + 2;            // [2]
   static constexpr int bVTail = bOFull + 2;
   static constexpr int kNumBars = bVTail + 1;
   static constexpr int kTmemPtr = kBars + kNumBars * 8;
@@ -85,6 +96,7 @@ __global__ void __launch_bounds__(kP2Threads, 1)
 paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                        const __grid_constant__ CUtensorMap tm_v, const P2Args a) {
   using L = P2Smem<NK, NV>;
+  static_assert(NK == 4 && NV == 4, "ring stages are addressed as step & 3");
   constexpr bool kBf16 = !std::is_same<T, __half>::value;
 
   // ---- which pair of query tiles -----------------------------------------------------------------------------------
@@ -100,7 +112,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   if (pair < 0) return;
   const int i0 = pair * pair_tokens;
   const int j_begin = sp * a.tiles_per_split;
-  // nt[t]: KV tiles walked for query tile t (local tile index j = 0 .. nt[t]-1 is global tile j_begin + j)
+  // nt[t]: KV steps walked for query tile t (local step j = 0 .. nt[t]-1 is global step j_begin + j)
   int nt[2];
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
@@ -110,8 +122,8 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     } else {
       const int i_last = min(q_len, first + a.tq) - 1;
       const int kv_end = i_last + (kv_len - q_len) + 1;  // keys [0, kv_end) are visible to the tile
-      const int n_all = (kv_end + kP2TileN - 1) / kP2TileN;
-      nt[t] = max(0, min(n_all - j_begin, a.tiles_per_split));
+      const int n_vis = (kv_end + kP2TileN - 1) / kP2TileN;
+      nt[t] = max(0, min(n_vis - j_begin, a.tiles_per_split));
     }
   }
   const int n_all = max(nt[0], nt[1]);
@@ -123,7 +135,8 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
-  auto bar = [&](int idx) -> uint32_t { return smem_base + L::kBars + idx * 8; };
+  const uint32_t bars = smem_base + L::kBars;
+  auto bar = [&](int idx) -> uint32_t { return bars + idx * 8; };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + L::kTmemPtr);
 
   const int warp = threadIdx.x >> 5;
@@ -132,8 +145,9 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   // ---- one-time setup ------------------------------------------------------------------------------------------------
   if (threadIdx.x == 0) {
     for (int i = 0; i < L::kNumBars; ++i) ptx::mbar_init(bar(i), 1);
-    ptx::mbar_init(bar(L::bPFull + 0), kP2TileM);  // every softmax thread of the tile arrives
-    ptx::mbar_init(bar(L::bPFull + 1), kP2TileM);
+    for (int i = 0; i < NK; ++i) ptx::mbar_init(bar(L::bKEmpty + i), 2);  // released by both MMA lanes
+    for (int i = 0; i < NV; ++i) ptx::mbar_init(bar(L::bVEmpty + i), 2);
+    for (int i = 0; i < 4; ++i) ptx::mbar_init(bar(L::bPFull + i), kP2TileM);  // every softmax thread of the tile arrives
     ptx::fence_mbar_init();
   }
   if (warp == 8) {
@@ -151,151 +165,153 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp >= 8) {
-    // ===================================== producer / MMA warpgroup (warps 10-11 idle) ================================
-    // Both roles keep the whole warp converged (every lane waits on the barriers) and issue the asynchronous
-    // instructions from one elected lane: warp-uniform control flow lets the compiler keep descriptors, barrier
-    // addresses and loop state in uniform registers instead of emulating them per lane.
+    // ========================== TMA producers (warps 8, 11) and MMA lanes (warps 9, 10) ==============================
     ptx::setmaxnreg_dec<72>();
-    if (warp == 8) {
-      // ================================================ TMA producer ================================================
-      if (ptx::elect_one()) {
+    if (warp == 8 || warp == 11) {
+      // ---- TMA producer: warp 8 stages Q and the K ring, warp 11 the V ring.  The warp stays converged; one elected lane
+      // issues.  Lane p holds the block id of page p of the step.
+      const bool is_k = warp == 8;
+      const CUtensorMap* tm = is_k ? &tm_k : &tm_v;
+      if (is_k && ptx::elect_one()) {
         const uint32_t q_bytes = 2u * static_cast<uint32_t>(a.group * a.tq) * 128u;
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           if (nt[t] > 0) {
-            const uint32_t dst = smem_base + L::kQ + t * kP2Tile;
+            const uint32_t dst = smem_base + L::kQ + t * kP2QTile;
             ptx::mbar_arrive_expect_tx(bar(L::bQFull + t), q_bytes);
             ptx::tma_load_3d(dst, &tm_q, bar(L::bQFull + t), 0, kvh * a.group, q_start + i0 + t * a.tq);
-            ptx::tma_load_3d(dst + kP2Half, &tm_q, bar(L::bQFull + t), 64, kvh * a.group, q_start + i0 + t * a.tq);
+            ptx::tma_load_3d(dst + kP2QHalf, &tm_q, bar(L::bQFull + t), 64, kvh * a.group, q_start + i0 + t * a.tq);
           }
         }
       }
       __syncwarp();
       const uint32_t page_half_bytes = static_cast<uint32_t>(a.block_size) * 128u;
-      for (int j = 0; j < n_all; ++j) {
+      const int b_full = is_k ? L::bKFull : L::bVFull;
+      const int b_empty = is_k ? L::bKEmpty : L::bVEmpty;
+      const uint32_t ring = smem_base + (is_k ? L::kK : L::kV);
+      // Lane p holds the block id of page p of the step; the ids of step j+1 are fetched while step j is being issued.
+      auto pages_of = [&](int j, int& n_valid) -> int {
         const int page0 = (j_begin + j) * pages_per_tile;
-        const int n_valid = max(0, min(pages_per_tile, n_pages - page0));
-        int blk_lane = 0;
-        if (lane < n_valid) blk_lane = __ldg(a.block_tables + blk0 + page0 + lane);  // lane p holds page p of the tile
+        n_valid = (a.debug & 4) ? 0 : max(0, min(pages_per_tile, n_pages - page0));
+        return (j < n_all && lane < n_valid) ? __ldg(a.block_tables + blk0 + page0 + lane) : 0;
+      };
+      int n_valid_next = 0;
+      int blk_next = pages_of(0, n_valid_next);
+      for (int j = 0; j < n_all; ++j) {
+        const int n_valid = n_valid_next;
+        const int blk_lane = blk_next;
+        blk_next = pages_of(j + 1, n_valid_next);
         const uint32_t tx = static_cast<uint32_t>(n_valid) * 2u * page_half_bytes;
-        {  // K(j)
-          const int st = j % NK;
-          ptx::mbar_wait(bar(L::bKEmpty + st), (static_cast<uint32_t>(j / NK) & 1u) ^ 1u);
-          const uint32_t full_bar = bar(L::bKFull + st);
-          uint32_t dst = smem_base + L::kK + st * kP2Tile;
-          if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(full_bar, tx);
-          __syncwarp();
-          for (int p = 0; p < n_valid; ++p, dst += page_half_bytes) {
-            const int slot0 = __shfl_sync(0xffffffffu, blk_lane, p) * a.block_size;
-            if (ptx::elect_one()) {
-              ptx::tma_load_3d(dst, &tm_k, full_bar, 0, kvh, slot0);
-              ptx::tma_load_3d(dst + kP2Half, &tm_k, full_bar, 64, kvh, slot0);
-            }
-            __syncwarp();
+        const int st = j & 3;
+        const int kv0 = (j_begin + j) * kP2TileN;
+        const bool tail = !is_k && (kv0 + kP2TileN > kv_len);  // at most one such step per sequence
+        ptx::mbar_wait(bar(b_empty + st), (static_cast<uint32_t>(j >> 2) & 1u) ^ 1u);
+        const uint32_t full_bar = tail ? bar(L::bVTail) : bar(b_full + st);
+        uint32_t dst = ring + st * kP2Tile;
+        if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(full_bar, tx);
+        __syncwarp();
+        for (int p = 0; p < n_valid; ++p, dst += page_half_bytes) {
+          const int slot0 = __shfl_sync(0xffffffffu, blk_lane, p) * a.block_size;
+          if (ptx::elect_one()) {
+            ptx::tma_load_3d(dst, tm, full_bar, 0, kvh, slot0);
+            ptx::tma_load_3d(dst + kP2Half, tm, full_bar, 64, kvh, slot0);
           }
+          __syncwarp();
         }
-        {  // V(j)
-          const int st = j % NV;
-          const int kv0 = (j_begin + j) * kP2TileN;
-          const bool tail = kv0 + kP2TileN > kv_len;  // at most one such tile per sequence
-          ptx::mbar_wait(bar(L::bVEmpty + st), (static_cast<uint32_t>(j / NV) & 1u) ^ 1u);
-          const uint32_t full_bar = tail ? bar(L::bVTail) : bar(L::bVFull + st);
-          uint32_t dst = smem_base + L::kV + st * kP2Tile;
-          if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(full_bar, tx);
-          __syncwarp();
-          for (int p = 0; p < n_valid; ++p, dst += page_half_bytes) {
-            const int slot0 = __shfl_sync(0xffffffffu, blk_lane, p) * a.block_size;
-            if (ptx::elect_one()) {
-              ptx::tma_load_3d(dst, &tm_v, full_bar, 0, kvh, slot0);
-              ptx::tma_load_3d(dst + kP2Half, &tm_v, full_bar, 64, kvh, slot0);
-            }
-            __syncwarp();
-          }
-          if (tail) {
-            // Keys at or beyond kv_len carry P == 0, but their V rows are whatever the pool / stale shared memory holds:
-            // zero them (0 * NaN must not reach O), then publish the tile.
-            ptx::mbar_wait(bar(L::bVTail), 0);
-            uint8_t* vt = smem_gen + L::kV + st * kP2Tile;
-            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-            for (int r = max(0, kv_len - kv0) + lane; r < kP2TileN; r += 32) {
-              uint4* row0 = reinterpret_cast<uint4*>(vt + r * 128);
-              uint4* row1 = reinterpret_cast<uint4*>(vt + kP2Half + r * 128);
+        if (tail) {
+          // Keys at or beyond kv_len carry P == 0, but their V rows are whatever the pool / stale shared memory holds:
+          // zero them (0 * NaN must not reach O), then publish the step.
+          ptx::mbar_wait(bar(L::bVTail), 0);
+          uint8_t* vt = smem_gen + L::kV + st * kP2Tile;
+          const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+          for (int r = max(0, kv_len - kv0) + lane; r < kP2TileN; r += 32) {
+            uint4* row0 = reinterpret_cast<uint4*>(vt + r * 128);
+            uint4* row1 = reinterpret_cast<uint4*>(vt + kP2Half + r * 128);
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                row0[e] = z;
-                row1[e] = z;
-              }
+            for (int e = 0; e < 8; ++e) {
+              row0[e] = z;
+              row1[e] = z;
             }
-            ptx::fence_proxy_async_smem();
-            __syncwarp();
-            if (ptx::elect_one()) ptx::mbar_arrive(bar(L::bVFull + st));
-            __syncwarp();
           }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (ptx::elect_one()) ptx::mbar_arrive(bar(L::bVFull + st));
+          __syncwarp();
         }
       }
-    } else if (warp == 9) {
-      // ================================================ MMA issuer ==================================================
+    } else {
+      // ---- MMA warp of tile t: the warp stays converged (every lane polls the barriers), one elected lane issues ------------
+      const int t = warp - 9;
+      const int n_t = t ? nt[1] : nt[0];
       constexpr uint32_t idesc_qk = ptx::make_idesc_f16(kBf16, false, false, kP2TileM, kP2TileN);
       constexpr uint32_t idesc_pv = ptx::make_idesc_f16(kBf16, false, true, kP2TileM, kP2D);
-      // Descriptors of the operand bases, built once; a k-step only adds a constant to the 14-bit start-address field.
-      const uint64_t desc_q0 = ptx::make_smem_desc_sw128(smem_base + L::kQ, 16, 1024);
-      const uint64_t desc_k0 = ptx::make_smem_desc_sw128(smem_base + L::kK, 16, 1024);
-      const uint64_t desc_v0 = ptx::make_smem_desc_sw128(smem_base + L::kV, kP2Half, 1024);
-      auto issue_qk = [&](int t, int st) {  // S_t = Q_t . K(st)^T
-        const uint64_t dq = desc_q0 + static_cast<uint64_t>((t * kP2Tile) >> 4);
-        const uint64_t dk = desc_k0 + static_cast<uint64_t>((st * kP2Tile) >> 4);
-        const uint32_t tmem_s = tmem_base + kP2ColS + t * 128;
+      // Descriptors of the operand bases, built once; stages and k-steps only add to the 14-bit start-address field.
+      const uint64_t desc_q = ptx::make_smem_desc_sw128(smem_base + L::kQ + t * kP2QTile, 16, 1024);
+      const uint64_t desc_k = ptx::make_smem_desc_sw128(smem_base + L::kK, 16, 1024);
+      const uint64_t desc_v = ptx::make_smem_desc_sw128(smem_base + L::kV, kP2Half, 1024);
+      const uint32_t tmem_t = tmem_base + t * kP2ColTile;
+      const uint32_t tmem_o = tmem_t + kP2ColO;
+      const bool no_mma = (a.debug & 2) != 0;
+      auto issue_qk = [&](int st, int buf) {  // S_t[buf] = Q_t . K(stage)^T; releases the K stage
+        const uint64_t dk = desc_k + static_cast<uint64_t>(st * (kP2Tile >> 4));
+        const uint32_t tmem_s = tmem_t + buf * kP2TileN;
+        if (!no_mma) {
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {  // 2 halves x 4 k-steps of 16 dims; both operands K-major, 8-row groups 1024 B apart
-          const uint64_t off = static_cast<uint64_t>(((kk >> 2) * kP2Half + (kk & 3) * 32) >> 4);
-          ptx::mma_f16_ss(tmem_s, dq + off, dk + off, idesc_qk, kk > 0);
+          for (int kk = 0; kk < 8; ++kk) {  // 2 halves x 4 k-steps of 16 dims; K-major operands, 8-row groups 1024 B apart
+            ptx::mma_f16_ss(tmem_s, desc_q + static_cast<uint64_t>(((kk >> 2) * kP2QHalf + (kk & 3) * 32) >> 4),
+                            dk + static_cast<uint64_t>(((kk >> 2) * kP2Half + (kk & 3) * 32) >> 4), idesc_qk, kk > 0);
+          }
         }
-        ptx::mma_commit(bar(L::bSFull + t));
+        ptx::mma_commit(bar(L::bSFull + 2 * t + buf));
+        ptx::mma_commit(bar(L::bKEmpty + st));
       };
-      auto issue_pv = [&](int t, int st, bool accumulate) {  // O_t (+)= P_t . V(st)
-        const uint64_t dv = desc_v0 + static_cast<uint64_t>((st * kP2Tile) >> 4);
-        const uint32_t tmem_p = tmem_base + kP2ColS + t * 128;
-        const uint32_t tmem_o = tmem_base + kP2ColO + t * 128;
+      auto issue_pv = [&](int st, int buf, bool accumulate) {  // O_t (+)= P_t[buf] . V(stage); releases the V stage
+        const uint64_t dv = desc_v + static_cast<uint64_t>(st * (kP2Tile >> 4));
+        const uint32_t tmem_p = tmem_t + buf * kP2TileN;
+        if (!no_mma) {
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {  // 8 k-steps of 16 tokens; A = P in TMEM (8 columns per step), B = V MN-major
-          ptx::mma_f16_ts(tmem_o, tmem_p + kk * 8, dv + static_cast<uint64_t>((kk * 2048) >> 4), idesc_pv, accumulate || (kk > 0));
+          for (int kk = 0; kk < 4; ++kk) {  // 4 k-steps of 16 keys; A = P in TMEM (8 columns per step), B = V MN-major
+            ptx::mma_f16_ts(tmem_o, tmem_p + kk * 8, dv + static_cast<uint64_t>((kk * 2048) >> 4), idesc_pv, accumulate || (kk > 0));
+          }
         }
+        ptx::mma_commit(bar(L::bVEmpty + st));
       };
-      // prologue: S_t(0)
-      ptx::mbar_wait(bar(L::bKFull + 0), 0);
+      // prologue: S_t(0) and S_t(1).  Steps at or beyond n_t (this tile sees fewer keys than its sibling) only release
+      // the ring stages.
+      if (n_t > 0) ptx::mbar_wait(bar(L::bQFull + t), 0);
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        if (nt[t] > 0) {
-          ptx::mbar_wait(bar(L::bQFull + t), 0);
-          ptx::tc_fence_after_sync();
-          if (ptx::elect_one()) issue_qk(t, 0);
-          __syncwarp();
-        }
-      }
-      if (ptx::elect_one()) ptx::mma_commit(bar(L::bKEmpty + 0));
-      __syncwarp();
-      for (int j = 0; j < n_all; ++j) {
-        const int stv = j % NV;
-        const int stk = (j + 1) % NK;
-        ptx::mbar_wait(bar(L::bVFull + stv), static_cast<uint32_t>(j / NV) & 1u);
-        if (j + 1 < n_all) ptx::mbar_wait(bar(L::bKFull + stk), static_cast<uint32_t>((j + 1) / NK) & 1u);
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const bool has_pv = j < nt[t];
-          const bool has_qk = j + 1 < nt[t];
-          if (has_pv) ptx::mbar_wait(bar(L::bPFull + t), static_cast<uint32_t>(j) & 1u);
+      for (int jj = 0; jj < 2; ++jj) {
+        if (jj < n_all) {
+          ptx::mbar_wait(bar(L::bKFull + jj), 0);
           ptx::tc_fence_after_sync();
           if (ptx::elect_one()) {
-            if (has_pv) {
-              issue_pv(t, stv, j > 0);
-              if (j == nt[t] - 1) ptx::mma_commit(bar(L::bOFull + t));
-            }
-            if (t == 1) ptx::mma_commit(bar(L::bVEmpty + stv));  // V(j) reusable once both tiles' P.V have read it
-            if (has_qk) issue_qk(t, stk);
-            if (t == 1 && j + 1 < n_all) ptx::mma_commit(bar(L::bKEmpty + stk));
+            if (jj < n_t) issue_qk(jj, jj); else ptx::mbar_arrive(bar(L::bKEmpty + jj));
           }
           __syncwarp();
         }
+      }
+      // step j: P_t.V(j), then Q_t.K(j+2) into the S buffer P_t(j) just vacated (in order behind P_t.V(j))
+      for (int j = 0; j < n_all; ++j) {
+        const int s = j & 3, s2 = (j + 2) & 3, buf = j & 1;
+        const bool has_pv = j < n_t;
+        const bool more = j + 2 < n_all;
+        ptx::mbar_wait(bar(L::bVFull + s), static_cast<uint32_t>(j >> 2) & 1u);
+        if (more) ptx::mbar_wait(bar(L::bKFull + s2), static_cast<uint32_t>((j + 2) >> 2) & 1u);
+        if (has_pv) ptx::mbar_wait(bar(L::bPFull + 2 * t + buf), static_cast<uint32_t>(j >> 1) & 1u);
+        ptx::tc_fence_after_sync();
+        if (ptx::elect_one()) {
+          if (has_pv) {
+            issue_pv(s, buf, j > 0);
+            if (j == n_t - 2) ptx::mma_commit(bar(L::bPvDone + t));
+            if (j == n_t - 1) ptx::mma_commit(bar(L::bOFull + t));
+          } else {
+            ptx::mbar_arrive(bar(L::bVEmpty + s));
+          }
+          if (more) {
+            if (j + 2 < n_t) issue_qk(s2, buf); else ptx::mbar_arrive(bar(L::bKEmpty + s2));
+          }
+        }
+        __syncwarp();
       }
     }
   } else {
@@ -304,8 +320,8 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     const int t = warp >> 2;                         // query tile of this warpgroup
     const int r = threadIdx.x & 127;                 // tile row == TMEM lane
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const uint32_t tmem_s = tmem_base + lane_base + kP2ColS + t * 128;
-    const uint32_t tmem_o = tmem_base + lane_base + kP2ColO + t * 128;
+    const uint32_t tmem_t = tmem_base + lane_base + t * kP2ColTile;
+    const uint32_t tmem_o = tmem_t + kP2ColO;
     const int tok = r / a.group;
     const int g = r - tok * a.group;
     const int first = i0 + t * a.tq;
@@ -320,18 +336,20 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     const bool warp_active = (warp & 3) * 32 < rows_real;
 
     for (int j = 0; j < n_mine; ++j) {
+      const int buf = j & 1;
+      const uint32_t tmem_s = tmem_t + buf * kP2TileN;
       const int kv0 = (j_begin + j) * kP2TileN;
       const int col_lim = lim - kv0;                 // columns [0, col_lim] are visible
-      ptx::mbar_wait(bar(L::bSFull + t), static_cast<uint32_t>(j) & 1u);
+      ptx::mbar_wait(bar(L::bSFull + 2 * t + buf), static_cast<uint32_t>(j >> 1) & 1u);
       ptx::tc_fence_after_sync();
-      if (warp_active) {
-        uint32_t s[4][32];
+      if (warp_active && !(a.debug & 1)) {
+        uint32_t s[2][32];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) ptx::tmem_ld_x32(tmem_s + c * 32, s[c]);
+        for (int c = 0; c < 2; ++c) ptx::tmem_ld_x32(tmem_s + c * 32, s[c]);
         ptx::tmem_wait_ld();
-        if (__any_sync(0xffffffffu, col_lim < kP2TileN - 1)) {  // tile touches the causal diagonal / end of the sequence
+        if (__any_sync(0xffffffffu, col_lim < kP2TileN - 1)) {  // step touches the causal diagonal / end of the sequence
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 2; ++c) {
 #pragma unroll
             for (int e = 0; e < 32; ++e)
               if (c * 32 + e > col_lim) s[c][e] = 0xff800000u;  // -inf
@@ -339,7 +357,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         }
         float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
 #pragma unroll
           for (int e = 0; e < 32; e += 8) {
 #pragma unroll
@@ -351,7 +369,12 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         if (j == 0) {
           m_used = (mxs == -INFINITY) ? 0.f : mxs;
         } else if (__any_sync(0xffffffffu, mxs > m_used + kP2Rescale)) {
-          // Lazy rescale: the warp pays the TMEM round trip only when some row's max grew by more than 2^8.
+          // Lazy rescale: the warp pays the TMEM round trip only when some row's max grew by more than 2^8.  O_t must be
+          // quiescent: P_t.V(j-1) complete (implied by S_t(j+1), issued behind it; the last step has its own commit) and
+          // P_t.V(j) not issued before this thread's P arrival below.
+          if (j + 1 < n_mine) ptx::mbar_wait(bar(L::bSFull + 2 * t + (buf ^ 1)), static_cast<uint32_t>((j + 1) >> 1) & 1u);
+          else ptx::mbar_wait(bar(L::bPvDone + t), 0);
+          ptx::tc_fence_after_sync();
           const float m_new = fmaxf(m_used, mxs);
           const float alpha = fast_exp2(m_used - m_new);
           l *= alpha;
@@ -371,7 +394,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         const float2 nm2 = make_float2(-m_used, -m_used);
         float2 ls2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
           uint32_t pk[16];
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
@@ -386,7 +409,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       }
       ptx::tmem_wait_st();
       ptx::tc_fence_before_sync();
-      ptx::mbar_arrive(bar(L::bPFull + t));
+      ptx::mbar_arrive(bar(L::bPFull + 2 * t + buf));
     }
 
     // ---- epilogue: O / l -> out (or the fp32 split-KV partial) ---------------------------------------------------------
@@ -450,7 +473,7 @@ bool attn_pair_supported(const HiAttnArgs& args) {
 template <typename T, int PF>
 static int launch_pair_t(const HiAttnArgs& args, const P2Args& a, const CUtensorMap& mq, const CUtensorMap& mk,
                          const CUtensorMap& mv, cudaStream_t stream) {
-  constexpr int NK = 2, NV = 2;
+  constexpr int NK = 4, NV = 4;  // 4 + 4 steps of 64 keys (16 KiB each) + 64 KiB of Q = 192 KiB
   using L = P2Smem<NK, NV>;
   static bool configured = false;
   if (!configured) {
@@ -469,7 +492,7 @@ static int launch_pair_t(const HiAttnArgs& args, const P2Args& a, const CUtensor
 
 int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
   if (!attn_pair_supported(args)) {
-    set_error("paged_attention: the tcgen05 pair-tile path needs fp16/bf16, head_dim 128, block_size in {8,16,32,64,128} and 16-byte aligned rows");
+    set_error("paged_attention: the tcgen05 pair-tile path needs fp16/bf16, head_dim 128, block_size in {8,16,32,64} and 16-byte aligned rows");
     return HI_ERR_UNSUPPORTED;
   }
   P2Args a{};
@@ -488,7 +511,7 @@ int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
 
   // ---- split-KV: only for launches too small to fill the machine (one CTA per SM) ---------------------------------------
   constexpr int kSplitTargetCtas = 296;  // 148 SMs x 2
-  constexpr int kMinTilesPerSplit = 2;   // never finer than 256 tokens
+  constexpr int kMinTilesPerSplit = 4;   // never finer than 256 tokens
   const int n_pairs = (args.max_q_len + 2 * a.tq - 1) / (2 * a.tq);
   const int64_t base_ctas = static_cast<int64_t>(n_pairs) * args.n_kv_heads * args.n_seqs;
   const int max_kv_tiles = (args.max_kv_len + kP2TileN - 1) / kP2TileN;
@@ -521,7 +544,8 @@ int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
   rc = pool_map(&mv, args.dtype, args.value_cache, n_slots, args.n_kv_heads, args.block_size);
   if (rc != HI_OK) return rc;
 
-  int poly = 1;  // exponentials per 4 moved from MUFU to the FMA pipes
+  if (const char* env = getenv("HI_PAIR_DEBUG")) a.debug = atoi(env);
+  int poly = 0;  // exponentials per 4 moved from MUFU to the FMA pipes (measured: no gain while the softmax warps have idle issue slots)
   if (const char* env = getenv("HI_PAIR_POLY")) poly = atoi(env);  // tuning override
   if (args.dtype == HI_BF16) {
     rc = poly <= 0 ? launch_pair_t<__nv_bfloat16, 0>(args, a, mq, mk, mv, stream)
@@ -550,3 +574,14 @@ int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
 }
 
 }  // namespace hi
+
+#ifdef HI_MBAR_DEBUG
+// Debug builds only: copies (and clears) the first mbarrier timeout recorded by the pair kernel.
+extern "C" int hi_debug_mbar_timeout(unsigned int out[64]) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out, hi::ptx::g_mbar_debug, 64 * sizeof(unsigned int)) != cudaSuccess) return -1;
+  unsigned int zero[64] = {};
+  cudaMemcpyToSymbol(hi::ptx::g_mbar_debug, zero, sizeof(zero));
+  return 0;
+}
+#endif

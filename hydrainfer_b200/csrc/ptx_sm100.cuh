@@ -39,6 +39,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // Blocking wait with a watchdog: a protocol bug traps (the launch fails) instead of hanging the GPU.
+// With -DHI_MBAR_DEBUG the first timeout is recorded in g_mbar_debug (barrier address, parity, thread, block) and the
+// wait gives up after ~10 ms, so the kernel terminates and the host can read the record (hi_debug_mbar_timeout).
+#ifdef HI_MBAR_DEBUG
+static __device__ unsigned int g_mbar_debug[64];  // per warp id: {flag, barrier address, parity, block x | y << 16}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 20000000LL) {
+      const unsigned int w = (threadIdx.x >> 5) & 15u;
+      if (atomicCAS(&g_mbar_debug[4 * w], 0u, 1u) == 0u) {
+        g_mbar_debug[4 * w + 1] = bar;
+        g_mbar_debug[4 * w + 2] = parity;
+        g_mbar_debug[4 * w + 3] = blockIdx.x | (blockIdx.y << 16);
+      }
+      return;
+    }
+  }
+}
+#else
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
@@ -46,6 +66,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s at 2 GHz
   }
 }
+#endif
 
 // One lane of the (converged) warp is elected; the others get false.
 __device__ __forceinline__ bool elect_one() {
