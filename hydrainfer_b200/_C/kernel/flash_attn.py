@@ -26,9 +26,14 @@ def _workspace(dev: torch.device, head_dim: int) -> Tensor:
 def mha_varlen_fwd(out: Tensor, q: Tensor, k: Tensor, v: Tensor, cu_seqlens_q: Tensor, cu_seqlens_k: Tensor,
                    block_table_: Optional[Tensor], cu_block_lens: Optional[Tensor], alibi_slopes: Optional[Tensor],
                    max_seqlen_q: int, max_seqlen_k: int, softmax_scale: float, softcap: float, window_size_left: int,
-                   window_size_right: int, num_splits: int, path: int = _lib.HI_ATTN_AUTO) -> None:
+                   window_size_right: int, num_splits: int, path: int = _lib.HI_ATTN_AUTO,
+                   work_items: Optional[Tensor] = None, work_tile_tokens: int = 0, qk_work_hint: int = 0) -> None:
     """Paged causal varlen attention. q/out [T, Hq, d] (row stride free), k/v caches [NB, bs, Hkv, d] contiguous,
     int32 cu_seqlens_q/k [B+1], flattened block table + cu_block_lens [B+1] (flash_api.cpp:216-232).
+
+    `path`, `work_items` (int32 device tensor [n_items, 2] = (sequence, tile), heaviest first, tiles of `work_tile_tokens`
+    query tokens) and `qk_work_hint` are optional extensions after the reference's 16 positional arguments: the host-side
+    plan AttentionParametersBuilder builds next to the metadata.
 
     Only the configuration the reference's attention layer uses is implemented (causal_attention.py:274-291):
     no alibi, no softcap, window (-1, 0) == causal, paged KV; anything else raises RuntimeError like TORCH_CHECK."""
@@ -53,6 +58,8 @@ def mha_varlen_fwd(out: Tensor, q: Tensor, k: Tensor, v: Tensor, cu_seqlens_q: T
     n_seqs = cu_seqlens_q.shape[0] - 1
     if cu_seqlens_k.shape[0] != n_seqs + 1 or cu_block_lens.shape[0] != n_seqs + 1:
         raise RuntimeError("mha_varlen_fwd: cu_seqlens_q, cu_seqlens_k and cu_block_lens must all have batch + 1 entries")
+    if work_items is not None and (work_items.dtype != torch.int32 or work_items.device != dev or work_items.dim() != 2 or work_items.shape[1] != 2 or not work_items.is_contiguous()):
+        raise RuntimeError("mha_varlen_fwd: work_items must be a contiguous int32 device tensor of shape [n_items, 2]")
     ws = _workspace(dev, head_dim)
     row = n_qo_heads * head_dim
     args = _lib.HiAttnArgs(
@@ -64,7 +71,9 @@ def mha_varlen_fwd(out: Tensor, q: Tensor, k: Tensor, v: Tensor, cu_seqlens_q: T
         n_qo_heads=n_qo_heads, n_kv_heads=n_kv_heads, head_dim=head_dim, block_size=block_size, n_blocks=n_blocks,
         dtype=_lib.dtype_code(q.dtype), softmax_scale=float(softmax_scale),
         workspace=ws.data_ptr(), workspace_bytes=ws.numel(), path=int(path), device=dev.index or 0,
-        kv_blocks_hint=int(block_table_.numel()))
+        kv_blocks_hint=int(block_table_.numel()),
+        work_items=work_items.data_ptr() if work_items is not None else None, qk_work_hint=int(qk_work_hint),
+        n_work_items=int(work_items.shape[0]) if work_items is not None else 0, work_tile_tokens=int(work_tile_tokens))
     _lib.check(_lib.lib.hi_paged_attention(args, _lib.current_stream_ptr(dev)))
 
 

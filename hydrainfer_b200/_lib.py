@@ -32,6 +32,7 @@ class HiAttnArgs(Structure):
         ("dtype", c_int32), ("softmax_scale", c_float),
         ("workspace", c_void_p), ("workspace_bytes", c_int64),
         ("path", c_int32), ("device", c_int32), ("kv_blocks_hint", c_int32), ("reserved", c_int32 * 3),
+        ("work_items", c_void_p), ("qk_work_hint", c_int64), ("n_work_items", c_int32), ("work_tile_tokens", c_int32),
     ]
 
 
@@ -54,6 +55,7 @@ SIGNATURES = {
     "hi_set_image_cache": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
     "hi_attention_workspace_bytes": (c_int64, [c_int32, c_int32, c_int32, c_int32]),
     "hi_paged_attention": (c_int, [POINTER(HiAttnArgs), c_void_p]),
+    "hi_attention_tile_tokens": (c_int32, [c_int32, c_int32]),
     "hi_migrate_blocks": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, HiPoolGeom, HiPoolGeom, c_int, c_void_p]),
     "hi_ipc_get_handle": (c_int, [c_void_p, POINTER(c_uint8), POINTER(c_int64), c_int]),
     "hi_ipc_open_handle": (c_int, [POINTER(c_uint8), c_int64, c_int, POINTER(c_void_p)]),

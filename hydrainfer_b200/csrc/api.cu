@@ -6,7 +6,7 @@
 
 #include "common.cuh"
 
-static_assert(sizeof(HiAttnArgs) == 168, "HiAttnArgs layout is part of the ABI (ctypes mirror in hydrainfer_b200/_lib.py)");
+static_assert(sizeof(HiAttnArgs) == 192, "HiAttnArgs layout is part of the ABI (ctypes mirror in hydrainfer_b200/_lib.py)");
 static_assert(sizeof(HiPoolGeom) == 32, "HiPoolGeom layout is part of the ABI");
 
 namespace hi {
@@ -60,6 +60,12 @@ extern "C" int64_t hi_attention_workspace_bytes(int32_t n_tokens, int32_t n_qo_h
   int64_t need = hi::simt_workspace_bytes(head_dim > 0 ? head_dim : 128);
   if (hi::tc_workspace_bytes() > need) need = hi::tc_workspace_bytes();
   return (need + 255) / 256 * 256;
+}
+
+extern "C" int32_t hi_attention_tile_tokens(int32_t n_qo_heads, int32_t n_kv_heads) {
+  if (n_qo_heads <= 0 || n_kv_heads <= 0 || n_qo_heads % n_kv_heads != 0) return 0;
+  const int group = n_qo_heads / n_kv_heads;
+  return group <= 128 ? 2 * (128 / group) : 0;  // two 128-row tiles of (token, head-in-group) rows per CTA (attn_tc2.cu)
 }
 
 extern "C" int hi_paged_attention(const HiAttnArgs* p, void* stream_) {

@@ -517,9 +517,9 @@ static int launch_tc_t(const HiAttnArgs& args, const TcArgs& a, const CUtensorMa
 }
 
 int64_t tc_workspace_bytes() {
-  // split-KV partials: rows * heads * n_splits entries of (128 + 2) floats; splits are only used while the launch has
-  // fewer than kSplitTargetCtas CTAs, which bounds rows*heads*n_splits by about 2 * 128 * kSplitTargetCtas.
-  return static_cast<int64_t>(2) * 128 * 600 * (kHeadDim + 2) * 4;
+  // split-KV partials of the tcgen05 kernels: rows * heads * n_splits entries of (128 + 2) floats.  192 MiB holds e.g.
+  // 3 chunks of a 4096-token, 28-head ragged prefill batch; launches that would need more use fewer chunks.
+  return static_cast<int64_t>(192) << 20;
 }
 
 int launch_attn_tc(const HiAttnArgs& args, cudaStream_t stream) {

@@ -57,6 +57,7 @@ struct P2Args {
   const int32_t* kv_cu;
   const int32_t* block_tables;
   const int32_t* cu_blocks;
+  const int32_t* work_items;  // optional host plan: [n][2] = (sequence, pair of tiles), heaviest first; grid.x walks it
   int n_qo_heads, n_kv_heads, group, block_size;
   int tq;            // query tokens per 128-row tile: 128 / group
   float scale_log2;
@@ -100,16 +101,31 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   constexpr bool kBf16 = !std::is_same<T, __half>::value;
 
   // ---- which pair of query tiles -----------------------------------------------------------------------------------
-  const int b = blockIdx.z;
-  const int kvh = blockIdx.y;
+  // With a host plan the grid is one-dimensional: x = (item, KV head, split), heaviest item first.  Without one it is
+  // (pairs x splits, KV heads, sequences) and the CTAs of a sequence's missing pairs exit at once.
+  int b, kvh, sp, pair;
+  if (a.work_items != nullptr) {
+    const int x = static_cast<int>(blockIdx.x);
+    sp = x % a.n_splits;
+    kvh = (x / a.n_splits) % a.n_kv_heads;
+    const int item = x / (a.n_splits * a.n_kv_heads);
+    b = __ldg(a.work_items + 2 * item);
+    pair = __ldg(a.work_items + 2 * item + 1);
+  } else {
+    b = static_cast<int>(blockIdx.z);
+    kvh = static_cast<int>(blockIdx.y);
+    sp = static_cast<int>(blockIdx.x) % a.n_splits;
+    pair = -1;  // set below from the sequence's own pair count: heaviest (latest) tiles first
+  }
   const int q_start = __ldg(a.q_cu + b);
   const int q_len = __ldg(a.q_cu + b + 1) - q_start;
   const int kv_len = __ldg(a.kv_cu + b + 1) - __ldg(a.kv_cu + b);
   const int pair_tokens = 2 * a.tq;
-  const int n_pairs = (q_len + pair_tokens - 1) / pair_tokens;
-  const int sp = static_cast<int>(blockIdx.x) % a.n_splits;
-  const int pair = n_pairs - 1 - static_cast<int>(blockIdx.x) / a.n_splits;  // heaviest (latest) tiles first
-  if (pair < 0) return;
+  if (a.work_items == nullptr) {
+    const int n_pairs = (q_len + pair_tokens - 1) / pair_tokens;
+    pair = n_pairs - 1 - static_cast<int>(blockIdx.x) / a.n_splits;
+    if (pair < 0) return;
+  }
   const int i0 = pair * pair_tokens;
   const int j_begin = sp * a.tiles_per_split;
   // nt[t]: KV steps walked for query tile t (local step j = 0 .. nt[t]-1 is global step j_begin + j)
@@ -481,7 +497,8 @@ static int launch_pair_t(const HiAttnArgs& args, const P2Args& a, const CUtensor
     configured = true;
   }
   const int n_pairs = (args.max_q_len + 2 * a.tq - 1) / (2 * a.tq);
-  const dim3 grid(n_pairs * a.n_splits, args.n_kv_heads, args.n_seqs);
+  const dim3 grid = a.work_items != nullptr ? dim3(static_cast<unsigned>(args.n_work_items) * a.n_splits * args.n_kv_heads, 1, 1)
+                                            : dim3(n_pairs * a.n_splits, args.n_kv_heads, args.n_seqs);
   timing_mark_start(stream);
   paged_attn_pair_kernel<T, NK, NV, PF><<<grid, kP2Threads, L::kDynamicBytes, stream>>>(mq, mk, mv, a);
   timing_mark_stop(stream);
@@ -502,6 +519,7 @@ int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
   a.kv_cu = args.kv_cu_seq_lens;
   a.block_tables = args.block_tables;
   a.cu_blocks = args.cu_blocks_lens;
+  a.work_items = (args.work_items != nullptr && args.n_work_items > 0 && args.work_tile_tokens == 2 * (kP2TileM / (args.n_qo_heads / args.n_kv_heads))) ? args.work_items : nullptr;
   a.n_qo_heads = args.n_qo_heads;
   a.n_kv_heads = args.n_kv_heads;
   a.group = args.n_qo_heads / args.n_kv_heads;
@@ -509,15 +527,25 @@ int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
   a.tq = kP2TileM / a.group;
   a.scale_log2 = args.softmax_scale * 1.4426950408889634f;
 
-  // ---- split-KV: only for launches too small to fill the machine (one CTA per SM) ---------------------------------------
-  constexpr int kSplitTargetCtas = 296;  // 148 SMs x 2
+  // ---- split-KV ---------------------------------------------------------------------------------------------------------
+  // One CTA per SM: a launch is balanced when no CTA carries much more than (total work / #SMs).  With the host's work
+  // hint the chunk is sized from the real total (ragged batches: a few long sequences among short ones get split, the
+  // short ones do not); without it only launches too small to fill the machine are split.
+  constexpr int kSms = 148;
   constexpr int kMinTilesPerSplit = 4;   // never finer than 256 tokens
   const int n_pairs = (args.max_q_len + 2 * a.tq - 1) / (2 * a.tq);
-  const int64_t base_ctas = static_cast<int64_t>(n_pairs) * args.n_kv_heads * args.n_seqs;
+  const int64_t base_ctas = a.work_items != nullptr ? static_cast<int64_t>(args.n_work_items) * args.n_kv_heads
+                                                    : static_cast<int64_t>(n_pairs) * args.n_kv_heads * args.n_seqs;
   const int max_kv_tiles = (args.max_kv_len + kP2TileN - 1) / kP2TileN;
   int n_splits = 1;
-  if (base_ctas < kSplitTargetCtas) {
-    n_splits = static_cast<int>((kSplitTargetCtas + base_ctas - 1) / base_ctas);
+  if (args.qk_work_hint > 0 && a.work_items != nullptr) {
+    // CTA-steps: every work item walks its visible keys in 64-key steps, once per KV head
+    const double total_steps = static_cast<double>(args.qk_work_hint) / kP2TileN * args.n_kv_heads;
+    int chunk = static_cast<int>(total_steps / (2.0 * kSms)) + 1;
+    if (chunk < kMinTilesPerSplit) chunk = kMinTilesPerSplit;
+    if (chunk < max_kv_tiles) n_splits = (max_kv_tiles + chunk - 1) / chunk;
+  } else if (base_ctas < 2 * kSms) {
+    n_splits = static_cast<int>((2 * kSms + base_ctas - 1) / base_ctas);
     const int max_splits = (max_kv_tiles + kMinTilesPerSplit - 1) / kMinTilesPerSplit;
     if (n_splits > max_splits) n_splits = max_splits;
   }

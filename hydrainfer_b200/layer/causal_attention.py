@@ -37,8 +37,14 @@ class AttentionParameters:
     q_max_seq_len: int = 128
     kv_max_seq_len: int = 128
     flash_infer_handler: Optional[object] = None  # kept for signature compatibility; unused
+    # host-side plan for the B200 prefill kernel (the analogue of flashinfer's plan(), causal_attention.py:171-195): the
+    # query tiles of the batch as (sequence, tile) pairs sorted by cost, and the total number of keys they walk.
+    # Results never depend on them.
+    work_items: Tensor = None              # int32 [n_items, 2]; None for decode-only batches
+    work_tile_tokens: int = 0
+    qk_work: int = 0
 
-    _TENSOR_FIELDS = ("q_cu_seq_lens", "kv_cu_seq_lens", "paged_kv_last_page_len", "new_cache_slots", "block_tables", "cu_blocks_lens")
+    _TENSOR_FIELDS = ("q_cu_seq_lens", "kv_cu_seq_lens", "paged_kv_last_page_len", "new_cache_slots", "block_tables", "cu_blocks_lens", "work_items")
 
     def to(self, device: torch.device) -> None:
         for name in self._TENSOR_FIELDS:
@@ -106,6 +112,7 @@ class AttentionParametersBuilder:
         self.all_sequences_decode = True
         self.q_max_seq_len = 0
         self.kv_max_seq_len = 0
+        self.seq_lens: list[tuple[int, int]] = []  # (q, kv) per sequence, for the host-side plan
 
     def add_request(self, q_seq_len: int, kv_seq_len: int, new_cache_slots: list[int], block_table: list[int]) -> None:
         self.q_cu_seq_lens.append(self.q_cu_seq_lens[-1] + q_seq_len)
@@ -118,13 +125,15 @@ class AttentionParametersBuilder:
         self.all_sequences_decode = self.all_sequences_decode and q_seq_len == 1
         self.q_max_seq_len = max(self.q_max_seq_len, q_seq_len)
         self.kv_max_seq_len = max(self.kv_max_seq_len, kv_seq_len)
+        self.seq_lens.append((q_seq_len, kv_seq_len))
 
     def add_kv_cache(self, kv_cache: KVCache) -> None:
         self.kv_caches.append(kv_cache)
 
     def build_attention_parameters(self) -> list[AttentionParameters]:
+        work_flat, tile_tokens, qk_work = self._plan()
         parts = [self.q_cu_seq_lens, self.kv_cu_seq_lens, self.paged_kv_last_page_len, self.new_cache_slots,
-                 self.block_tables, self.cu_blocks_lens]
+                 self.block_tables, self.cu_blocks_lens, work_flat]
         # each slice starts on a 16-byte boundary (4 int32) so the kernels' vector paths never see a misaligned table
         offsets, flat_list = [], []
         for part in parts:
@@ -143,7 +152,26 @@ class AttentionParametersBuilder:
             block_tables=views[4], cu_blocks_lens=views[5],
             num_sequences=self.num_sequences, all_sequences_decode=self.all_sequences_decode,
             q_max_seq_len=self.q_max_seq_len, kv_max_seq_len=self.kv_max_seq_len, flash_infer_handler=None,
+            work_items=views[6].view(-1, 2) if work_flat else None, work_tile_tokens=tile_tokens, qk_work=qk_work,
         ) for kv_cache in self.kv_caches]
+
+    def _plan(self) -> tuple[list[int], int, int]:
+        """Host-side plan for batches with prefill rows: every run of `tile_tokens` query tokens of a sequence is one work
+        item whose cost is the number of keys its last token sees; items go out heaviest first (longest-processing-time
+        order), so the launch ends on light tiles, and the grid holds exactly the tiles that exist."""
+        if self.all_sequences_decode or self.device.type != "cuda":
+            return [], 0, 0
+        from .. import _lib
+        tile_tokens = int(_lib.lib.hi_attention_tile_tokens(self.num_qo_heads, self.num_kv_heads))
+        if tile_tokens <= 0:
+            return [], 0, 0
+        items = []
+        for b, (q, kv) in enumerate(self.seq_lens):
+            for tile in range((q + tile_tokens - 1) // tile_tokens):
+                items.append((kv - q + min(q, (tile + 1) * tile_tokens), b, tile))
+        items.sort(reverse=True)
+        flat = [x for _, b, tile in items for x in (b, tile)]
+        return flat, tile_tokens, sum(cost for cost, _, _ in items)
 
 
 @dataclass
@@ -184,6 +212,7 @@ class B200CausalGroupedQueryPageAttentionHandler(nn.Module):
             attention_params.block_tables, attention_params.cu_blocks_lens,
             None, attention_params.q_max_seq_len, attention_params.kv_max_seq_len,
             1.0 / math.sqrt(self.head_dim), 0, -1, 0, 0, self.path,
+            attention_params.work_items, attention_params.work_tile_tokens, attention_params.qk_work,
         )
         return CausalGroupedQueryPageAttentionOutput(o=output.view(-1, self.n_qo_heads * self.head_dim))
 

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HI_B200_ABI_VERSION 1
+#define HI_B200_ABI_VERSION 2
 
 typedef enum HiStatus {
   HI_OK = 0,
@@ -117,12 +117,24 @@ typedef struct HiAttnArgs {
   int32_t kv_blocks_hint;    /* entries of block_tables (sum of ceil(L_b / block_size)); 0 = unknown.  Only steers the
                                 split-KV heuristics (ragged batches are split finer); never affects results. */
   int32_t reserved[3];
+  /* ABI 2: optional host-side plan.  The host builds the metadata from Python ints (AttentionParametersBuilder), so it
+   * can also enumerate the query tiles of the batch, sorted by cost, the way flashinfer's plan() does for the reference
+   * (causal_attention.py:171-195).  The plan steers work order, grid size and split-KV only; results never depend on it.
+   * Tiles are runs of hi_attention_tile_tokens(n_qo_heads, n_kv_heads) consecutive query tokens of one sequence. */
+  const int32_t* work_items; /* [dev] [n_work_items][2] = (sequence, tile index within the sequence), heaviest first; NULL = none */
+  int64_t qk_work_hint;      /* sum over the work items of the number of keys the item walks, i.e. of
+                                L_b - q_b + min(q_b, (tile + 1) * tile_tokens); 0 = unknown */
+  int32_t n_work_items;
+  int32_t work_tile_tokens;  /* tile size the plan was built for; the plan is ignored if it does not match the kernel's */
 } HiAttnArgs;
 
 /* Upper bound of the scratch hi_paged_attention needs for a batch with these extents (split-KV partials). */
 int64_t hi_attention_workspace_bytes(int32_t n_tokens, int32_t n_qo_heads, int32_t head_dim, int32_t max_kv_len);
 
 int hi_paged_attention(const HiAttnArgs* args, void* stream);
+
+/* Query tokens per work item of the prefill kernel for this head geometry (0 if that kernel does not cover it). */
+int32_t hi_attention_tile_tokens(int32_t n_qo_heads, int32_t n_kv_heads);
 
 /* Number of kernels the last API call on this thread launched (bench bookkeeping). */
 int hi_last_launch_count(void);

@@ -30,13 +30,13 @@ def test_binding_table_matches_header():
 
 
 def test_abi_version_and_error_string():
-    assert _lib.lib.hi_abi_version() == 1
+    assert _lib.lib.hi_abi_version() == 2
     assert isinstance(_lib.lib.hi_last_error(), bytes)
 
 
 def test_struct_layout_matches_header():
     # HiAttnArgs: 4 ptrs + 2 i64 + 4 ptrs + 8 i32 + i64 + i32 + f32 + ptr + i64 + 2 i32 + 4 i32 (natural alignment, no packing)
-    assert ctypes.sizeof(_lib.HiAttnArgs) == 4 * 8 + 2 * 8 + 4 * 8 + 8 * 4 + 8 + 4 + 4 + 8 + 8 + 2 * 4 + 4 * 4
+    assert ctypes.sizeof(_lib.HiAttnArgs) == 4 * 8 + 2 * 8 + 4 * 8 + 8 * 4 + 8 + 4 + 4 + 8 + 8 + 2 * 4 + 4 * 4 + 8 + 8 + 4 + 4
     assert ctypes.sizeof(_lib.HiPoolGeom) == 32
 
 

@@ -63,10 +63,17 @@ def run_case(name, seq_lens, hq, hkv, paths, out_lines, flashinfer_cmp=False, dt
     q_cu, kv_cu, bt, cu_b = i32(batch.q_cu_seq_lens), i32(batch.kv_cu_seq_lens), i32(batch.block_tables), i32(batch.cu_blocks_lens)
     nbytes, flops = algo_bytes(seq_lens, hq, hkv, d), algo_flops(seq_lens, hq, d)
     results = {}
+    from hydrainfer_b200 import _lib
+    tt = int(_lib.lib.hi_attention_tile_tokens(hq, hkv))
+    items = sorted(((L - q + min(q, (tile + 1) * tt), b, tile) for b, (q, L) in enumerate(seq_lens) for tile in range((q + tt - 1) // tt)), reverse=True)
+    plan = i32([x for _, b, tile in items for x in (b, tile)]).view(-1, 2)
+    work = sum(cost for cost, _, _ in items)
+    paths = list(paths) + [(p + "+plan", c) for p, c in paths if p == "pair"]
     for pname, path in paths:
+        hints = (plan, tt, work) if pname.endswith("+plan") else (None, 0, 0)
         def fn():
             mha_varlen_fwd(out, q3, batch.key_cache, batch.value_cache, q_cu, kv_cu, bt, cu_b, None, batch.q_max, batch.kv_max,
-                           1 / math.sqrt(d), 0, -1, 0, 0, path)
+                           1 / math.sqrt(d), 0, -1, 0, 0, path, *hints)
         try:
             med, best = time_call(fn)
         except RuntimeError as e:
