@@ -226,6 +226,40 @@ def test_tile_kernel_split_kv_and_ring_depth_variants(monkeypatch, splits, stage
         check_batch(batch, [TC, DEC, PAIR], f"splits={splits} stages={stages} heads={heads}")
 
 
+def test_host_plan_ragged_prefill_through_the_layer(monkeypatch):
+    """AttentionParametersBuilder's plan (cost-sorted work items + work hint) drives the pair kernel's grid and split-KV chunk:
+    a ragged chunked-prefill + decode batch must give the same answer with and without it, for forced split counts too."""
+    from hydrainfer_b200.layer import AttentionParametersBuilder, CausalGroupedQueryPageAttention, CausalGroupedQueryPageAttentionConfig
+    from hydrainfer_b200.memory import KVCache
+    seq_lens = [(1, 900), (37, 37), (200, 1500), (1, 64), (130, 130), (512, 2048), (1, 1)]
+    for heads in ((28, 4), (8, 8)):
+        batch = make_batch(seq_lens, heads[0], heads[1], 128, 16, dtype=torch.bfloat16, seed=41)
+        kc, vc = batch.clone_caches()
+        t = batch.n_tokens
+        oracle.set_kv_cache(torch.tensor(batch.new_cache_slots, dtype=torch.int32), batch.key.view(t, heads[1], 128), batch.value.view(t, heads[1], 128), kc, vc)
+        fp32 = oracle_fp32(batch, kc, vc)
+        for splits in (None, "1", "3"):
+            if splits is None:
+                monkeypatch.delenv("HI_TC_SPLITS", raising=False)
+            else:
+                monkeypatch.setenv("HI_TC_SPLITS", splits)
+            builder = AttentionParametersBuilder(heads[0], heads[1], 128, 16, torch.device(DEV))
+            for req in batch.requests():
+                builder.add_request(*req)
+            builder.add_kv_cache(KVCache(batch.key_cache.to(DEV), batch.value_cache.to(DEV)))
+            params = builder.build_attention_parameters()[0]
+            assert params.work_items is not None and params.work_items.shape[1] == 2 and params.work_tile_tokens == 2 * (128 // (heads[0] // heads[1]))
+            # the plan covers every query tile exactly once
+            tiles = {(int(b), int(tl)) for b, tl in params.work_items.cpu().tolist()}
+            want = {(b, tl) for b, (q, _) in enumerate(seq_lens) for tl in range(-(-q // params.work_tile_tokens))}
+            assert tiles == want and len(tiles) == params.work_items.shape[0]
+            layer = CausalGroupedQueryPageAttention(CausalGroupedQueryPageAttentionConfig(heads[0], heads[1], 128))
+            layer.handler.path = PAIR
+            out = layer(batch.query.to(DEV), batch.key.to(DEV), batch.value.to(DEV), params).o
+            torch.cuda.synchronize()
+            assert_close_to_fp32(out, fp32, batch.dtype, f"plan heads={heads} splits={splits}")
+
+
 # ---- full-size configs: sampled oracle rows + size-independent properties -------------------------------------------------
 def _sampled_check(batch_dev, sample_seqs, path, what):
     """Oracle on a subset of sequences (copied to CPU); the kernels ran on the whole batch."""
