@@ -24,6 +24,11 @@
 //   * O is rescaled lazily (only when a row max grows by more than 2^8) by the softmax thread itself, after waiting for
 //     P_t.V(j-1) (its own commit barrier; S_t(j) no longer implies it).
 //   * The TMA producer zeroes V rows at or beyond kv_len of the last step (P is 0 there, the pool bytes are arbitrary).
+//   * PERSISTENT: one CTA per SM walks the launch's work items (item = sequence x KV head x pair of tiles x split) with a
+//     stride of gridDim.x.  TMEM, barriers and tensor maps are set up once, and the item boundary is pipelined like any
+//     other step: ring stages, S/P buffers and barrier phases run on counters that never reset, the producers load the
+//     next item's Q/K/V while the softmax warps are still in the epilogue of the current one (Q_t and O_t each have an
+//     "empty" barrier), so short sequences do not pay a CTA launch + TMEM allocation + pipeline fill per tile.
 // Rows are (token, head-in-group) pairs, so GQA groups share the staged K/V exactly as in attn_tc.cu.
 #include <cuda.h>
 
@@ -65,6 +70,9 @@ struct P2Args {
   int tiles_per_split;  // in 64-key steps
   float* part_o;
   float* part_ml;
+  unsigned int* work_counter;  // zeroed before the launch; NULL = static (boustrophedon) assignment
+  int n_items;       // work items of the launch = CTA-sized units: (sequence, KV head, pair of tiles, split)
+  int max_pairs;     // without a host plan: pair slots per sequence, ceil(max_q_len / (2 tq))
   int debug;  // timing experiments only (HI_PAIR_DEBUG): bit 0 = softmax warps skip their math, bit 1 = no MMA is issued,
               // bit 2 = K/V tiles are not loaded (barriers only)
 };
@@ -85,11 +93,84 @@ struct P2Smem {
   static constexpr int bPvDone = bPFull + 4;            // [2] P_t.V(n_t - 2) complete (lazy rescale in the last step)
   static constexpr int bOFull = bPvDone + 2;            // [2]
   static constexpr int bVTail = bOFull + 2;
-  static constexpr int kNumBars = bVTail + 1;
+  static constexpr int bQEmpty = bVTail + 1;            // [2] every Q_t.K of the item has read Q_t (next item's Q may land)
+  static constexpr int bOEmpty = bQEmpty + 2;           // [2] the epilogue has read O_t out of TMEM (next item may overwrite it)
+  static constexpr int bItemFull = bOEmpty + 2;         // [4] ring of work-item indices published by warp 8
+  static constexpr int bItemEmpty = bItemFull + 4;      // [4] read by warp 11, both MMA warps (one lane each) and all 256 softmax threads
+  static constexpr int kNumBars = bItemEmpty + 4;
   static constexpr int kTmemPtr = kBars + kNumBars * 8;
-  static constexpr int kTotal = kTmemPtr + 16;
+  static constexpr int kItemRing = kTmemPtr + 16;       // int[4]
+  static constexpr int kTotal = kItemRing + 16;
   static constexpr int kDynamicBytes = kTotal + 1024;   // slack to align the base to 1024 B (128B-swizzle atoms)
 };
+
+// One work item, decoded identically by every role.
+struct P2Item {
+  int b, kvh, sp;
+  int q_start, q_len, kv_len;
+  int i0;        // first query token of the pair (position within the sequence)
+  int j_begin;   // first 64-key step of this split
+  int nt[2];     // steps walked for tile t (local step j is global step j_begin + j)
+  int n_all;     // max(nt[0], nt[1]); 0 = nothing to do
+  int blk0, n_pages;
+};
+
+__device__ __forceinline__ void p2_decode_item(const P2Args& a, int k, P2Item& it) {
+  int pair;
+  if (a.work_items != nullptr) {
+    it.sp = k % a.n_splits;
+    it.kvh = (k / a.n_splits) % a.n_kv_heads;
+    const int item = k / (a.n_splits * a.n_kv_heads);
+    it.b = __ldg(a.work_items + 2 * item);
+    pair = __ldg(a.work_items + 2 * item + 1);
+  } else {
+    it.sp = k % a.n_splits;
+    const int slot = (k / a.n_splits) % a.max_pairs;
+    it.kvh = (k / (a.n_splits * a.max_pairs)) % a.n_kv_heads;
+    it.b = k / (a.n_splits * a.max_pairs * a.n_kv_heads);
+    pair = -1 - slot;  // resolved below: the sequence's latest (heaviest) pair first
+  }
+  it.q_start = __ldg(a.q_cu + it.b);
+  it.q_len = __ldg(a.q_cu + it.b + 1) - it.q_start;
+  it.kv_len = __ldg(a.kv_cu + it.b + 1) - __ldg(a.kv_cu + it.b);
+  it.blk0 = __ldg(a.cu_blocks + it.b);
+  it.n_pages = __ldg(a.cu_blocks + it.b + 1) - it.blk0;
+  const int pair_tokens = 2 * a.tq;
+  if (pair < 0) pair += (it.q_len + pair_tokens - 1) / pair_tokens;  // n_pairs - 1 - slot
+  it.i0 = pair * pair_tokens;
+  it.j_begin = it.sp * a.tiles_per_split;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int first = it.i0 + t * a.tq;
+    if (pair < 0 || first >= it.q_len) {
+      it.nt[t] = 0;
+    } else {
+      const int i_last = min(it.q_len, first + a.tq) - 1;
+      const int kv_end = i_last + (it.kv_len - it.q_len) + 1;  // keys [0, kv_end) are visible to the tile
+      const int n_vis = (kv_end + kP2TileN - 1) / kP2TileN;
+      it.nt[t] = max(0, min(n_vis - it.j_begin, a.tiles_per_split));
+    }
+  }
+  it.n_all = max(it.nt[0], it.nt[1]);
+}
+
+// Work distribution.  Items are claimed DYNAMICALLY from a global counter (the list is sorted heaviest first by the host
+// plan, so this is longest-processing-time-first scheduling with an error of at most one item); warp 8 claims them, one
+// ahead of use, and publishes the indices to the other roles through a 4-entry shared-memory ring so that every role
+// walks the same sequence while running up to a few items apart.  Without a counter (no workspace) the assignment is
+// static in boustrophedon order: even rounds left to right, odd rounds right to left, which pairs a heavy item of one
+// round with a light one of the next.  An index >= n_items ends the walk.
+__device__ __forceinline__ int p2_claim_item(const P2Args& a, int round, int lane) {
+  if (a.work_counter != nullptr) {
+    int k = 0;
+    if (lane == 0) k = static_cast<int>(atomicAdd(a.work_counter, 1u));
+    return __shfl_sync(0xffffffffu, k, 0);
+  }
+  const int g = static_cast<int>(gridDim.x), c = static_cast<int>(blockIdx.x);
+  if (round * g >= a.n_items) return a.n_items;
+  const int k = round * g + ((round & 1) ? g - 1 - c : c);
+  return k < a.n_items ? k : a.n_items + 1;  // + 1: a hole in the last round, not the end (static mode only)
+}
 
 // PF = how many of every 4 (pairs of) exponentials run on the FMA pipes (exp2_poly2) instead of MUFU.EX2.
 template <typename T, int NK, int NV, int PF>
@@ -100,54 +181,6 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   static_assert(NK == 4 && NV == 4, "ring stages are addressed as step & 3");
   constexpr bool kBf16 = !std::is_same<T, __half>::value;
 
-  // ---- which pair of query tiles -----------------------------------------------------------------------------------
-  // With a host plan the grid is one-dimensional: x = (item, KV head, split), heaviest item first.  Without one it is
-  // (pairs x splits, KV heads, sequences) and the CTAs of a sequence's missing pairs exit at once.
-  int b, kvh, sp, pair;
-  if (a.work_items != nullptr) {
-    const int x = static_cast<int>(blockIdx.x);
-    sp = x % a.n_splits;
-    kvh = (x / a.n_splits) % a.n_kv_heads;
-    const int item = x / (a.n_splits * a.n_kv_heads);
-    b = __ldg(a.work_items + 2 * item);
-    pair = __ldg(a.work_items + 2 * item + 1);
-  } else {
-    b = static_cast<int>(blockIdx.z);
-    kvh = static_cast<int>(blockIdx.y);
-    sp = static_cast<int>(blockIdx.x) % a.n_splits;
-    pair = -1;  // set below from the sequence's own pair count: heaviest (latest) tiles first
-  }
-  const int q_start = __ldg(a.q_cu + b);
-  const int q_len = __ldg(a.q_cu + b + 1) - q_start;
-  const int kv_len = __ldg(a.kv_cu + b + 1) - __ldg(a.kv_cu + b);
-  const int pair_tokens = 2 * a.tq;
-  if (a.work_items == nullptr) {
-    const int n_pairs = (q_len + pair_tokens - 1) / pair_tokens;
-    pair = n_pairs - 1 - static_cast<int>(blockIdx.x) / a.n_splits;
-    if (pair < 0) return;
-  }
-  const int i0 = pair * pair_tokens;
-  const int j_begin = sp * a.tiles_per_split;
-  // nt[t]: KV steps walked for query tile t (local step j = 0 .. nt[t]-1 is global step j_begin + j)
-  int nt[2];
-#pragma unroll
-  for (int t = 0; t < 2; ++t) {
-    const int first = i0 + t * a.tq;
-    if (first >= q_len) {
-      nt[t] = 0;
-    } else {
-      const int i_last = min(q_len, first + a.tq) - 1;
-      const int kv_end = i_last + (kv_len - q_len) + 1;  // keys [0, kv_end) are visible to the tile
-      const int n_vis = (kv_end + kP2TileN - 1) / kP2TileN;
-      nt[t] = max(0, min(n_vis - j_begin, a.tiles_per_split));
-    }
-  }
-  const int n_all = max(nt[0], nt[1]);
-  if (n_all == 0) return;  // this split sees no key of the pair; the merge skips it too
-  const int blk0 = __ldg(a.cu_blocks + b);
-  const int n_pages = __ldg(a.cu_blocks + b + 1) - blk0;
-  const int pages_per_tile = kP2TileN / a.block_size;
-
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
@@ -157,13 +190,16 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int pages_per_tile = kP2TileN / a.block_size;
 
   // ---- one-time setup ------------------------------------------------------------------------------------------------
   if (threadIdx.x == 0) {
     for (int i = 0; i < L::kNumBars; ++i) ptx::mbar_init(bar(i), 1);
-    for (int i = 0; i < NK; ++i) ptx::mbar_init(bar(L::bKEmpty + i), 2);  // released by both MMA lanes
+    for (int i = 0; i < NK; ++i) ptx::mbar_init(bar(L::bKEmpty + i), 2);  // released by both MMA warps
     for (int i = 0; i < NV; ++i) ptx::mbar_init(bar(L::bVEmpty + i), 2);
     for (int i = 0; i < 4; ++i) ptx::mbar_init(bar(L::bPFull + i), kP2TileM);  // every softmax thread of the tile arrives
+    for (int i = 0; i < 2; ++i) ptx::mbar_init(bar(L::bOEmpty + i), kP2TileM);
+    for (int i = 0; i < 4; ++i) ptx::mbar_init(bar(L::bItemEmpty + i), 3 + 2 * kP2TileM);  // warps 9, 10, 11 + 256 softmax threads
     ptx::fence_mbar_init();
   }
   if (warp == 8) {
@@ -179,86 +215,131 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  volatile int* item_ring = reinterpret_cast<volatile int*>(smem_gen + L::kItemRing);
+  // Next work item of a consumer role (see p2_claim_item): entry n of the ring sequence.  `warp_role` consumers stay
+  // converged and release the slot from one lane; softmax threads release it individually.
+  auto next_item = [&](uint32_t n, bool warp_role) -> int {
+    const uint32_t slot = n & 3u;
+    ptx::mbar_wait(bar(L::bItemFull + slot), (n >> 2) & 1u);
+    const int k = item_ring[slot];
+    if (warp_role) {
+      __syncwarp();
+      if (ptx::elect_one()) ptx::mbar_arrive(bar(L::bItemEmpty + slot));
+      __syncwarp();
+    } else {
+      ptx::mbar_arrive(bar(L::bItemEmpty + slot));
+    }
+    return k;
+  };
 
+  // Running counters (identical in every role, never reset): g = K/V steps so far (ring stage g & 3, phase g >> 2);
+  // per tile, steps so far (S/P buffer & 1, phase >> 1), items in which the tile was active (Q/O barriers) and items
+  // with at least two steps (P.V(n-2) barrier).
   if (warp >= 8) {
-    // ========================== TMA producers (warps 8, 11) and MMA lanes (warps 9, 10) ==============================
+    // ========================== TMA producers (warps 8, 11) and MMA warps (9, 10) ====================================
     ptx::setmaxnreg_dec<72>();
     if (warp == 8 || warp == 11) {
       // ---- TMA producer: warp 8 stages Q and the K ring, warp 11 the V ring.  The warp stays converged; one elected lane
-      // issues.  Lane p holds the block id of page p of the step.
+      // issues.
       const bool is_k = warp == 8;
       const CUtensorMap* tm = is_k ? &tm_k : &tm_v;
-      if (is_k && ptx::elect_one()) {
-        const uint32_t q_bytes = 2u * static_cast<uint32_t>(a.group * a.tq) * 128u;
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          if (nt[t] > 0) {
-            const uint32_t dst = smem_base + L::kQ + t * kP2QTile;
-            ptx::mbar_arrive_expect_tx(bar(L::bQFull + t), q_bytes);
-            ptx::tma_load_3d(dst, &tm_q, bar(L::bQFull + t), 0, kvh * a.group, q_start + i0 + t * a.tq);
-            ptx::tma_load_3d(dst + kP2QHalf, &tm_q, bar(L::bQFull + t), 64, kvh * a.group, q_start + i0 + t * a.tq);
-          }
-        }
-      }
-      __syncwarp();
       const uint32_t page_half_bytes = static_cast<uint32_t>(a.block_size) * 128u;
       const int b_full = is_k ? L::bKFull : L::bVFull;
       const int b_empty = is_k ? L::bKEmpty : L::bVEmpty;
       const uint32_t ring = smem_base + (is_k ? L::kK : L::kV);
-      // Lane p holds the block id of page p of the step; the ids of step j+1 are fetched while step j is being issued.
-      auto pages_of = [&](int j, int& n_valid) -> int {
-        const int page0 = (j_begin + j) * pages_per_tile;
-        n_valid = (a.debug & 4) ? 0 : max(0, min(pages_per_tile, n_pages - page0));
-        return (j < n_all && lane < n_valid) ? __ldg(a.block_tables + blk0 + page0 + lane) : 0;
-      };
-      int n_valid_next = 0;
-      int blk_next = pages_of(0, n_valid_next);
-      for (int j = 0; j < n_all; ++j) {
-        const int n_valid = n_valid_next;
-        const int blk_lane = blk_next;
-        blk_next = pages_of(j + 1, n_valid_next);
-        const uint32_t tx = static_cast<uint32_t>(n_valid) * 2u * page_half_bytes;
-        const int st = j & 3;
-        const int kv0 = (j_begin + j) * kP2TileN;
-        const bool tail = !is_k && (kv0 + kP2TileN > kv_len);  // at most one such step per sequence
-        ptx::mbar_wait(bar(b_empty + st), (static_cast<uint32_t>(j >> 2) & 1u) ^ 1u);
-        const uint32_t full_bar = tail ? bar(L::bVTail) : bar(b_full + st);
-        uint32_t dst = ring + st * kP2Tile;
-        if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(full_bar, tx);
-        __syncwarp();
-        for (int p = 0; p < n_valid; ++p, dst += page_half_bytes) {
-          const int slot0 = __shfl_sync(0xffffffffu, blk_lane, p) * a.block_size;
+      uint32_t g = 0, n_q[2] = {0, 0}, n_tail = 0, n_it = 0;
+      int k_next = is_k ? p2_claim_item(a, 0, lane) : 0;
+      for (;;) {
+        int k;
+        if (is_k) {  // claim one item ahead and publish the current one to the other roles
+          k = k_next;
+          const uint32_t slot = n_it & 3u;
+          ptx::mbar_wait(bar(L::bItemEmpty + slot), ((n_it >> 2) & 1u) ^ 1u);
           if (ptx::elect_one()) {
-            ptx::tma_load_3d(dst, tm, full_bar, 0, kvh, slot0);
-            ptx::tma_load_3d(dst + kP2Half, tm, full_bar, 64, kvh, slot0);
+            item_ring[slot] = k;
+            ptx::mbar_arrive(bar(L::bItemFull + slot));
           }
           __syncwarp();
+          if (k < a.n_items) k_next = p2_claim_item(a, static_cast<int>(n_it) + 1, lane);
+        } else {
+          k = next_item(n_it, true);
         }
-        if (tail) {
-          // Keys at or beyond kv_len carry P == 0, but their V rows are whatever the pool / stale shared memory holds:
-          // zero them (0 * NaN must not reach O), then publish the step.
-          ptx::mbar_wait(bar(L::bVTail), 0);
-          uint8_t* vt = smem_gen + L::kV + st * kP2Tile;
-          const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-          for (int r = max(0, kv_len - kv0) + lane; r < kP2TileN; r += 32) {
-            uint4* row0 = reinterpret_cast<uint4*>(vt + r * 128);
-            uint4* row1 = reinterpret_cast<uint4*>(vt + kP2Half + r * 128);
+        ++n_it;
+        if (k >= a.n_items) break;
+        P2Item it;
+        p2_decode_item(a, k, it);
+        if (it.n_all == 0) continue;
+        if (is_k) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              row0[e] = z;
-              row1[e] = z;
+          for (int t = 0; t < 2; ++t) {
+            if (it.nt[t] > 0) {
+              ptx::mbar_wait(bar(L::bQEmpty + t), (n_q[t] & 1u) ^ 1u);  // the previous item's Q_t.K products are done
+              if (ptx::elect_one()) {
+                const uint32_t dst = smem_base + L::kQ + t * kP2QTile;
+                ptx::mbar_arrive_expect_tx(bar(L::bQFull + t), 2u * static_cast<uint32_t>(a.group * a.tq) * 128u);
+                ptx::tma_load_3d(dst, &tm_q, bar(L::bQFull + t), 0, it.kvh * a.group, it.q_start + it.i0 + t * a.tq);
+                ptx::tma_load_3d(dst + kP2QHalf, &tm_q, bar(L::bQFull + t), 64, it.kvh * a.group, it.q_start + it.i0 + t * a.tq);
+              }
+              __syncwarp();
+              ++n_q[t];
             }
           }
-          ptx::fence_proxy_async_smem();
+        }
+        // Lane p holds the block id of page p of the step; the ids of step j+1 are fetched while step j is being issued.
+        auto pages_of = [&](int j, int& n_valid) -> int {
+          const int page0 = (it.j_begin + j) * pages_per_tile;
+          n_valid = (a.debug & 4) ? 0 : max(0, min(pages_per_tile, it.n_pages - page0));
+          return (j < it.n_all && lane < n_valid) ? __ldg(a.block_tables + it.blk0 + page0 + lane) : 0;
+        };
+        int n_valid_next = 0;
+        int blk_next = pages_of(0, n_valid_next);
+        for (int j = 0; j < it.n_all; ++j, ++g) {
+          const int n_valid = n_valid_next;
+          const int blk_lane = blk_next;
+          blk_next = pages_of(j + 1, n_valid_next);
+          const uint32_t tx = static_cast<uint32_t>(n_valid) * 2u * page_half_bytes;
+          const int st = g & 3;
+          const int kv0 = (it.j_begin + j) * kP2TileN;
+          const bool tail = !is_k && (kv0 + kP2TileN > it.kv_len);  // at most one such step per item
+          ptx::mbar_wait(bar(b_empty + st), ((g >> 2) & 1u) ^ 1u);
+          const uint32_t full_bar = tail ? bar(L::bVTail) : bar(b_full + st);
+          uint32_t dst = ring + st * kP2Tile;
+          if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(full_bar, tx);
           __syncwarp();
-          if (ptx::elect_one()) ptx::mbar_arrive(bar(L::bVFull + st));
-          __syncwarp();
+          for (int p = 0; p < n_valid; ++p, dst += page_half_bytes) {
+            const int slot0 = __shfl_sync(0xffffffffu, blk_lane, p) * a.block_size;
+            if (ptx::elect_one()) {
+              ptx::tma_load_3d(dst, tm, full_bar, 0, it.kvh, slot0);
+              ptx::tma_load_3d(dst + kP2Half, tm, full_bar, 64, it.kvh, slot0);
+            }
+            __syncwarp();
+          }
+          if (tail) {
+            // Keys at or beyond kv_len carry P == 0, but their V rows are whatever the pool / stale shared memory holds:
+            // zero them (0 * NaN must not reach O), then publish the step.
+            ptx::mbar_wait(bar(L::bVTail), n_tail & 1u);
+            ++n_tail;
+            uint8_t* vt = smem_gen + L::kV + st * kP2Tile;
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+            for (int r = max(0, it.kv_len - kv0) + lane; r < kP2TileN; r += 32) {
+              uint4* row0 = reinterpret_cast<uint4*>(vt + r * 128);
+              uint4* row1 = reinterpret_cast<uint4*>(vt + kP2Half + r * 128);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                row0[e] = z;
+                row1[e] = z;
+              }
+            }
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (ptx::elect_one()) ptx::mbar_arrive(bar(L::bVFull + st));
+            __syncwarp();
+          }
         }
       }
     } else {
       // ---- MMA warp of tile t: the warp stays converged (every lane polls the barriers), one elected lane issues ------------
       const int t = warp - 9;
-      const int n_t = t ? nt[1] : nt[0];
       constexpr uint32_t idesc_qk = ptx::make_idesc_f16(kBf16, false, false, kP2TileM, kP2TileN);
       constexpr uint32_t idesc_pv = ptx::make_idesc_f16(kBf16, false, true, kP2TileM, kP2D);
       // Descriptors of the operand bases, built once; stages and k-steps only add to the 14-bit start-address field.
@@ -268,7 +349,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       const uint32_t tmem_t = tmem_base + t * kP2ColTile;
       const uint32_t tmem_o = tmem_t + kP2ColO;
       const bool no_mma = (a.debug & 2) != 0;
-      auto issue_qk = [&](int st, int buf) {  // S_t[buf] = Q_t . K(stage)^T; releases the K stage
+      auto issue_qk = [&](int st, int buf, bool last_of_item) {  // S_t[buf] = Q_t . K(stage)^T; releases the K stage
         const uint64_t dk = desc_k + static_cast<uint64_t>(st * (kP2Tile >> 4));
         const uint32_t tmem_s = tmem_t + buf * kP2TileN;
         if (!no_mma) {
@@ -280,6 +361,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         }
         ptx::mma_commit(bar(L::bSFull + 2 * t + buf));
         ptx::mma_commit(bar(L::bKEmpty + st));
+        if (last_of_item) ptx::mma_commit(bar(L::bQEmpty + t));
       };
       auto issue_pv = [&](int st, int buf, bool accumulate) {  // O_t (+)= P_t[buf] . V(stage); releases the V stage
         const uint64_t dv = desc_v + static_cast<uint64_t>(st * (kP2Tile >> 4));
@@ -292,42 +374,60 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         }
         ptx::mma_commit(bar(L::bVEmpty + st));
       };
-      // prologue: S_t(0) and S_t(1).  Steps at or beyond n_t (this tile sees fewer keys than its sibling) only release
-      // the ring stages.
-      if (n_t > 0) ptx::mbar_wait(bar(L::bQFull + t), 0);
+      uint32_t g = 0, gs = 0, n_act = 0, n_it = 0;
+      for (;;) {
+        const int k = next_item(n_it++, true);
+        if (k >= a.n_items) break;
+        P2Item it;
+        p2_decode_item(a, k, it);
+        if (it.n_all == 0) continue;
+        const int n_t = t ? it.nt[1] : it.nt[0];
+        const int n_all = it.n_all;
+        // prologue: S_t(0) and S_t(1).  Steps at or beyond n_t (this tile sees fewer keys than its sibling) only release
+        // the ring stages.
+        if (n_t > 0) ptx::mbar_wait(bar(L::bQFull + t), n_act & 1u);
 #pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
-        if (jj < n_all) {
-          ptx::mbar_wait(bar(L::bKFull + jj), 0);
+        for (int jj = 0; jj < 2; ++jj) {
+          if (jj < n_all) {
+            const uint32_t gj = g + jj;
+            ptx::mbar_wait(bar(L::bKFull + (gj & 3)), (gj >> 2) & 1u);
+            ptx::tc_fence_after_sync();
+            if (ptx::elect_one()) {
+              if (jj < n_t) issue_qk(gj & 3, (gs + jj) & 1, jj == n_t - 1); else ptx::mbar_arrive(bar(L::bKEmpty + (gj & 3)));
+            }
+            __syncwarp();
+          }
+        }
+        // step j: P_t.V(j), then Q_t.K(j+2) into the S buffer P_t(j) just vacated (in order behind P_t.V(j))
+        for (int j = 0; j < n_all; ++j) {
+          const uint32_t gj = g + j;
+          const int s = gj & 3, s2 = (gj + 2) & 3, buf = (gs + j) & 1;
+          const bool has_pv = j < n_t;
+          const bool more = j + 2 < n_all;
+          ptx::mbar_wait(bar(L::bVFull + s), (gj >> 2) & 1u);
+          if (more) ptx::mbar_wait(bar(L::bKFull + s2), ((gj + 2) >> 2) & 1u);
+          if (has_pv) {
+            if (j == 0) ptx::mbar_wait(bar(L::bOEmpty + t), (n_act & 1u) ^ 1u);  // the previous item's O_t has been read out
+            ptx::mbar_wait(bar(L::bPFull + 2 * t + buf), ((gs + j) >> 1) & 1u);
+          }
           ptx::tc_fence_after_sync();
           if (ptx::elect_one()) {
-            if (jj < n_t) issue_qk(jj, jj); else ptx::mbar_arrive(bar(L::bKEmpty + jj));
+            if (has_pv) {
+              issue_pv(s, buf, j > 0);
+              if (j == n_t - 2) ptx::mma_commit(bar(L::bPvDone + t));
+              if (j == n_t - 1) ptx::mma_commit(bar(L::bOFull + t));
+            } else {
+              ptx::mbar_arrive(bar(L::bVEmpty + s));
+            }
+            if (more) {
+              if (j + 2 < n_t) issue_qk(s2, buf, j + 2 == n_t - 1); else ptx::mbar_arrive(bar(L::bKEmpty + s2));
+            }
           }
           __syncwarp();
         }
-      }
-      // step j: P_t.V(j), then Q_t.K(j+2) into the S buffer P_t(j) just vacated (in order behind P_t.V(j))
-      for (int j = 0; j < n_all; ++j) {
-        const int s = j & 3, s2 = (j + 2) & 3, buf = j & 1;
-        const bool has_pv = j < n_t;
-        const bool more = j + 2 < n_all;
-        ptx::mbar_wait(bar(L::bVFull + s), static_cast<uint32_t>(j >> 2) & 1u);
-        if (more) ptx::mbar_wait(bar(L::bKFull + s2), static_cast<uint32_t>((j + 2) >> 2) & 1u);
-        if (has_pv) ptx::mbar_wait(bar(L::bPFull + 2 * t + buf), static_cast<uint32_t>(j >> 1) & 1u);
-        ptx::tc_fence_after_sync();
-        if (ptx::elect_one()) {
-          if (has_pv) {
-            issue_pv(s, buf, j > 0);
-            if (j == n_t - 2) ptx::mma_commit(bar(L::bPvDone + t));
-            if (j == n_t - 1) ptx::mma_commit(bar(L::bOFull + t));
-          } else {
-            ptx::mbar_arrive(bar(L::bVEmpty + s));
-          }
-          if (more) {
-            if (j + 2 < n_t) issue_qk(s2, buf); else ptx::mbar_arrive(bar(L::bKEmpty + s2));
-          }
-        }
-        __syncwarp();
+        g += n_all;
+        gs += n_t;
+        if (n_t > 0) ++n_act;
       }
     }
   } else {
@@ -340,113 +440,126 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     const uint32_t tmem_o = tmem_t + kP2ColO;
     const int tok = r / a.group;
     const int g = r - tok * a.group;
-    const int first = i0 + t * a.tq;
-    const int i = first + tok;                       // query position within the sequence
-    const bool row_valid = (tok < a.tq) && (i < q_len);
-    const int lim = i + (kv_len - q_len);            // last visible key index of this row
-    const int n_mine = t ? nt[1] : nt[0];
-    float m_used = 0.f;                              // exponent reference (scaled log2 domain)
-    float l = 0.f;
-    // Rows past the tile's valid (token, head) pairs are padding; a warp that owns only padding rows skips the math.
-    const int rows_real = (min(q_len, first + a.tq) - first) * a.group;
-    const bool warp_active = (warp & 3) * 32 < rows_real;
+    uint32_t gs = 0, n_act = 0, n_pv2 = 0, n_it = 0;
 
-    for (int j = 0; j < n_mine; ++j) {
-      const int buf = j & 1;
-      const uint32_t tmem_s = tmem_t + buf * kP2TileN;
-      const int kv0 = (j_begin + j) * kP2TileN;
-      const int col_lim = lim - kv0;                 // columns [0, col_lim] are visible
-      ptx::mbar_wait(bar(L::bSFull + 2 * t + buf), static_cast<uint32_t>(j >> 1) & 1u);
-      ptx::tc_fence_after_sync();
-      if (warp_active && !(a.debug & 1)) {
-        uint32_t s[2][32];
+    for (;;) {
+      const int k = next_item(n_it++, false);
+      if (k >= a.n_items) break;
+      P2Item it;
+      p2_decode_item(a, k, it);
+      const int n_mine = t ? it.nt[1] : it.nt[0];
+      if (n_mine == 0) continue;
+      const int first = it.i0 + t * a.tq;
+      const int i = first + tok;                       // query position within the sequence
+      const bool row_valid = (tok < a.tq) && (i < it.q_len);
+      const int lim = i + (it.kv_len - it.q_len);      // last visible key index of this row
+      float m_used = 0.f;                              // exponent reference (scaled log2 domain)
+      float l = 0.f;
+      // Rows past the tile's valid (token, head) pairs are padding; a warp that owns only padding rows skips the math.
+      const int rows_real = (min(it.q_len, first + a.tq) - first) * a.group;
+      const bool warp_active = (warp & 3) * 32 < rows_real;
+
+      for (int j = 0; j < n_mine; ++j) {
+        const uint32_t sj = gs + j;
+        const int buf = sj & 1;
+        const uint32_t tmem_s = tmem_t + buf * kP2TileN;
+        const int kv0 = (it.j_begin + j) * kP2TileN;
+        const int col_lim = lim - kv0;                 // columns [0, col_lim] are visible
+        ptx::mbar_wait(bar(L::bSFull + 2 * t + buf), (sj >> 1) & 1u);
+        ptx::tc_fence_after_sync();
+        if (warp_active && !(a.debug & 1)) {
+          uint32_t s[2][32];
 #pragma unroll
-        for (int c = 0; c < 2; ++c) ptx::tmem_ld_x32(tmem_s + c * 32, s[c]);
-        ptx::tmem_wait_ld();
-        if (__any_sync(0xffffffffu, col_lim < kP2TileN - 1)) {  // step touches the causal diagonal / end of the sequence
+          for (int c = 0; c < 2; ++c) ptx::tmem_ld_x32(tmem_s + c * 32, s[c]);
+          ptx::tmem_wait_ld();
+          if (__any_sync(0xffffffffu, col_lim < kP2TileN - 1)) {  // step touches the causal diagonal / end of the sequence
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e)
+                if (c * 32 + e > col_lim) s[c][e] = 0xff800000u;  // -inf
+            }
+          }
+          float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (c * 32 + e > col_lim) s[c][e] = 0xff800000u;  // -inf
+            for (int e = 0; e < 32; e += 8) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                mx4[u] = fmax3(mx4[u], __uint_as_float(s[c][e + 2 * u]), __uint_as_float(s[c][e + 2 * u + 1]));
+            }
           }
-        }
-        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+          const float mxs = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * a.scale_log2;
+          if (j == 0) {
+            m_used = (mxs == -INFINITY) ? 0.f : mxs;
+          } else if (__any_sync(0xffffffffu, mxs > m_used + kP2Rescale)) {
+            // Lazy rescale: the warp pays the TMEM round trip only when some row's max grew by more than 2^8.  O_t must be
+            // quiescent: P_t.V(j-1) complete (implied by S_t(j+1), issued behind it; the last step has its own commit) and
+            // P_t.V(j) not issued before this thread's P arrival below.
+            if (j + 1 < n_mine) ptx::mbar_wait(bar(L::bSFull + 2 * t + (buf ^ 1)), ((sj + 1) >> 1) & 1u);
+            else ptx::mbar_wait(bar(L::bPvDone + t), n_pv2 & 1u);
+            ptx::tc_fence_after_sync();
+            const float m_new = fmaxf(m_used, mxs);
+            const float alpha = fast_exp2(m_used - m_new);
+            l *= alpha;
+            m_used = m_new;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+            for (int c = 0; c < 4; ++c) {
+              uint32_t o[32];
+              ptx::tmem_ld_x32(tmem_o + c * 32, o);
+              ptx::tmem_wait_ld();
 #pragma unroll
-          for (int e = 0; e < 32; e += 8) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              mx4[u] = fmax3(mx4[u], __uint_as_float(s[c][e + 2 * u]), __uint_as_float(s[c][e + 2 * u + 1]));
+              for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+              ptx::tmem_st_x32(tmem_o + c * 32, o);
+            }
           }
-        }
-        const float mxs = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * a.scale_log2;
-        if (j == 0) {
-          m_used = (mxs == -INFINITY) ? 0.f : mxs;
-        } else if (__any_sync(0xffffffffu, mxs > m_used + kP2Rescale)) {
-          // Lazy rescale: the warp pays the TMEM round trip only when some row's max grew by more than 2^8.  O_t must be
-          // quiescent: P_t.V(j-1) complete (implied by S_t(j+1), issued behind it; the last step has its own commit) and
-          // P_t.V(j) not issued before this thread's P arrival below.
-          if (j + 1 < n_mine) ptx::mbar_wait(bar(L::bSFull + 2 * t + (buf ^ 1)), static_cast<uint32_t>((j + 1) >> 1) & 1u);
-          else ptx::mbar_wait(bar(L::bPvDone + t), 0);
-          ptx::tc_fence_after_sync();
-          const float m_new = fmaxf(m_used, mxs);
-          const float alpha = fast_exp2(m_used - m_new);
-          l *= alpha;
-          m_used = m_new;
+          // P = exp2(S * scale - m) as 16-bit pairs, written over S (every S column is already in registers)
+          const float2 sc2 = make_float2(a.scale_log2, a.scale_log2);
+          const float2 nm2 = make_float2(-m_used, -m_used);
+          float2 ls2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t o[32];
-            ptx::tmem_ld_x32(tmem_o + c * 32, o);
-            ptx::tmem_wait_ld();
+          for (int c = 0; c < 2; ++c) {
+            uint32_t pk[16];
 #pragma unroll
-            for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
-            ptx::tmem_st_x32(tmem_o + c * 32, o);
+            for (int e = 0; e < 32; e += 2) {
+              const float2 x2 = ffma2(make_float2(__uint_as_float(s[c][e]), __uint_as_float(s[c][e + 1])), sc2, nm2);
+              const float2 p2 = (((e >> 1) & 3) >= 4 - PF) ? exp2_poly2(x2) : make_float2(fast_exp2(x2.x), fast_exp2(x2.y));
+              ls2[(e >> 1) & 1] = fadd2(ls2[(e >> 1) & 1], p2);
+              pk[e >> 1] = pack2<T>(p2.x, p2.y);
+            }
+            ptx::tmem_st_x16(tmem_s + c * 16, pk);
           }
+          l += (ls2[0].x + ls2[0].y) + (ls2[1].x + ls2[1].y);
         }
-        // P = exp2(S * scale - m) as 16-bit pairs, written over S (every S column is already in registers)
-        const float2 sc2 = make_float2(a.scale_log2, a.scale_log2);
-        const float2 nm2 = make_float2(-m_used, -m_used);
-        float2 ls2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            const float2 x2 = ffma2(make_float2(__uint_as_float(s[c][e]), __uint_as_float(s[c][e + 1])), sc2, nm2);
-            const float2 p2 = (((e >> 1) & 3) >= 4 - PF) ? exp2_poly2(x2) : make_float2(fast_exp2(x2.x), fast_exp2(x2.y));
-            ls2[(e >> 1) & 1] = fadd2(ls2[(e >> 1) & 1], p2);
-            pk[e >> 1] = pack2<T>(p2.x, p2.y);
-          }
-          ptx::tmem_st_x16(tmem_s + c * 16, pk);
-        }
-        l += (ls2[0].x + ls2[0].y) + (ls2[1].x + ls2[1].y);
+        ptx::tmem_wait_st();
+        ptx::tc_fence_before_sync();
+        ptx::mbar_arrive(bar(L::bPFull + 2 * t + buf));
       }
-      ptx::tmem_wait_st();
-      ptx::tc_fence_before_sync();
-      ptx::mbar_arrive(bar(L::bPFull + 2 * t + buf));
-    }
 
-    // ---- epilogue: O / l -> out (or the fp32 split-KV partial) ---------------------------------------------------------
-    if (n_mine > 0) {
-      ptx::mbar_wait(bar(L::bOFull + t), 0);
+      // ---- epilogue: O / l -> out (or the fp32 split-KV partial) ---------------------------------------------------------
+      ptx::mbar_wait(bar(L::bOFull + t), n_act & 1u);
       ptx::tc_fence_after_sync();
       const float inv_l = 1.f / l;
-      const int head = kvh * a.group + g;
-      T* orow = static_cast<T*>(a.out) + static_cast<int64_t>(q_start + i) * a.out_row_stride + head * kP2D;
-      const int64_t pidx = (static_cast<int64_t>(q_start + i) * a.n_qo_heads + head) * a.n_splits + sp;
+      const int head = it.kvh * a.group + g;
+      T* orow = static_cast<T*>(a.out) + static_cast<int64_t>(it.q_start + i) * a.out_row_stride + head * kP2D;
+      const int64_t pidx = (static_cast<int64_t>(it.q_start + i) * a.n_qo_heads + head) * a.n_splits + it.sp;
       if (a.n_splits > 1 && row_valid) {
         a.part_ml[pidx * 2 + 0] = m_used;
         a.part_ml[pidx * 2 + 1] = l;
       }
-      if (warp_active) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t v[32];
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        if (warp_active) {
           ptx::tmem_ld_x32(tmem_o + c * 32, v);
           ptx::tmem_wait_ld();
-          if (!row_valid) continue;
+        }
+        if (c == 3) {  // O_t has left TMEM: the next item's first P.V may overwrite it
+          ptx::tc_fence_before_sync();
+          ptx::mbar_arrive(bar(L::bOEmpty + t));
+        }
+        if (warp_active && row_valid) {
           if (a.n_splits > 1) {
             float4* dst = reinterpret_cast<float4*>(a.part_o + pidx * kP2D + c * 32);
 #pragma unroll
@@ -465,6 +578,9 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
           }
         }
       }
+      gs += n_mine;
+      ++n_act;
+      if (n_mine >= 2) ++n_pv2;
     }
   }
 
@@ -496,9 +612,12 @@ static int launch_pair_t(const HiAttnArgs& args, const P2Args& a, const CUtensor
     HI_CUDA(cudaFuncSetAttribute(paged_attn_pair_kernel<T, NK, NV, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamicBytes));
     configured = true;
   }
-  const int n_pairs = (args.max_q_len + 2 * a.tq - 1) / (2 * a.tq);
-  const dim3 grid = a.work_items != nullptr ? dim3(static_cast<unsigned>(args.n_work_items) * a.n_splits * args.n_kv_heads, 1, 1)
-                                            : dim3(n_pairs * a.n_splits, args.n_kv_heads, args.n_seqs);
+  // persistent: one CTA per SM walks the items with a stride of the grid size
+  static int n_sms = 0;
+  if (n_sms == 0) HI_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, args.device));
+  int ctas = a.n_items < n_sms ? a.n_items : n_sms;
+  if (const char* env = getenv("HI_PAIR_CTAS")) ctas = atoi(env) > 0 ? atoi(env) : ctas;  // tuning / test override
+  const dim3 grid(ctas, 1, 1);
   timing_mark_start(stream);
   paged_attn_pair_kernel<T, NK, NV, PF><<<grid, kP2Threads, L::kDynamicBytes, stream>>>(mq, mk, mv, a);
   timing_mark_stop(stream);
@@ -561,6 +680,18 @@ int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
     const int64_t entries = static_cast<int64_t>(args.n_tokens) * args.n_qo_heads * a.n_splits;
     a.part_o = static_cast<float*>(args.workspace);
     a.part_ml = a.part_o + entries * kP2D;
+  }
+  a.max_pairs = n_pairs;
+  a.n_items = static_cast<int>(base_ctas * a.n_splits);
+  // dynamic work distribution: a counter in the last 256 bytes of the workspace, zeroed in stream order before the launch
+  a.work_counter = nullptr;
+  {
+    const int64_t partial_bytes = a.n_splits > 1 ? static_cast<int64_t>(args.n_tokens) * args.n_qo_heads * a.n_splits * (kP2D + 2) * 4 : 0;
+    const char* env = getenv("HI_PAIR_STATIC");  // tuning / test override: static boustrophedon assignment
+    if (args.workspace != nullptr && args.workspace_bytes >= partial_bytes + 512 && !(env != nullptr && env[0] == '1')) {
+      a.work_counter = reinterpret_cast<unsigned int*>(static_cast<char*>(args.workspace) + ((args.workspace_bytes - 256) & ~int64_t(255)));
+      HI_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned int), stream));
+    }
   }
 
   CUtensorMap mq, mk, mv;

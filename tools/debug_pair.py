@@ -18,8 +18,8 @@ NK = NV = 4
 KBARS = 2 * 32768 + (NK + NV) * 16384
 NAMES = (["qfull0", "qfull1"] + [f"kfull{i}" for i in range(NK)] + [f"kempty{i}" for i in range(NK)] + [f"vfull{i}" for i in range(NV)]
          + [f"vempty{i}" for i in range(NV)] + ["sfull00", "sfull01", "sfull10", "sfull11", "pfull00", "pfull01", "pfull10", "pfull11", "pvdone0", "pvdone1",
-                                                 "ofull0", "ofull1", "vtail"])
-cases = [("q128 kv128", [(128, 128)], 1, 1), ("q256 kv256", [(256, 256)], 1, 1), ("q300 kv300", [(300, 300)], 1, 1),
+                                                 "ofull0", "ofull1", "vtail", "qempty0", "qempty1", "oempty0", "oempty1", "itemfull0", "itemfull1", "itemfull2", "itemfull3", "itemempty0", "itemempty1", "itemempty2", "itemempty3"])
+cases = [("q128 kv128", [(128, 128)], 1, 1), ("2 heads q128 kv128", [(128, 128)], 2, 2), ("mha4 ragged", [(300, 300), (1, 77), (64, 500), (700, 1500)], 4, 4), ("q256 kv256", [(256, 256)], 1, 1), ("q300 kv300", [(300, 300)], 1, 1),
          ("q700 kv1500", [(700, 1500)], 1, 1), ("gqa7", [(1, 300), (40, 170), (1, 17), (200, 513)], 28, 4)]
 dev = "cuda:0"
 fn = _lib.lib.hi_debug_mbar_timeout
