@@ -68,6 +68,14 @@ SIGNATURES = {
 def _load() -> ctypes.CDLL:
     from . import build as _build
 
+    override = os.environ.get("HI_B200_LIB")  # dev only: an instrumented variant built by build.build_variant()
+    if override:
+        lib = ctypes.CDLL(override)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        return lib
     force = os.environ.get("HI_B200_REBUILD") == "1"
     if force or not LIB_PATH.exists() or not _build.is_current():
         try:

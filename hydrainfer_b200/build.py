@@ -55,6 +55,27 @@ def is_current() -> bool:
     return LIB_PATH.exists() and stamp_file.exists() and stamp_file.read_text() == _stamp()
 
 
+def build_variant(name: str, defines: list[str]) -> Path:
+    """Dev builds (tracing / debug instrumentation): lib/libhi_b200_<name>.so compiled with extra -D flags.  Loaded
+    instead of the product library when HI_B200_LIB points at it (hydrainfer_b200/_lib.py); never the default."""
+    nvcc = _nvcc()
+    obj_dir = CSRC / f"build_{name}"
+    obj_dir.mkdir(parents=True, exist_ok=True)
+    LIB_DIR.mkdir(parents=True, exist_ok=True)
+    out = LIB_DIR / f"libhi_b200_{name}.so"
+    objs = []
+    for src in SOURCES:
+        obj = obj_dir / (Path(src).stem + ".o")
+        res = subprocess.run([nvcc, *NVCC_FLAGS, *defines, "-c", str(CSRC / src), "-o", str(obj)], capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{res.stdout}\n{res.stderr}")
+        objs.append(str(obj))
+    res = subprocess.run([nvcc, "-shared", "-o", str(out), *objs, "-cudart", "static"], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile (if sources changed) and return the path of the shared library."""
     stamp_file = LIB_DIR / "build.stamp"
@@ -88,5 +109,9 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose=True)
-    print(path)
+    if "--variant" in sys.argv:  # python -m hydrainfer_b200.build --variant trace -DHI_PAIR_TRACE
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        path = build(force="--force" in sys.argv, verbose=True)
+        print(path)

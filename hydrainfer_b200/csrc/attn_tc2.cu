@@ -172,6 +172,14 @@ __device__ __forceinline__ int p2_claim_item(const P2Args& a, int round, int lan
   return k < a.n_items ? k : a.n_items + 1;  // + 1: a hole in the last round, not the end (static mode only)
 }
 
+// Timeline instrumentation (dev builds with -DHI_PAIR_TRACE, tools/pair_trace.py): CTA 0 records, per role, clock64 stamps
+// of its hand-off points.  Record = clock (40 bits) | tag << 40 | step << 44 | item << 56.
+#ifdef HI_PAIR_TRACE
+constexpr int kTraceRoles = 6, kTraceCap = 8192;
+static __device__ unsigned long long g_pair_trace[kTraceRoles * kTraceCap];
+static __device__ unsigned int g_pair_trace_n[kTraceRoles];
+#endif
+
 // PF = how many of every 4 (pairs of) exponentials run on the FMA pipes (exp2_poly2) instead of MUFU.EX2.
 template <typename T, int NK, int NV, int PF>
 __global__ void __launch_bounds__(kP2Threads, 1)
@@ -191,6 +199,18 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int pages_per_tile = kP2TileN / a.block_size;
+#ifdef HI_PAIR_TRACE
+  const int tr_role = (warp == 8) ? 0 : (warp == 11) ? 1 : (warp == 9) ? 2 : (warp == 10) ? 3 : (threadIdx.x == 0) ? 4 : (threadIdx.x == 128) ? 5 : -1;
+  const bool tr_on = blockIdx.x == 0 && tr_role >= 0 && (warp < 8 || lane == 0);
+  unsigned int tr_n = 0;
+  auto trace = [&](int tag, unsigned int item, int step) {
+    if (tr_on && tr_n < kTraceCap)
+      g_pair_trace[tr_role * kTraceCap + tr_n++] = (static_cast<unsigned long long>(clock64()) & 0xffffffffffull) | (static_cast<unsigned long long>(tag & 15) << 40) |
+                                                   (static_cast<unsigned long long>(step & 4095) << 44) | (static_cast<unsigned long long>(item & 255u) << 56);
+  };
+#else
+  auto trace = [&](int, unsigned int, int) {};
+#endif
 
   // ---- one-time setup ------------------------------------------------------------------------------------------------
   if (threadIdx.x == 0) {
@@ -269,11 +289,13 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         P2Item it;
         p2_decode_item(a, k, it);
         if (it.n_all == 0) continue;
+        trace(1, n_it, it.n_all);
         if (is_k) {
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             if (it.nt[t] > 0) {
               ptx::mbar_wait(bar(L::bQEmpty + t), (n_q[t] & 1u) ^ 1u);  // the previous item's Q_t.K products are done
+              trace(2, n_it, t);
               if (ptx::elect_one()) {
                 const uint32_t dst = smem_base + L::kQ + t * kP2QTile;
                 ptx::mbar_arrive_expect_tx(bar(L::bQFull + t), 2u * static_cast<uint32_t>(a.group * a.tq) * 128u);
@@ -302,6 +324,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
           const int kv0 = (it.j_begin + j) * kP2TileN;
           const bool tail = !is_k && (kv0 + kP2TileN > it.kv_len);  // at most one such step per item
           ptx::mbar_wait(bar(b_empty + st), ((g >> 2) & 1u) ^ 1u);
+          trace(3, n_it, j);
           const uint32_t full_bar = tail ? bar(L::bVTail) : bar(b_full + st);
           uint32_t dst = ring + st * kP2Tile;
           if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(full_bar, tx);
@@ -383,9 +406,11 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         if (it.n_all == 0) continue;
         const int n_t = t ? it.nt[1] : it.nt[0];
         const int n_all = it.n_all;
+        trace(1, n_it, n_t);
         // prologue: S_t(0) and S_t(1).  Steps at or beyond n_t (this tile sees fewer keys than its sibling) only release
         // the ring stages.
         if (n_t > 0) ptx::mbar_wait(bar(L::bQFull + t), n_act & 1u);
+        trace(2, n_it, 0);
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
           if (jj < n_all) {
@@ -411,6 +436,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
             ptx::mbar_wait(bar(L::bPFull + 2 * t + buf), ((gs + j) >> 1) & 1u);
           }
           ptx::tc_fence_after_sync();
+          trace(3, n_it, j);
           if (ptx::elect_one()) {
             if (has_pv) {
               issue_pv(s, buf, j > 0);
@@ -424,6 +450,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
             }
           }
           __syncwarp();
+          trace(4, n_it, j);
         }
         g += n_all;
         gs += n_t;
@@ -449,6 +476,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       p2_decode_item(a, k, it);
       const int n_mine = t ? it.nt[1] : it.nt[0];
       if (n_mine == 0) continue;
+      trace(1, n_it, n_mine);
       const int first = it.i0 + t * a.tq;
       const int i = first + tok;                       // query position within the sequence
       const bool row_valid = (tok < a.tq) && (i < it.q_len);
@@ -467,6 +495,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         const int col_lim = lim - kv0;                 // columns [0, col_lim] are visible
         ptx::mbar_wait(bar(L::bSFull + 2 * t + buf), (sj >> 1) & 1u);
         ptx::tc_fence_after_sync();
+        trace(3, n_it, j);
         if (warp_active && !(a.debug & 1)) {
           uint32_t s[2][32];
 #pragma unroll
@@ -535,11 +564,13 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         ptx::tmem_wait_st();
         ptx::tc_fence_before_sync();
         ptx::mbar_arrive(bar(L::bPFull + 2 * t + buf));
+        trace(4, n_it, j);
       }
 
       // ---- epilogue: O / l -> out (or the fp32 split-KV partial) ---------------------------------------------------------
       ptx::mbar_wait(bar(L::bOFull + t), n_act & 1u);
       ptx::tc_fence_after_sync();
+      trace(5, n_it, 0);
       const float inv_l = 1.f / l;
       const int head = it.kvh * a.group + g;
       T* orow = static_cast<T*>(a.out) + static_cast<int64_t>(it.q_start + i) * a.out_row_stride + head * kP2D;
@@ -578,6 +609,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
           }
         }
       }
+      trace(6, n_it, 0);
       gs += n_mine;
       ++n_act;
       if (n_mine >= 2) ++n_pv2;
@@ -585,6 +617,9 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   }
 
   // ---- teardown ----------------------------------------------------------------------------------------------------
+#ifdef HI_PAIR_TRACE
+  if (tr_on) g_pair_trace_n[tr_role] = tr_n;
+#endif
   ptx::tc_fence_before_sync();
   __syncthreads();
   if (warp == 8) {
@@ -741,6 +776,16 @@ extern "C" int hi_debug_mbar_timeout(unsigned int out[64]) {
   if (cudaMemcpyFromSymbol(out, hi::ptx::g_mbar_debug, 64 * sizeof(unsigned int)) != cudaSuccess) return -1;
   unsigned int zero[64] = {};
   cudaMemcpyToSymbol(hi::ptx::g_mbar_debug, zero, sizeof(zero));
+  return 0;
+}
+#endif
+
+#ifdef HI_PAIR_TRACE
+// Dev builds only: copies the timeline CTA 0 recorded during the last pair-kernel launch (see tools/pair_trace.py).
+extern "C" int hi_debug_pair_trace(unsigned long long* records /* [6][8192] */, unsigned int* counts /* [6] */) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(records, hi::g_pair_trace, sizeof(unsigned long long) * hi::kTraceRoles * hi::kTraceCap) != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(counts, hi::g_pair_trace_n, sizeof(unsigned int) * hi::kTraceRoles) != cudaSuccess) return -1;
   return 0;
 }
 #endif

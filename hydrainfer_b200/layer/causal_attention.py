@@ -62,6 +62,7 @@ class _PinnedStaging:
     def __init__(self, device: torch.device, slots: int = 4):
         self.device = device
         self.buffers = [torch.empty(0, dtype=torch.int32) for _ in range(slots)]
+        self.views = [memoryview(b"").cast("i") for _ in range(slots)]  # int32 memoryviews of the pinned buffers
         self.events = [None] * slots
         self.cursor = 0
 
@@ -72,27 +73,69 @@ class _PinnedStaging:
             ring = cls._rings[device] = cls(device)
         return ring
 
-    def upload(self, flat: array) -> Tensor:
+    def upload(self, parts: list, offsets: list[int], total: int) -> Tensor:
+        """Writes the int32 arrays `parts` at `offsets` of one pinned buffer and starts its H2D copy."""
         i = self.cursor
         self.cursor = (i + 1) % len(self.buffers)
         if self.events[i] is not None:
             self.events[i].synchronize()  # the copy that last used this slot has finished
-        n = len(flat)
-        if self.buffers[i].numel() < n:
-            self.buffers[i] = torch.empty(max(n, 4096, 2 * self.buffers[i].numel()), dtype=torch.int32).pin_memory()
-        host = self.buffers[i][:n]
-        host.copy_(torch.frombuffer(flat, dtype=torch.int32))
-        dev = host.to(self.device, non_blocking=True)
+        if self.buffers[i].numel() < total:
+            self.buffers[i] = torch.empty(max(total, 4096, 2 * self.buffers[i].numel()), dtype=torch.int32).pin_memory()
+            self.views[i] = memoryview(self.buffers[i].numpy()).cast("B").cast("i")
+        view = self.views[i]
+        for part, o in zip(parts, offsets):
+            if len(part):
+                view[o:o + len(part)] = memoryview(part)  # memcpy
+        dev = self.buffers[i][:total].to(self.device, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.device))
         self.events[i] = ev
         return dev
 
 
+class _BlockTableCache:
+    """int32 images of the per-sequence block-table lists.
+
+    The engine passes `virtual_kv_cache.block_table` to add_request every step (reference engine/parameters_builder.py:
+    63-69): the SAME list object for the lifetime of a request, grown in place by whole blocks
+    (token_cache_manger.py:150-159).  Converting its Python ints to int32 again every step is the largest host cost of a
+    decode step (8192 ints for batch 64 at context 2048), so the converted image is kept per list object and only the
+    appended tail is converted.  An entry is used only after its snapshot compares equal to the list (a C-speed list
+    compare), so a recycled id() or an in-place edit can never produce a stale table."""
+
+    def __init__(self, capacity: int = 8192):
+        self.capacity = capacity
+        self.entries: dict[int, tuple[list[int], array]] = {}
+
+    def image(self, table: list[int]) -> array:
+        key = id(table)
+        hit = self.entries.get(key)
+        if hit is not None:
+            snap, img = hit
+            n = len(snap)
+            if len(table) == n:
+                if table == snap:
+                    return img
+            elif len(table) > n and table[:n] == snap:  # grown by whole blocks since the last step
+                tail = table[n:]
+                img = img + array("i", tail)  # a new array: images handed out earlier stay intact
+                self.entries[key] = (snap + tail, img)
+                return img
+        img = array("i", table)
+        if len(self.entries) >= self.capacity:
+            self.entries.clear()
+        self.entries[key] = (list(table), img)
+        return img
+
+
+_block_table_cache = _BlockTableCache()
+
+
 class AttentionParametersBuilder:
     """add_request() per sequence, add_kv_cache() per layer, then build_attention_parameters()
-    (causal_attention.py:110-210).  The six metadata lists are uploaded ONCE as a single pinned int32 buffer and
-    sliced on the device (the reference does six torch.tensor(list) H2D copies, :163-168)."""
+    (causal_attention.py:110-210).  The six metadata arrays are uploaded ONCE as a single pinned int32 buffer and
+    sliced on the device (the reference does six torch.tensor(list) H2D copies, :163-168); they are accumulated as
+    int32 `array`s, not Python lists, so assembling the buffer is a handful of memcpys."""
 
     def __init__(self, num_qo_heads: int, num_kv_heads: int, head_dim: int, block_size: int, device: torch.device,
                  flash_infer_batch_prefill_handler=None, flash_infer_batch_decode_handler=None):
@@ -102,12 +145,12 @@ class AttentionParametersBuilder:
         self.block_size = block_size
         self.device = torch.device(device)
         self.kv_caches: list[KVCache] = []
-        self.q_cu_seq_lens: list[int] = [0]
-        self.kv_cu_seq_lens: list[int] = [0]
-        self.paged_kv_last_page_len: list[int] = []
-        self.new_cache_slots: list[int] = []
-        self.block_tables: list[int] = []
-        self.cu_blocks_lens: list[int] = [0]
+        self.q_cu_seq_lens = array("i", [0])
+        self.kv_cu_seq_lens = array("i", [0])
+        self.paged_kv_last_page_len = array("i")
+        self.new_cache_slots = array("i")
+        self.block_tables = array("i")
+        self.cu_blocks_lens = array("i", [0])
         self.num_sequences = 0
         self.all_sequences_decode = True
         self.q_max_seq_len = 0
@@ -118,13 +161,16 @@ class AttentionParametersBuilder:
         self.q_cu_seq_lens.append(self.q_cu_seq_lens[-1] + q_seq_len)
         self.kv_cu_seq_lens.append(self.kv_cu_seq_lens[-1] + kv_seq_len)
         self.paged_kv_last_page_len.append((kv_seq_len + self.block_size - 1) % self.block_size + 1)
-        self.new_cache_slots += new_cache_slots
-        self.block_tables += block_table
+        self.new_cache_slots.fromlist(new_cache_slots) if type(new_cache_slots) is list else self.new_cache_slots.extend(new_cache_slots)
+        self.block_tables.extend(_block_table_cache.image(block_table) if type(block_table) is list else array("i", block_table))
         self.cu_blocks_lens.append(self.cu_blocks_lens[-1] + len(block_table))
         self.num_sequences += 1
-        self.all_sequences_decode = self.all_sequences_decode and q_seq_len == 1
-        self.q_max_seq_len = max(self.q_max_seq_len, q_seq_len)
-        self.kv_max_seq_len = max(self.kv_max_seq_len, kv_seq_len)
+        if q_seq_len != 1:
+            self.all_sequences_decode = False
+        if q_seq_len > self.q_max_seq_len:
+            self.q_max_seq_len = q_seq_len
+        if kv_seq_len > self.kv_max_seq_len:
+            self.kv_max_seq_len = kv_seq_len
         self.seq_lens.append((q_seq_len, kv_seq_len))
 
     def add_kv_cache(self, kv_cache: KVCache) -> None:
@@ -135,16 +181,17 @@ class AttentionParametersBuilder:
         parts = [self.q_cu_seq_lens, self.kv_cu_seq_lens, self.paged_kv_last_page_len, self.new_cache_slots,
                  self.block_tables, self.cu_blocks_lens, work_flat]
         # each slice starts on a 16-byte boundary (4 int32) so the kernels' vector paths never see a misaligned table
-        offsets, flat_list = [], []
+        offsets, total = [], 0
         for part in parts:
-            offsets.append(len(flat_list))
-            flat_list += part
-            flat_list += [0] * (-len(flat_list) % 4)
-        flat = array("i", flat_list)  # one C-speed conversion (about 5x faster than torch.tensor(list))
+            offsets.append(total)
+            total += (len(part) + 3) & ~3
         if self.device.type == "cuda":
-            dev = _PinnedStaging.get(self.device).upload(flat)
+            dev = _PinnedStaging.get(self.device).upload(parts, offsets, total)
         else:
-            dev = torch.frombuffer(flat, dtype=torch.int32).clone() if len(flat) else torch.empty(0, dtype=torch.int32)
+            dev = torch.zeros(total, dtype=torch.int32)
+            for part, o in zip(parts, offsets):
+                if len(part):
+                    dev[o:o + len(part)] = torch.frombuffer(part, dtype=torch.int32)
         views = [dev[o:o + len(part)] for o, part in zip(offsets, parts)]
         return [AttentionParameters(
             kv_cache=kv_cache,
@@ -152,25 +199,26 @@ class AttentionParametersBuilder:
             block_tables=views[4], cu_blocks_lens=views[5],
             num_sequences=self.num_sequences, all_sequences_decode=self.all_sequences_decode,
             q_max_seq_len=self.q_max_seq_len, kv_max_seq_len=self.kv_max_seq_len, flash_infer_handler=None,
-            work_items=views[6].view(-1, 2) if work_flat else None, work_tile_tokens=tile_tokens, qk_work=qk_work,
+            work_items=views[6].view(-1, 2) if len(work_flat) else None, work_tile_tokens=tile_tokens, qk_work=qk_work,
         ) for kv_cache in self.kv_caches]
 
-    def _plan(self) -> tuple[list[int], int, int]:
+    def _plan(self) -> tuple[array, int, int]:
         """Host-side plan for batches with prefill rows: every run of `tile_tokens` query tokens of a sequence is one work
         item whose cost is the number of keys its last token sees; items go out heaviest first (longest-processing-time
         order), so the launch ends on light tiles, and the grid holds exactly the tiles that exist."""
+        empty = array("i")
         if self.all_sequences_decode or self.device.type != "cuda":
-            return [], 0, 0
+            return empty, 0, 0
         from .. import _lib
         tile_tokens = int(_lib.lib.hi_attention_tile_tokens(self.num_qo_heads, self.num_kv_heads))
         if tile_tokens <= 0:
-            return [], 0, 0
+            return empty, 0, 0
         items = []
         for b, (q, kv) in enumerate(self.seq_lens):
             for tile in range((q + tile_tokens - 1) // tile_tokens):
                 items.append((kv - q + min(q, (tile + 1) * tile_tokens), b, tile))
         items.sort(reverse=True)
-        flat = [x for _, b, tile in items for x in (b, tile)]
+        flat = array("i", [x for _, b, tile in items for x in (b, tile)])
         return flat, tile_tokens, sum(cost for cost, _, _ in items)
 
 

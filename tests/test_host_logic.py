@@ -152,3 +152,44 @@ def test_backend_selection_by_host():
     with pytest.raises(AssertionError):
         mgr.migrate_blocks(v(0, 4), v(1, 5), False)
     assert mgr.in_same_machine(0, 1) and not mgr.in_same_machine(1, 2)
+
+
+def _built_tables(requests, bs=16):
+    builder = AttentionParametersBuilder(4, 4, 128, bs, torch.device("cpu"))
+    for req in requests:
+        builder.add_request(*req)
+    builder.add_kv_cache(None)
+    p = builder.build_attention_parameters()[0]
+    return p.block_tables.tolist(), p.cu_blocks_lens.tolist(), p.new_cache_slots.tolist()
+
+
+def test_block_table_image_cache_follows_the_list():
+    """The builder keeps int32 images of the per-request block_table lists between steps (same list object every step, as
+    in the reference engine); the metadata must follow every kind of change to those lists."""
+    t0, t1 = [7, 3, 9], [5]
+    assert _built_tables([(1, 40, [9 * 16 + 7], t0), (1, 3, [5 * 16 + 2], t1)]) == ([7, 3, 9, 5], [0, 3, 4], [151, 82])
+    # unchanged lists: served from the cache
+    assert _built_tables([(1, 40, [151], t0), (1, 3, [82], t1)])[0] == [7, 3, 9, 5]
+    # grown in place by realloc (token_cache_manger.py:150-159)
+    t0 += [11, 2]
+    t1.append(6)
+    assert _built_tables([(1, 70, [0], t0), (1, 17, [0], t1)])[:2] == ([7, 3, 9, 11, 2, 5, 6], [0, 5, 7])
+    # shrunk, then edited in place at the same length: a stale image must never be used
+    del t0[2:]
+    assert _built_tables([(1, 20, [0], t0)])[0] == [7, 3]
+    t0[1] = 99
+    assert _built_tables([(1, 20, [0], t0)])[0] == [7, 99]
+    # grown AND edited inside the old prefix
+    t1[0] = 4
+    t1.append(8)
+    assert _built_tables([(1, 40, [0], t1)])[0] == [4, 6, 8]
+    # an image handed out earlier is not modified by later growth of the list
+    builder = AttentionParametersBuilder(4, 4, 128, 16, torch.device("cpu"))
+    builder.add_request(1, 40, [0], t1)
+    t1.append(1)
+    builder.add_request(1, 50, [0], t1)
+    builder.add_kv_cache(None)
+    p = builder.build_attention_parameters()[0]
+    assert p.block_tables.tolist() == [4, 6, 8, 4, 6, 8, 1] and p.cu_blocks_lens.tolist() == [0, 3, 7]
+    # tuples / other sequences are accepted too (converted every time)
+    assert _built_tables([(2, 20, (3, 4), (1, 2))])[0] == [1, 2]
