@@ -36,6 +36,18 @@ class HiAttnArgs(Structure):
     ]
 
 
+class HiRopeArgs(Structure):
+    _fields_ = [
+        ("q", c_void_p), ("k", c_void_p), ("v", c_void_p),
+        ("q_row_stride", c_int64), ("k_row_stride", c_int64), ("v_row_stride", c_int64),
+        ("positions", c_void_p), ("cos_sin", c_void_p), ("slot_ids", c_void_p), ("key_cache", c_void_p), ("value_cache", c_void_p),
+        ("n_tokens", c_int64),
+        ("n_qo_heads", c_int32), ("n_kv_heads", c_int32), ("head_dim", c_int32), ("rotary_dim", c_int32),
+        ("dtype", c_int32), ("cos_sin_dtype", c_int32), ("positions_int64", c_int32), ("interleaved", c_int32),
+        ("write_back_k", c_int32), ("force_scalar", c_int32), ("device", c_int32), ("reserved", c_int32),
+    ]
+
+
 class HiPoolGeom(Structure):
     _fields_ = [("n_layers", c_int64), ("n_tokens", c_int64), ("n_blocks", c_int64), ("run_bytes", c_int64)]
 
@@ -53,6 +65,7 @@ SIGNATURES = {
     "hi_set_kv_cache": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
                                 c_int, c_int, c_void_p]),
     "hi_set_image_cache": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
+    "hi_rope_append": (c_int, [POINTER(HiRopeArgs), c_void_p]),
     "hi_attention_workspace_bytes": (c_int64, [c_int32, c_int32, c_int32, c_int32]),
     "hi_paged_attention": (c_int, [POINTER(HiAttnArgs), c_void_p]),
     "hi_attention_tile_tokens": (c_int32, [c_int32, c_int32]),

@@ -18,7 +18,7 @@ CSRC = PKG_DIR / "csrc"
 LIB_DIR = PKG_DIR / "lib"
 LIB_PATH = LIB_DIR / "libhi_b200.so"
 OBJ_DIR = CSRC / "build"
-SOURCES = ["api.cu", "scatter.cu", "attn_simt.cu", "attn_tc.cu", "attn_tc2.cu", "attn_decode_tc.cu", "migrate.cu"]
+SOURCES = ["api.cu", "scatter.cu", "rope.cu", "attn_simt.cu", "attn_tc.cu", "attn_tc2.cu", "attn_decode_tc.cu", "migrate.cu"]
 HEADERS = ["common.cuh", "ptx_sm100.cuh", "attn_common.cuh", "tma_maps.h", "../../include/hi_b200.h"]
 
 NVCC_FLAGS = [

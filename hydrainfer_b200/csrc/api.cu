@@ -8,6 +8,7 @@
 
 static_assert(sizeof(HiAttnArgs) == 192, "HiAttnArgs layout is part of the ABI (ctypes mirror in hydrainfer_b200/_lib.py)");
 static_assert(sizeof(HiPoolGeom) == 32, "HiPoolGeom layout is part of the ABI");
+static_assert(sizeof(HiRopeArgs) == 144, "HiRopeArgs layout is part of the ABI");
 
 namespace hi {
 

@@ -1,6 +1,7 @@
 from .causal_attention import (AttentionParameters, AttentionParametersBuilder, B200CausalGroupedQueryPageAttentionHandler,
                                CausalGroupedQueryPageAttention, CausalGroupedQueryPageAttentionConfig,
                                CausalGroupedQueryPageAttentionOutput)
+from .rotary_embedding import B200RotaryEmbeddingHandler, RotaryEmbedding, compute_default_inv_freq
 
-__all__ = ["AttentionParameters", "AttentionParametersBuilder", "B200CausalGroupedQueryPageAttentionHandler",
+__all__ = ["B200RotaryEmbeddingHandler", "RotaryEmbedding", "compute_default_inv_freq", "AttentionParameters", "AttentionParametersBuilder", "B200CausalGroupedQueryPageAttentionHandler",
            "CausalGroupedQueryPageAttention", "CausalGroupedQueryPageAttentionConfig", "CausalGroupedQueryPageAttentionOutput"]

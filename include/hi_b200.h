@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HI_B200_ABI_VERSION 2
+#define HI_B200_ABI_VERSION 3
 
 typedef enum HiStatus {
   HI_OK = 0,
@@ -72,6 +72,47 @@ int hi_set_image_cache(const int32_t* slot_ids /*[dev] [n_tokens]*/,
                        int64_t n_tokens, int64_t row_elems /* n_heads*head_dim */,
                        int64_t token_row_stride /*elements*/,
                        int dtype, int device, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Rotary embedding fused with the KV append — replaces apply_rotary_pos_emb
+ * (csrc/kernel/position_embedding/rope.cu:90-117, bound in position_embedding_pybind.cpp) and, when slot_ids is not
+ * NULL, also the set_kv_cache launch that ROPECausalGroupedQueryPageAttention.forward issues right after it
+ * (hydrainfer/model/model_forward.py:81-83 -> hydrainfer/layer/causal_attention.py:402).
+ *
+ *   pair (x, y) of a head, c/s = cos/sin of the token's position:  x' = x*c - y*s,  y' = x*s + y*c
+ *   interleaved: (x, y) = (head[2i], head[2i+1]);  otherwise (head[i], head[i + rotary_dim/2])   (rope.cu:19-29)
+ *   dims >= rotary_dim pass through.  q is rotated in place.  With slot_ids: the rotated k and v go to
+ *   key_cache / value_cache[slot_ids[t]] (geometry as hi_set_kv_cache) and k itself is rewritten only if
+ *   write_back_k; without slot_ids k is rotated in place (plain apply_rotary_pos_emb).
+ *
+ * Rounding is the reference's: every product and the final sum round separately, to the element type when the
+ * table has the element type (rope.cu computes in c10::Half/BFloat16; torch's 16-bit ops in
+ * TorchRotaryEmbeddingHandler, hydrainfer/layer/rotary_embedding.py:44-83, do the same), to fp32 when the table is
+ * fp32 (torch promotes).  Results are bit-identical to that path.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct HiRopeArgs {
+  void* q;                   /* [dev] [n_tokens, n_qo_heads, head_dim], head stride == head_dim; rotated in place */
+  void* k;                   /* [dev] [n_tokens, n_kv_heads, head_dim] */
+  const void* v;             /* [dev] [n_tokens, n_kv_heads, head_dim]; only read when slot_ids != NULL */
+  int64_t q_row_stride, k_row_stride, v_row_stride; /* elements between consecutive tokens */
+  const void* positions;     /* [dev] [n_tokens] int32 (rope.cu:107) or int64 */
+  const void* cos_sin;       /* [dev] [max_positions, 2, rotary_dim/2]: cos then sin per position (rotary_embedding.py:113-115) */
+  const int32_t* slot_ids;   /* [dev] [n_tokens] physical cache slots, or NULL for rotation only */
+  void* key_cache;           /* [dev] [n_blocks, block_size, n_kv_heads, head_dim] contiguous */
+  void* value_cache;         /* [dev] same geometry */
+  int64_t n_tokens;
+  int32_t n_qo_heads, n_kv_heads, head_dim, rotary_dim;
+  int32_t dtype;             /* HiDtype of q/k/v/caches */
+  int32_t cos_sin_dtype;     /* HiDtype of the table: == dtype or HI_F32 */
+  int32_t positions_int64;   /* 0: int32 positions, 1: int64 */
+  int32_t interleaved;
+  int32_t write_back_k;      /* with slot_ids: also rewrite k in place (the reference always does) */
+  int32_t force_scalar;      /* tests: take the any-shape scalar kernel even when the vector kernel applies */
+  int32_t device;
+  int32_t reserved;
+} HiRopeArgs;
+
+int hi_rope_append(const HiRopeArgs* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Paged causal GQA attention — replaces mha_varlen_fwd (csrc/kernel/flash_attn/flash_api.cpp:216-355)

@@ -12,6 +12,8 @@ imports matplotlib / seaborn, which this image lacks; nothing on the path uses t
   TokenCache.set_caches (CPU path)                   hydrainfer/memory/token_cache.py:53-56
   BlockAllocator                                     hydrainfer/memory/block_allocator.py:11-39
   TokenCacheBlockManager.v2p                         hydrainfer/memory/token_cache_manger.py:126-133
+  RotaryEmbedding -> TorchRotaryEmbeddingHandler     hydrainfer/layer/rotary_embedding.py:19-99, 136-148
+  ROPECausalGroupedQueryPageAttention.forward        hydrainfer/model/model_forward.py:66-86
 """
 from __future__ import annotations
 
@@ -60,6 +62,87 @@ ATTENTION_CASES = [
     ("mqa_fp16_d256", [(1, 20), (7, 19)], 4, 1, 256, 16, torch.float16, False),
     ("gqa_bf16_d64_bs8", [(1, 9), (12, 30)], 4, 2, 64, 8, torch.bfloat16, False),
 ]
+
+
+# (name, n_tokens, Hq, Hkv, d, rotary_dim, theta, interleaved, max_positions, dtype, table dtype) — the reference's grid
+# (tests/layer/test_rotary_embedding.py:66-75) scaled down, plus partial rotation and a rotary_dim the vector kernel cannot take
+ROPE_CASES = [
+    ("f32_half", 16, 8, 2, 128, 128, 100000., False, 4096, torch.float32, torch.float32),
+    ("f16_interleaved", 9, 8, 1, 128, 128, 500000., True, 8192, torch.float16, torch.float16),
+    ("bf16_partial", 7, 4, 2, 64, 32, 10000., False, 2048, torch.bfloat16, torch.bfloat16),
+    ("bf16_f32table_interleaved_rd24", 5, 4, 4, 32, 24, 10000., True, 512, torch.bfloat16, torch.float32),
+    ("f16_f32table_half", 3, 8, 8, 128, 128, 1000000., False, 4096, torch.float16, torch.float32),
+]
+
+
+def rope_goldens(ca, mem) -> None:
+    """Rotary embedding alone and the ROPE attention module, reference vs oracle, frozen as fixtures."""
+    import hydrainfer.layer.rotary_embedding as ref_rope
+    import hydrainfer.model.model_forward as ref_mf
+
+    for idx, (name, t, hq, hkv, d, rd, theta, inter, max_pos, dtype, table_dtype) in enumerate(ROPE_CASES):
+        g = torch.Generator().manual_seed(500 + idx)
+        q = torch.randn(t, hq, d, generator=g).to(dtype)
+        k = torch.randn(t, hkv, d, generator=g).to(dtype)
+        pos = torch.randint(0, max_pos, (t,), generator=g, dtype=torch.int32)
+        inv_freq = ref_rope.compute_default_inv_freq(rotary_dim=rd, theta=theta)
+        emb = ref_rope.RotaryEmbedding(rotary_dim=rd, max_position_embeddings=max_pos, inv_freq=inv_freq, interleaved=inter)
+        for h in emb.handlers:  # handlers live in a plain list (rotary_embedding.py:139-142): convert each like model.to(dtype) would a registered one
+            h.to(table_dtype)
+        with torch.inference_mode():
+            ref_q, ref_k = emb(q.clone(), k.clone(), pos)
+        table = oracle.rotary_cos_sin_table(rd, max_pos, inv_freq)
+        # the torch handler's cache holds the same numbers as the fused layout: cos part = first rd columns
+        ref_cache = emb.handlers[1].cos_sin_cache.float()
+        n = rd // 2
+        ref_cos = ref_cache[:, :rd:2] if inter else ref_cache[:, :n]
+        ref_sin = ref_cache[:, rd::2] if inter else ref_cache[:, rd:rd + n]
+        tt = table.to(table_dtype)
+        assert torch.equal(tt[:, 0].float(), ref_cos) and torch.equal(tt[:, 1].float(), ref_sin), f"rope {name}: cos/sin table differs"
+        my_q, my_k = oracle.apply_rotary(q, k, pos, tt, rd, inter)
+        assert torch.equal(my_q, ref_q) and torch.equal(my_k, ref_k), f"rope {name}: oracle differs from the reference"
+        np.savez_compressed(GOLDEN / f"rope_{name}.npz", dtype=DTYPE_NAMES[dtype], table_dtype=DTYPE_NAMES[table_dtype],
+                            geometry=np.array([t, hq, hkv, d, rd, max_pos]), theta=theta, interleaved=int(inter),
+                            query=to_np(q), key=to_np(k), positions=pos.numpy(), ref_query=to_np(ref_q), ref_key=to_np(ref_k),
+                            table_checksum=np.array([float(tt.double().sum())]))
+
+    # ---- the ROPE attention module, driven like a decoder layer drives it (identity projections: q/k/v are slices of a fused tensor)
+    name, seq_lens, hq, hkv, d, bs, dtype = "ropeattn_qwen_bf16", [(1, 40), (9, 33), (1, 16)], 28, 4, 128, 16, torch.bfloat16
+    theta, max_pos = 1000000., 256
+    batch = make_batch(seq_lens, hq, hkv, d, bs, dtype=dtype, seed=700, fused_qkv=True)
+    positions = torch.tensor([p for q_len, kv_len in seq_lens for p in range(kv_len - q_len, kv_len)], dtype=torch.int32)
+    qkv = torch.cat([batch.query, batch.key, batch.value], dim=1).contiguous()
+    inv_freq = ref_rope.compute_default_inv_freq(rotary_dim=d, theta=theta)
+    emb = ref_rope.RotaryEmbedding(rotary_dim=d, max_position_embeddings=max_pos, inv_freq=inv_freq, interleaved=False)
+    for h in emb.handlers:
+        h.to(dtype)
+    module = ref_mf.ROPECausalGroupedQueryPageAttention(n_qo_heads=hq, n_kv_heads=hkv, head_dim=d, rotary_emb=emb, qkv_proj=torch.nn.Identity())
+    kc, vc = batch.clone_caches()
+    builder = ca.AttentionParametersBuilder(hq, hkv, d, bs, torch.device("cpu"))
+    for req in batch.requests():
+        builder.add_request(*req)
+    builder.add_kv_cache(mem.KVCache(kc, vc))
+    params = builder.build_attention_parameters()[0]
+    with torch.inference_mode():
+        ref_out = module.forward(qkv.clone(), positions, params)
+    table = oracle.rotary_cos_sin_table(d, max_pos, inv_freq).to(dtype)
+    my_kc, my_vc = batch.clone_caches()
+    meta = oracle.build_metadata(batch.requests(), bs)
+    out, q_rot, k_rot = oracle.rope_attention_layer_forward(
+        batch.query, batch.key, batch.value, positions, table, d, False, my_kc, my_vc, torch.tensor(meta.new_cache_slots, dtype=torch.int32),
+        meta.q_cu_seq_lens, meta.kv_cu_seq_lens, torch.tensor(meta.block_tables, dtype=torch.int32), meta.cu_blocks_lens, hq, hkv, d)
+    assert torch.equal(my_kc, kc) and torch.equal(my_vc, vc), "ROPE attention: oracle caches differ from the reference"
+    assert torch.equal(out, ref_out), "ROPE attention: oracle output differs from the reference"
+    fp32 = oracle.paged_attention_fp32(q_rot, my_kc, my_vc, meta.q_cu_seq_lens, meta.kv_cu_seq_lens, torch.tensor(meta.block_tables, dtype=torch.int32),
+                                       meta.cu_blocks_lens, hq, hkv, d)
+    blocks = torch.tensor(sorted(set(batch.block_tables)), dtype=torch.long)
+    np.savez_compressed(GOLDEN / f"{name}.npz", dtype=DTYPE_NAMES[dtype], seq_lens=np.array(seq_lens, dtype=np.int64),
+                        geometry=np.array([hq, hkv, d, bs, batch.n_blocks, max_pos]), theta=theta, seed=700, qkv=to_np(qkv), positions=positions.numpy(),
+                        key_cache=to_np(batch.key_cache), value_cache=to_np(batch.value_cache), owned_blocks=blocks.numpy(),
+                        ref_key_cache_owned=to_np(kc[blocks]), ref_value_cache_owned=to_np(vc[blocks]), ref_out=to_np(ref_out),
+                        ref_fp32=fp32.numpy(), ref_query_rot=to_np(q_rot),
+                        new_cache_slots=np.array(meta.new_cache_slots), block_tables=np.array(meta.block_tables),
+                        q_cu_seq_lens=np.array(meta.q_cu_seq_lens), cu_blocks_lens=np.array(meta.cu_blocks_lens))
 
 
 def run_reference_layer(ca, mem, batch):
@@ -165,7 +248,9 @@ def main() -> None:
                         results=np.array([",".join(map(str, t[2])) for t in trace]),
                         v2p_table=np.array(table), v2p_vids=np.array(vids), v2p_slots=np.array(ref_slots))
 
-    print("oracle == reference on every case (bit-exact outputs, caches, metadata, allocator, v2p)")
+    rope_goldens(ca, mem)
+
+    print("oracle == reference on every case (bit-exact outputs, caches, metadata, allocator, v2p, rotary, ROPE attention)")
     for name, err in report:
         print(f"  {name:28s} max |reference(dtype) - fp32 recompute| = {err:.3e}")
     total = sum(p.stat().st_size for p in GOLDEN.glob("*.npz"))

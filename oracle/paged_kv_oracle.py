@@ -8,7 +8,8 @@ Parity pin: oracle/make_golden.py imports the REAL reference from /root/referenc
 and checks every function below against it on seeded inputs, then freezes the reference's outputs as fixtures in
 tests/golden/*.npz; tests/test_oracle_golden.py re-checks the oracle against those fixtures wherever the reference is
 absent (the GPU box).  Pinned this way: attention (Torch handler), set_kv_cache / set_image_cache (Python fallbacks),
-BlockAllocator, AttentionParametersBuilder metadata, v2p.  NOT pinned ("parity unpinned"): migrate_blocks — the
+BlockAllocator, AttentionParametersBuilder metadata, v2p, rotary embedding (Torch handler, both table dtypes) and the
+ROPE attention module (model_forward.py).  NOT pinned ("parity unpinned"): migrate_blocks — the
 reference implementation is CUDA-only C++ with no test or fixture anywhere in the reference tree; its
 index arithmetic is restated from the source alone.
 
@@ -44,6 +45,57 @@ def set_image_cache(slot_ids: Tensor, image_tokens: Tensor, image_cache: Tensor)
     csrc/kernel/cache_kernels/cache_kernels.cu:17-53."""
     slot_view = image_cache.view(-1, image_cache.shape[-2], image_cache.shape[-1])
     slot_view[slot_ids.long(), :, :] = image_tokens
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Rotary embedding (the step in front of the append, SURVEY §8f-2)
+# ---------------------------------------------------------------------------------------------------------------
+def rotary_cos_sin_table(rotary_dim: int, max_position_embeddings: int, inv_freq: Tensor) -> Tensor:
+    """fp32 [max_positions, 2, rotary_dim/2]: cos then sin of position x inv_freq — the fused handler's cache layout
+    (hydrainfer/layer/rotary_embedding.py:110-115); the torch handler holds the same numbers repeated per pair (:30-41).
+    Cast it to the model dtype to mimic `module.to(dtype)`."""
+    t = torch.arange(max_position_embeddings, dtype=torch.float)
+    freqs = torch.einsum("i,j->ij", t, inv_freq.float())
+    return torch.stack([freqs.cos(), freqs.sin()], dim=1)
+
+
+def apply_rotary(query: Tensor, key: Tensor, positions: Tensor, cos_sin: Tensor, rotary_dim: int, interleaved: bool) -> tuple[Tensor, Tensor]:
+    """TorchRotaryEmbeddingHandler.forward (hydrainfer/layer/rotary_embedding.py:44-83), same result as the CUDA kernel
+    csrc/kernel/position_embedding/rope.cu:9-31: for each pair (x, y) of a head — (2i, 2i+1) when interleaved (:58-70,
+    rotate_every_two :85-93), else (i, i + rotary_dim/2) (:71-81, rotate_half :95-99) —
+        x' = x*cos + (-y)*sin        y' = y*cos + x*sin
+    as separate elementwise torch ops, so a 16-bit table rounds every product and the sum to 16 bits and an fp32 table
+    promotes to fp32 and rounds once in the final `.to(dtype)` (:83).  Dims >= rotary_dim pass through (:51-54, :81-82).
+    Returns new tensors [T, H, d] in the input dtype."""
+    n = rotary_dim // 2
+    cs = cos_sin[positions.long()]                      # [T, 2, n]
+    c, s = cs[:, 0, None, :], cs[:, 1, None, :]         # broadcast over heads
+
+    def rotate(t: Tensor) -> Tensor:
+        rot, rest = t[:, :, :rotary_dim], t[:, :, rotary_dim:]
+        if interleaved:
+            x, y = rot[:, :, 0::2], rot[:, :, 1::2]
+        else:
+            x, y = rot[:, :, :n], rot[:, :, n:]
+        xo = x * c + (-y) * s
+        yo = y * c + x * s
+        out = torch.stack([xo, yo], dim=-1).flatten(start_dim=-2) if interleaved else torch.cat([xo, yo], dim=-1)
+        return torch.cat([out, rest.to(out.dtype)], dim=-1).to(t.dtype)
+
+    return rotate(query), rotate(key)
+
+
+def rope_attention_layer_forward(query: Tensor, key: Tensor, value: Tensor, positions: Tensor, cos_sin: Tensor, rotary_dim: int,
+                                 interleaved: bool, key_cache: Tensor, value_cache: Tensor, new_cache_slots: Tensor, q_cu_seq_lens,
+                                 kv_cu_seq_lens, block_tables: Tensor, cu_blocks_lens, n_qo_heads: int, n_kv_heads: int, head_dim: int):
+    """ROPECausalGroupedQueryPageAttention.forward without projections (hydrainfer/model/model_forward.py:78-83): rotary,
+    then the attention layer (append + attend).  Returns (o [T, Hq*d], rotated query, rotated key)."""
+    q = query.reshape(-1, n_qo_heads, head_dim)
+    k = key.reshape(-1, n_kv_heads, head_dim)
+    q, k = apply_rotary(q, k, positions, cos_sin, rotary_dim, interleaved)
+    out = attention_layer_forward(q, k, value, key_cache, value_cache, new_cache_slots, q_cu_seq_lens, kv_cu_seq_lens, block_tables,
+                                  cu_blocks_lens, n_qo_heads, n_kv_heads, head_dim)
+    return out, q, k
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -15,7 +15,7 @@ def declared_functions() -> list[str]:
 
 def test_header_declares_the_path():
     names = declared_functions()
-    for required in ("hi_set_kv_cache", "hi_set_image_cache", "hi_paged_attention", "hi_migrate_blocks", "hi_ipc_get_handle", "hi_ipc_open_handle"):
+    for required in ("hi_set_kv_cache", "hi_set_image_cache", "hi_rope_append", "hi_paged_attention", "hi_migrate_blocks", "hi_ipc_get_handle", "hi_ipc_open_handle"):
         assert required in names
 
 
@@ -30,7 +30,7 @@ def test_binding_table_matches_header():
 
 
 def test_abi_version_and_error_string():
-    assert _lib.lib.hi_abi_version() == 2
+    assert _lib.lib.hi_abi_version() == 3
     assert isinstance(_lib.lib.hi_last_error(), bytes)
 
 
@@ -38,6 +38,8 @@ def test_struct_layout_matches_header():
     # HiAttnArgs: 4 ptrs + 2 i64 + 4 ptrs + 8 i32 + i64 + i32 + f32 + ptr + i64 + 2 i32 + 4 i32 (natural alignment, no packing)
     assert ctypes.sizeof(_lib.HiAttnArgs) == 4 * 8 + 2 * 8 + 4 * 8 + 8 * 4 + 8 + 4 + 4 + 8 + 8 + 2 * 4 + 4 * 4 + 8 + 8 + 4 + 4
     assert ctypes.sizeof(_lib.HiPoolGeom) == 32
+    # HiRopeArgs: 3 ptrs + 3 i64 + 5 ptrs + i64 + 12 i32
+    assert ctypes.sizeof(_lib.HiRopeArgs) == 3 * 8 + 3 * 8 + 5 * 8 + 8 + 12 * 4
 
 
 def test_argument_validation_needs_no_gpu():
