@@ -5,7 +5,9 @@
 
 Geometries: (a) LLaVA-7B pool [32,2,NB,16,32,128] bf16 (8 MiB/block), (b) Qwen2-VL-7B [28,2,NB,16,4,128] (896 KiB/block),
 (c) image pool [1,1,NB,576,32,128] (4.5 MiB/block).  n_blocks/request in {16, 64, 256, 1024, 4096} where the pool fits.
-Patterns at N>1: disjoint pairs 2i -> 2i+1 (all at once), and fan-out 0 -> {1..N-1} (all receivers pull from rank 0).
+Patterns at N>1: disjoint pairs 2i -> 2i+1 (all at once), fan-out 0 -> {1..N-1} (all receivers pull from rank 0) and, at
+N >= 4, "p2d": ranks [0, N/2) are prefill nodes, ranks [N/2, N) decode nodes, and every decode rank pulls 1/(N/2) of its request
+from EACH prefill rank at once (the disaggregated all-to-all of SURVEY §8d config 5).
 Also times the plain cudaMemcpyPeerAsync of the same payload (the NVLink roofline probe) and, for small requests, the
 reference's per-run memcpy loop restated with hi_peer_copy (block_migration.cpp:222-244) to show the launch-bound regime.
 Bit-exactness of every destination pool is checked against the source pool.
@@ -79,7 +81,8 @@ def main():
             src_bt = torch.randperm(pool_blocks, generator=g)[:n_move].tolist()
             dst_bt = torch.randperm(pool_blocks, generator=g)[:n_move].tolist()
             handle = bm.get_ipc_mem_handle(pool)
-            patterns = ["same_gpu"] if world == 1 else ["pairs", "fanout"]
+            patterns = ["same_gpu"] if world == 1 else ["pairs", "fanout"] + (["p2d"] if world >= 4 and world % 2 == 0 else [])
+            half = world // 2
             handles = [handle]
             if world > 1:
                 handles = [None] * world
@@ -91,13 +94,25 @@ def main():
                     receiver = rank % 2 == 1
                     src_rank = rank - 1 if receiver else rank
                     dst_pool, src_handle = pool if not receiver else torch.zeros_like(pool), handles[src_rank]
-                else:  # fanout
+                elif pattern == "fanout":
                     receiver = rank != 0
                     src_rank = 0
                     dst_pool, src_handle = pool if not receiver else torch.zeros_like(pool), handles[0]
+                else:  # p2d
+                    receiver = rank >= half
+                    src_rank = rank - half  # owner of part 0 (the part that is checked)
+                    dst_pool, src_handle = pool if not receiver else torch.zeros_like(pool), None
+                    part = (n_move + half - 1) // half
 
                 def run():
-                    if receiver:
+                    if not receiver:
+                        return
+                    if pattern == "p2d":
+                        for k in range(half):  # part k comes from prefill rank (k + rank) % half: sources are hit evenly
+                            lo, hi = k * part, min(n_move, (k + 1) * part)
+                            if lo < hi:
+                                bm.migrate_blocks(src_bt[lo:hi], dst_bt[lo:hi], handles[(k + rank) % half], dst_pool, pool_blocks)
+                    else:
                         bm.migrate_blocks(src_bt, dst_bt, src_handle, dst_pool, pool_blocks)
 
                 ms = timed(run)
@@ -112,13 +127,16 @@ def main():
                 if world > 1:
                     # owner sends its moved blocks (first 8 only, to bound time) to each of its receivers for the check
                     chk = min(8, n_move)
-                    if pattern == "pairs":
+                    if pattern == "p2d":
+                        chk = min(chk, part)
+                    if pattern in ("pairs", "p2d"):
+                        to_rank = rank + 1 if pattern == "pairs" else rank + half
                         if receiver:
                             buf = torch.empty_like(pool[:, :, :chk])
                             dist.recv(buf, src=src_rank)
                             ok = bool(torch.equal(dst_pool[:, :, dst_bt[:chk]].view(torch.int16), buf.view(torch.int16)))
-                        elif rank + 1 < world:
-                            dist.send(pool[:, :, src_bt[:chk]].contiguous(), dst=rank + 1)
+                        elif to_rank < world:
+                            dist.send(pool[:, :, src_bt[:chk]].contiguous(), dst=to_rank)
                     else:
                         if rank == 0:
                             blk = pool[:, :, src_bt[:chk]].contiguous()
@@ -131,10 +149,10 @@ def main():
                 okt = torch.tensor([1 if ok else 0], device=dev)
                 if world > 1:
                     dist.all_reduce(okt, op=dist.ReduceOp.MIN)
-                n_recv = 1 if world == 1 else (world // 2 if pattern == "pairs" else world - 1)
+                n_recv = 1 if world == 1 else (world - 1 if pattern == "fanout" else world // 2)
                 line = {"geom": gname, "pattern": pattern, "n_gpus": world, "n_blocks": n_move, "payload_bytes": payload, "ms": ms,
                         "gbs_per_receiver": payload / ms / 1e6, "gbs_aggregate": n_recv * payload / ms / 1e6, "bit_exact": bool(okt.item()),
-                        "run_bytes": bytes_per_block // (geom["n_layers"] * geom["n_tokens"]), "launches": 1,
+                        "run_bytes": bytes_per_block // (geom["n_layers"] * geom["n_tokens"]), "launches": half if pattern == "p2d" else 1,
                         "reference_memcpy_calls": geom["n_layers"] * geom["n_tokens"] * n_move}
                 if rank == 0:
                     print(json.dumps(line), flush=True)
