@@ -27,3 +27,21 @@ def set_image_cache(slot_ids: Tensor, image_tokens: Tensor, image_cache: Tensor)
         slot_ids.data_ptr(), image_tokens.data_ptr(), image_cache.data_ptr(), n_tokens, row,
         image_tokens.stride(0) if n_tokens > 1 else row, _lib.dtype_code(image_tokens.dtype), dev.index or 0,
         _lib.current_stream_ptr(dev)))
+
+
+def get_image_cache(slot_ids: Tensor, image_cache: Tensor) -> Tensor:
+    """image_cache.view(-1, H * d)[slot_ids, :] -> [T, H * d]: the read side of the image-embedding cache, the gather
+    LanguageModelParametersBuilder.add does with advanced indexing (hydrainfer/engine/parameters_builder.py:48-55).
+    Extension of the reference module (it has no such function); bit-exact, one launch."""
+    dev = _lib.require_cuda(slot_ids, image_cache)
+    if image_cache.dim() != 4 or not image_cache.is_contiguous():
+        raise RuntimeError("get_image_cache: image_cache must be contiguous [n_blocks, block_size, n_heads, head_dim]")
+    if slot_ids.dtype != torch.int32 or slot_ids.dim() != 1 or not slot_ids.is_contiguous():
+        raise RuntimeError("get_image_cache: slot_ids must be a contiguous int32 vector")
+    n_tokens = slot_ids.shape[0]
+    row = image_cache.shape[2] * image_cache.shape[3]
+    out = torch.empty((n_tokens, row), dtype=image_cache.dtype, device=dev)
+    _lib.check(_lib.lib.hi_get_image_cache(
+        slot_ids.data_ptr(), image_cache.data_ptr(), out.data_ptr(), n_tokens, row, row,
+        _lib.dtype_code(image_cache.dtype), dev.index or 0, _lib.current_stream_ptr(dev)))
+    return out

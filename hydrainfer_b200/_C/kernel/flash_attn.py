@@ -35,10 +35,18 @@ def mha_varlen_fwd(out: Tensor, q: Tensor, k: Tensor, v: Tensor, cu_seqlens_q: T
     query tokens) and `qk_work_hint` are optional extensions after the reference's 16 positional arguments: the host-side
     plan AttentionParametersBuilder builds next to the metadata.
 
-    Only the configuration the reference's attention layer uses is implemented (causal_attention.py:274-291):
-    no alibi, no softcap, window (-1, 0) == causal, paged KV; anything else raises RuntimeError like TORCH_CHECK."""
-    if block_table_ is None or cu_block_lens is None:
-        raise RuntimeError("mha_varlen_fwd: only the paged-KV form (block_table + cu_block_lens) is implemented")
+    Two forms, as in the reference: paged (block_table + cu_block_lens, window (-1, 0) == causal; the attention layer,
+    causal_attention.py:274-291) and un-paged (block_table None, k/v [T, Hkv, d], window (-1, -1) or (-1, 0); the vision
+    encoders, multihead_attention.py:140-157, 194-211).  No alibi, no softcap, no sliding window: those raise
+    RuntimeError like TORCH_CHECK."""
+    if block_table_ is None:
+        # the vision encoders' form (multihead_attention.py:140-157, 194-211): k/v are plain [T, H, d], window (-1, -1)
+        if alibi_slopes is not None or softcap != 0 or window_size_left != -1 or window_size_right not in (-1, 0):
+            raise RuntimeError("mha_varlen_fwd: alibi / softcap / sliding window are not implemented")
+        return _varlen_fwd(out, q, k, v, cu_seqlens_q, cu_seqlens_k, int(max_seqlen_q), int(max_seqlen_k), float(softmax_scale),
+                           causal=(window_size_right == 0))
+    if cu_block_lens is None:
+        raise RuntimeError("mha_varlen_fwd: a block_table needs cu_block_lens (flattened CSR block table)")
     if alibi_slopes is not None or softcap != 0 or window_size_left != -1 or window_size_right != 0:
         raise RuntimeError("mha_varlen_fwd: alibi / softcap / sliding window are not used by the paged attention layer and are not implemented")
     dev = _lib.require_cuda(out, q, k, v, cu_seqlens_q, cu_seqlens_k, block_table_, cu_block_lens)
@@ -75,6 +83,43 @@ def mha_varlen_fwd(out: Tensor, q: Tensor, k: Tensor, v: Tensor, cu_seqlens_q: T
         work_items=work_items.data_ptr() if work_items is not None else None, qk_work_hint=int(qk_work_hint),
         n_work_items=int(work_items.shape[0]) if work_items is not None else 0, work_tile_tokens=int(work_tile_tokens))
     _lib.check(_lib.lib.hi_paged_attention(args, _lib.current_stream_ptr(dev)))
+
+
+def _varlen_fwd(out: Tensor, q: Tensor, k: Tensor, v: Tensor, cu_seqlens_q: Tensor, cu_seqlens_k: Tensor,
+                max_seqlen_q: int, max_seqlen_k: int, softmax_scale: float, causal: bool) -> None:
+    """Un-paged varlen attention: q/out [Tq, Hq, d], k/v [Tk, Hkv, d] (row strides free), sequence b = rows
+    cu_seqlens[b] .. cu_seqlens[b + 1]; hi_varlen_attention (tcgen05 pair-tile kernel, head_dim % 8 == 0, <= 128)."""
+    dev = _lib.require_cuda(out, q, k, v, cu_seqlens_q, cu_seqlens_k)
+    for name, t in (("q", q), ("k", k), ("v", v), ("out", out)):
+        if t.dim() != 3 or t.stride(-1) != 1 or t.stride(-2) != t.size(-1):
+            raise RuntimeError(f"mha_varlen_fwd: {name} must be [n_tokens, n_heads, head_dim], contiguous over the last two dims")
+    if out.shape != q.shape or k.shape != v.shape or k.shape[-1] != q.shape[-1] or q.shape[1] % k.shape[1] != 0:
+        raise RuntimeError(f"mha_varlen_fwd: shape mismatch q {tuple(q.shape)} out {tuple(out.shape)} k {tuple(k.shape)} v {tuple(v.shape)}")
+    if not (q.dtype == out.dtype == k.dtype == v.dtype):
+        raise RuntimeError("mha_varlen_fwd: dtype mismatch")
+    if q.dtype not in (torch.float16, torch.bfloat16):
+        raise RuntimeError("mha_varlen_fwd: only fp16 and bf16 are supported")  # flash_api.cpp:236
+    for name, t in (("cu_seqlens_q", cu_seqlens_q), ("cu_seqlens_k", cu_seqlens_k)):
+        if t.dtype != torch.int32 or not t.is_contiguous() or t.dim() != 1:
+            raise RuntimeError(f"mha_varlen_fwd: {name} must be a contiguous int32 vector")
+    n_seqs = cu_seqlens_q.shape[0] - 1
+    if cu_seqlens_k.shape[0] != n_seqs + 1:
+        raise RuntimeError("mha_varlen_fwd: cu_seqlens_q and cu_seqlens_k must both have batch + 1 entries")
+    n_q, n_qo_heads, head_dim = q.shape
+    n_k, n_kv_heads, _ = k.shape
+    ws = _workspace(dev, 128)
+
+    def row_stride(t: Tensor) -> int:
+        return t.stride(0) if t.shape[0] > 1 else t.shape[1] * t.shape[2]
+
+    args = _lib.HiVarlenArgs(
+        q=q.data_ptr(), k=k.data_ptr(), v=v.data_ptr(), out=out.data_ptr(),
+        q_row_stride=row_stride(q), k_row_stride=row_stride(k), v_row_stride=row_stride(v), out_row_stride=row_stride(out),
+        cu_seqlens_q=cu_seqlens_q.data_ptr(), cu_seqlens_k=cu_seqlens_k.data_ptr(),
+        n_seqs=n_seqs, n_q_tokens=n_q, n_k_tokens=n_k, max_q_len=max_seqlen_q, max_kv_len=max_seqlen_k,
+        n_qo_heads=n_qo_heads, n_kv_heads=n_kv_heads, head_dim=head_dim, dtype=_lib.dtype_code(q.dtype), causal=int(causal),
+        softmax_scale=softmax_scale, device=dev.index or 0, workspace=ws.data_ptr(), workspace_bytes=ws.numel())
+    _lib.check(_lib.lib.hi_varlen_attention(args, _lib.current_stream_ptr(dev)))
 
 
 def last_launch_count() -> int:

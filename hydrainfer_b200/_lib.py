@@ -48,6 +48,18 @@ class HiRopeArgs(Structure):
     ]
 
 
+class HiVarlenArgs(Structure):
+    _fields_ = [
+        ("q", c_void_p), ("k", c_void_p), ("v", c_void_p), ("out", c_void_p),
+        ("q_row_stride", c_int64), ("k_row_stride", c_int64), ("v_row_stride", c_int64), ("out_row_stride", c_int64),
+        ("cu_seqlens_q", c_void_p), ("cu_seqlens_k", c_void_p),
+        ("n_seqs", c_int32), ("n_q_tokens", c_int32), ("n_k_tokens", c_int32), ("max_q_len", c_int32), ("max_kv_len", c_int32),
+        ("n_qo_heads", c_int32), ("n_kv_heads", c_int32), ("head_dim", c_int32), ("dtype", c_int32), ("causal", c_int32),
+        ("softmax_scale", c_float), ("device", c_int32),
+        ("workspace", c_void_p), ("workspace_bytes", c_int64), ("reserved", c_int64 * 2),
+    ]
+
+
 class HiPoolGeom(Structure):
     _fields_ = [("n_layers", c_int64), ("n_tokens", c_int64), ("n_blocks", c_int64), ("run_bytes", c_int64)]
 
@@ -65,11 +77,14 @@ SIGNATURES = {
     "hi_set_kv_cache": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
                                 c_int, c_int, c_void_p]),
     "hi_set_image_cache": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
+    "hi_get_image_cache": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
     "hi_rope_append": (c_int, [POINTER(HiRopeArgs), c_void_p]),
+    "hi_varlen_attention": (c_int, [POINTER(HiVarlenArgs), c_void_p]),
     "hi_attention_workspace_bytes": (c_int64, [c_int32, c_int32, c_int32, c_int32]),
     "hi_paged_attention": (c_int, [POINTER(HiAttnArgs), c_void_p]),
     "hi_attention_tile_tokens": (c_int32, [c_int32, c_int32]),
     "hi_migrate_blocks": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, HiPoolGeom, HiPoolGeom, c_int, c_void_p]),
+    "hi_migrate_blocks_layers": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, HiPoolGeom, HiPoolGeom, c_int64, c_int64, c_int, c_void_p]),
     "hi_ipc_get_handle": (c_int, [c_void_p, POINTER(c_uint8), POINTER(c_int64), c_int]),
     "hi_ipc_open_handle": (c_int, [POINTER(c_uint8), c_int64, c_int, POINTER(c_void_p)]),
     "hi_ipc_close_all": (c_int, []),

@@ -9,6 +9,7 @@
 static_assert(sizeof(HiAttnArgs) == 192, "HiAttnArgs layout is part of the ABI (ctypes mirror in hydrainfer_b200/_lib.py)");
 static_assert(sizeof(HiPoolGeom) == 32, "HiPoolGeom layout is part of the ABI");
 static_assert(sizeof(HiRopeArgs) == 144, "HiRopeArgs layout is part of the ABI");
+static_assert(sizeof(HiVarlenArgs) == 160, "HiVarlenArgs layout is part of the ABI");
 
 namespace hi {
 
@@ -45,6 +46,7 @@ int launch_attn_decode_tc(const HiAttnArgs& args, cudaStream_t stream);
 bool attn_decode_tc_supported(const HiAttnArgs& args);
 int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream);
 bool attn_pair_supported(const HiAttnArgs& args);
+int launch_varlen_pair(const HiVarlenArgs& args, cudaStream_t stream);
 int64_t simt_workspace_bytes(int head_dim);
 int64_t tc_workspace_bytes();
 
@@ -125,6 +127,26 @@ extern "C" int hi_paged_attention(const HiAttnArgs* p, void* stream_) {
   if (path == HI_ATTN_SIMT) return launch_attn_simt(a, stream);
   set_error("paged_attention: unknown path %d", path);
   return HI_ERR_INVALID_ARGUMENT;
+}
+
+extern "C" int hi_varlen_attention(const HiVarlenArgs* p, void* stream_) {
+  using namespace hi;
+  reset_launch_count();
+  HI_CHECK_ARG(p != nullptr, "varlen_attention: null args");
+  const HiVarlenArgs& a = *p;
+  HI_CHECK_ARG(a.n_seqs >= 0 && a.n_q_tokens >= 0 && a.n_k_tokens >= 0, "varlen_attention: negative extents");
+  if (a.n_seqs == 0 || a.n_q_tokens == 0) return HI_OK;
+  HI_CHECK_ARG(a.q && a.k && a.v && a.out && a.cu_seqlens_q && a.cu_seqlens_k, "varlen_attention: null pointer");
+  HI_CHECK_ARG(a.n_qo_heads > 0 && a.n_kv_heads > 0 && a.n_qo_heads % a.n_kv_heads == 0,
+               "varlen_attention: n_qo_heads %d is not divisible by n_kv_heads %d", a.n_qo_heads, a.n_kv_heads);
+  HI_CHECK_ARG(a.head_dim > 0 && a.max_q_len >= 1 && a.max_kv_len >= 1, "varlen_attention: bad head_dim %d / max lens q=%d kv=%d",
+               a.head_dim, a.max_q_len, a.max_kv_len);
+  HI_CHECK_SUPPORTED(dtype_size(a.dtype) != 0, "varlen_attention: unsupported dtype %d", a.dtype);
+  const int64_t qrow = static_cast<int64_t>(a.n_qo_heads) * a.head_dim, krow = static_cast<int64_t>(a.n_kv_heads) * a.head_dim;
+  HI_CHECK_ARG(a.q_row_stride >= qrow && a.out_row_stride >= qrow && a.k_row_stride >= krow && a.v_row_stride >= krow,
+               "varlen_attention: row stride smaller than n_heads*head_dim");
+  HI_CUDA(cudaSetDevice(a.device));
+  return launch_varlen_pair(a, static_cast<cudaStream_t>(stream_));
 }
 
 extern "C" int hi_event_create(void** event_out) {

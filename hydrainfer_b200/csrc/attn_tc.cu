@@ -434,11 +434,16 @@ static int get_encode_fn(EncodeTiledFn* out) {
 // 3-D map over [rows, heads, 128] 16-bit elements; box = {64 dims, box_heads, box_rows}, 128B swizzle.
 int make_map(CUtensorMap* map, int dtype, const void* base, int64_t rows, int64_t heads, int64_t row_stride_elems,
                     int box_heads, int box_rows) {
+  return make_map_d(map, dtype, base, rows, heads, kHeadDim, row_stride_elems, box_heads, box_rows);
+}
+
+int make_map_d(CUtensorMap* map, int dtype, const void* base, int64_t rows, int64_t heads, int head_dim, int64_t row_stride_elems,
+               int box_heads, int box_rows) {
   EncodeTiledFn encode = nullptr;
   const int rc = get_encode_fn(&encode);
   if (rc != HI_OK) return rc;
-  const cuuint64_t dims[3] = {static_cast<cuuint64_t>(kHeadDim), static_cast<cuuint64_t>(heads), static_cast<cuuint64_t>(rows)};
-  const cuuint64_t strides[2] = {static_cast<cuuint64_t>(kHeadDim) * 2, static_cast<cuuint64_t>(row_stride_elems) * 2};
+  const cuuint64_t dims[3] = {static_cast<cuuint64_t>(head_dim), static_cast<cuuint64_t>(heads), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[2] = {static_cast<cuuint64_t>(head_dim) * 2, static_cast<cuuint64_t>(row_stride_elems) * 2};
   const cuuint32_t box[3] = {64u, static_cast<cuuint32_t>(box_heads), static_cast<cuuint32_t>(box_rows)};
   const cuuint32_t estr[3] = {1u, 1u, 1u};
   const CUresult res = encode(map, dtype == HI_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,

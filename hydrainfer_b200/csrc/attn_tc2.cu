@@ -75,6 +75,16 @@ struct P2Args {
   int max_pairs;     // without a host plan: pair slots per sequence, ceil(max_q_len / (2 tq))
   int debug;  // timing experiments only (HI_PAIR_DEBUG): bit 0 = softmax warps skip their math, bit 1 = no MMA is issued,
               // bit 2 = K/V tiles are not loaded (barriers only)
+  // ---- un-paged varlen mode (template parameter VL; hi_varlen_attention) --------------------------------------------------
+  // K and V are plain [n_k_tokens, n_kv_heads, head_dim] tensors: key j of sequence b is row kv_cu[b] + j, a "page" is one
+  // 64-key step, block_tables / cu_blocks are unused.  head_dim may be any multiple of 8 up to 128: the tensor maps carry the
+  // real head_dim, TMA zero-fills the dims beyond it, Q.K^T walks ceil(head_dim / 16) k-steps and P.V produces
+  // round_up(head_dim, 16) columns.
+  int head_dim;
+  int causal;        // 0: every key of the sequence is visible to every query row (vision encoders)
+  int n_halves;      // 64-dim halves of a row that exist: 1 (head_dim <= 64) or 2
+  int n_kk;          // 16-dim k-steps of Q.K^T
+  uint32_t idesc_pv; // instruction descriptor of P.V with N = round_up(head_dim, 16)
 };
 
 template <int NK, int NV>
@@ -115,6 +125,7 @@ struct P2Item {
   int blk0, n_pages;
 };
 
+template <bool VL = false>
 __device__ __forceinline__ void p2_decode_item(const P2Args& a, int k, P2Item& it) {
   int pair;
   if (a.work_items != nullptr) {
@@ -133,8 +144,13 @@ __device__ __forceinline__ void p2_decode_item(const P2Args& a, int k, P2Item& i
   it.q_start = __ldg(a.q_cu + it.b);
   it.q_len = __ldg(a.q_cu + it.b + 1) - it.q_start;
   it.kv_len = __ldg(a.kv_cu + it.b + 1) - __ldg(a.kv_cu + it.b);
-  it.blk0 = __ldg(a.cu_blocks + it.b);
-  it.n_pages = __ldg(a.cu_blocks + it.b + 1) - it.blk0;
+  if constexpr (VL) {
+    it.blk0 = __ldg(a.kv_cu + it.b);  // first K/V row of the sequence
+    it.n_pages = (it.kv_len + a.block_size - 1) / a.block_size;
+  } else {
+    it.blk0 = __ldg(a.cu_blocks + it.b);
+    it.n_pages = __ldg(a.cu_blocks + it.b + 1) - it.blk0;
+  }
   const int pair_tokens = 2 * a.tq;
   if (pair < 0) pair += (it.q_len + pair_tokens - 1) / pair_tokens;  // n_pairs - 1 - slot
   it.i0 = pair * pair_tokens;
@@ -146,7 +162,7 @@ __device__ __forceinline__ void p2_decode_item(const P2Args& a, int k, P2Item& i
       it.nt[t] = 0;
     } else {
       const int i_last = min(it.q_len, first + a.tq) - 1;
-      const int kv_end = i_last + (it.kv_len - it.q_len) + 1;  // keys [0, kv_end) are visible to the tile
+      const int kv_end = (VL && !a.causal) ? it.kv_len : i_last + (it.kv_len - it.q_len) + 1;  // keys [0, kv_end) are visible to the tile
       const int n_vis = (kv_end + kP2TileN - 1) / kP2TileN;
       it.nt[t] = max(0, min(n_vis - it.j_begin, a.tiles_per_split));
     }
@@ -181,7 +197,7 @@ static __device__ unsigned int g_pair_trace_n[kTraceRoles];
 #endif
 
 // PF = how many of every 4 (pairs of) exponentials run on the FMA pipes (exp2_poly2) instead of MUFU.EX2.
-template <typename T, int NK, int NV, int PF>
+template <typename T, int NK, int NV, int PF, bool VL = false>
 __global__ void __launch_bounds__(kP2Threads, 1)
 paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                        const __grid_constant__ CUtensorMap tm_v, const P2Args a) {
@@ -264,6 +280,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       const bool is_k = warp == 8;
       const CUtensorMap* tm = is_k ? &tm_k : &tm_v;
       const uint32_t page_half_bytes = static_cast<uint32_t>(a.block_size) * 128u;
+      const uint32_t n_halves = VL ? static_cast<uint32_t>(a.n_halves) : 2u;
       const int b_full = is_k ? L::bKFull : L::bVFull;
       const int b_empty = is_k ? L::bKEmpty : L::bVEmpty;
       const uint32_t ring = smem_base + (is_k ? L::kK : L::kV);
@@ -287,7 +304,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         ++n_it;
         if (k >= a.n_items) break;
         P2Item it;
-        p2_decode_item(a, k, it);
+        p2_decode_item<VL>(a, k, it);
         if (it.n_all == 0) continue;
         trace(1, n_it, it.n_all);
         if (is_k) {
@@ -298,9 +315,9 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
               trace(2, n_it, t);
               if (ptx::elect_one()) {
                 const uint32_t dst = smem_base + L::kQ + t * kP2QTile;
-                ptx::mbar_arrive_expect_tx(bar(L::bQFull + t), 2u * static_cast<uint32_t>(a.group * a.tq) * 128u);
+                ptx::mbar_arrive_expect_tx(bar(L::bQFull + t), n_halves * static_cast<uint32_t>(a.group * a.tq) * 128u);
                 ptx::tma_load_3d(dst, &tm_q, bar(L::bQFull + t), 0, it.kvh * a.group, it.q_start + it.i0 + t * a.tq);
-                ptx::tma_load_3d(dst + kP2QHalf, &tm_q, bar(L::bQFull + t), 64, it.kvh * a.group, it.q_start + it.i0 + t * a.tq);
+                if (n_halves == 2u) ptx::tma_load_3d(dst + kP2QHalf, &tm_q, bar(L::bQFull + t), 64, it.kvh * a.group, it.q_start + it.i0 + t * a.tq);
               }
               __syncwarp();
               ++n_q[t];
@@ -311,6 +328,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         auto pages_of = [&](int j, int& n_valid) -> int {
           const int page0 = (it.j_begin + j) * pages_per_tile;
           n_valid = (a.debug & 4) ? 0 : max(0, min(pages_per_tile, it.n_pages - page0));
+          if constexpr (VL) return 0;
           return (j < it.n_all && lane < n_valid) ? __ldg(a.block_tables + it.blk0 + page0 + lane) : 0;
         };
         int n_valid_next = 0;
@@ -319,7 +337,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
           const int n_valid = n_valid_next;
           const int blk_lane = blk_next;
           blk_next = pages_of(j + 1, n_valid_next);
-          const uint32_t tx = static_cast<uint32_t>(n_valid) * 2u * page_half_bytes;
+          const uint32_t tx = static_cast<uint32_t>(n_valid) * n_halves * page_half_bytes;
           const int st = g & 3;
           const int kv0 = (it.j_begin + j) * kP2TileN;
           const bool tail = !is_k && (kv0 + kP2TileN > it.kv_len);  // at most one such step per item
@@ -330,10 +348,11 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
           if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(full_bar, tx);
           __syncwarp();
           for (int p = 0; p < n_valid; ++p, dst += page_half_bytes) {
-            const int slot0 = __shfl_sync(0xffffffffu, blk_lane, p) * a.block_size;
+            const int slot0 = VL ? it.blk0 + ((it.j_begin + j) * pages_per_tile + p) * a.block_size
+                                 : __shfl_sync(0xffffffffu, blk_lane, p) * a.block_size;
             if (ptx::elect_one()) {
               ptx::tma_load_3d(dst, tm, full_bar, 0, it.kvh, slot0);
-              ptx::tma_load_3d(dst + kP2Half, tm, full_bar, 64, it.kvh, slot0);
+              if (n_halves == 2u) ptx::tma_load_3d(dst + kP2Half, tm, full_bar, 64, it.kvh, slot0);
             }
             __syncwarp();
           }
@@ -364,7 +383,8 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       // ---- MMA warp of tile t: the warp stays converged (every lane polls the barriers), one elected lane issues ------------
       const int t = warp - 9;
       constexpr uint32_t idesc_qk = ptx::make_idesc_f16(kBf16, false, false, kP2TileM, kP2TileN);
-      constexpr uint32_t idesc_pv = ptx::make_idesc_f16(kBf16, false, true, kP2TileM, kP2D);
+      const uint32_t idesc_pv = VL ? a.idesc_pv : ptx::make_idesc_f16(kBf16, false, true, kP2TileM, kP2D);
+      const int n_kk = VL ? a.n_kk : 8;
       // Descriptors of the operand bases, built once; stages and k-steps only add to the 14-bit start-address field.
       const uint64_t desc_q = ptx::make_smem_desc_sw128(smem_base + L::kQ + t * kP2QTile, 16, 1024);
       const uint64_t desc_k = ptx::make_smem_desc_sw128(smem_base + L::kK, 16, 1024);
@@ -378,6 +398,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         if (!no_mma) {
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {  // 2 halves x 4 k-steps of 16 dims; K-major operands, 8-row groups 1024 B apart
+            if (VL && kk >= n_kk) break;
             ptx::mma_f16_ss(tmem_s, desc_q + static_cast<uint64_t>(((kk >> 2) * kP2QHalf + (kk & 3) * 32) >> 4),
                             dk + static_cast<uint64_t>(((kk >> 2) * kP2Half + (kk & 3) * 32) >> 4), idesc_qk, kk > 0);
           }
@@ -402,7 +423,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         const int k = next_item(n_it++, true);
         if (k >= a.n_items) break;
         P2Item it;
-        p2_decode_item(a, k, it);
+        p2_decode_item<VL>(a, k, it);
         if (it.n_all == 0) continue;
         const int n_t = t ? it.nt[1] : it.nt[0];
         const int n_all = it.n_all;
@@ -473,14 +494,14 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       const int k = next_item(n_it++, false);
       if (k >= a.n_items) break;
       P2Item it;
-      p2_decode_item(a, k, it);
+      p2_decode_item<VL>(a, k, it);
       const int n_mine = t ? it.nt[1] : it.nt[0];
       if (n_mine == 0) continue;
       trace(1, n_it, n_mine);
       const int first = it.i0 + t * a.tq;
       const int i = first + tok;                       // query position within the sequence
       const bool row_valid = (tok < a.tq) && (i < it.q_len);
-      const int lim = i + (it.kv_len - it.q_len);      // last visible key index of this row
+      const int lim = (VL && !a.causal) ? it.kv_len - 1 : i + (it.kv_len - it.q_len);  // last visible key index of this row
       float m_used = 0.f;                              // exponent reference (scaled log2 domain)
       float l = 0.f;
       // Rows past the tile's valid (token, head) pairs are padding; a warp that owns only padding rows skips the math.
@@ -573,7 +594,8 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       trace(5, n_it, 0);
       const float inv_l = 1.f / l;
       const int head = it.kvh * a.group + g;
-      T* orow = static_cast<T*>(a.out) + static_cast<int64_t>(it.q_start + i) * a.out_row_stride + head * kP2D;
+      const int d_out = VL ? a.head_dim : kP2D;
+      T* orow = static_cast<T*>(a.out) + static_cast<int64_t>(it.q_start + i) * a.out_row_stride + head * d_out;
       const int64_t pidx = (static_cast<int64_t>(it.q_start + i) * a.n_qo_heads + head) * a.n_splits + it.sp;
       if (a.n_splits > 1 && row_valid) {
         a.part_ml[pidx * 2 + 0] = m_used;
@@ -582,7 +604,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
-        if (warp_active) {
+        if (warp_active && c * 32 < d_out) {
           ptx::tmem_ld_x32(tmem_o + c * 32, v);
           ptx::tmem_wait_ld();
         }
@@ -599,6 +621,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
           } else {
 #pragma unroll
             for (int e = 0; e < 32; e += 8) {
+              if (VL && c * 32 + e >= d_out) break;
               uint4 w;
               w.x = pack2<T>(__uint_as_float(v[e + 0]) * inv_l, __uint_as_float(v[e + 1]) * inv_l);
               w.y = pack2<T>(__uint_as_float(v[e + 2]) * inv_l, __uint_as_float(v[e + 3]) * inv_l);
@@ -637,24 +660,24 @@ bool attn_pair_supported(const HiAttnArgs& args) {
          args.n_blocks > 0;
 }
 
-template <typename T, int PF>
-static int launch_pair_t(const HiAttnArgs& args, const P2Args& a, const CUtensorMap& mq, const CUtensorMap& mk,
+template <typename T, int PF, bool VL = false>
+static int launch_pair_t(int device, const P2Args& a, const CUtensorMap& mq, const CUtensorMap& mk,
                          const CUtensorMap& mv, cudaStream_t stream) {
   constexpr int NK = 4, NV = 4;  // 4 + 4 steps of 64 keys (16 KiB each) + 64 KiB of Q = 192 KiB
   using L = P2Smem<NK, NV>;
   static bool configured = false;
   if (!configured) {
-    HI_CUDA(cudaFuncSetAttribute(paged_attn_pair_kernel<T, NK, NV, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamicBytes));
+    HI_CUDA(cudaFuncSetAttribute(paged_attn_pair_kernel<T, NK, NV, PF, VL>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamicBytes));
     configured = true;
   }
   // persistent: one CTA per SM walks the items with a stride of the grid size
   static int n_sms = 0;
-  if (n_sms == 0) HI_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, args.device));
+  if (n_sms == 0) HI_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device));
   int ctas = a.n_items < n_sms ? a.n_items : n_sms;
   if (const char* env = getenv("HI_PAIR_CTAS")) ctas = atoi(env) > 0 ? atoi(env) : ctas;  // tuning / test override
   const dim3 grid(ctas, 1, 1);
   timing_mark_start(stream);
-  paged_attn_pair_kernel<T, NK, NV, PF><<<grid, kP2Threads, L::kDynamicBytes, stream>>>(mq, mk, mv, a);
+  paged_attn_pair_kernel<T, NK, NV, PF, VL><<<grid, kP2Threads, L::kDynamicBytes, stream>>>(mq, mk, mv, a);
   timing_mark_stop(stream);
   note_launch();
   HI_CUDA(cudaGetLastError());
@@ -742,13 +765,13 @@ int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
   int poly = 0;  // exponentials per 4 moved from MUFU to the FMA pipes (measured: no gain while the softmax warps have idle issue slots)
   if (const char* env = getenv("HI_PAIR_POLY")) poly = atoi(env);  // tuning override
   if (args.dtype == HI_BF16) {
-    rc = poly <= 0 ? launch_pair_t<__nv_bfloat16, 0>(args, a, mq, mk, mv, stream)
-       : poly == 1 ? launch_pair_t<__nv_bfloat16, 1>(args, a, mq, mk, mv, stream)
-                   : launch_pair_t<__nv_bfloat16, 2>(args, a, mq, mk, mv, stream);
+    rc = poly <= 0 ? launch_pair_t<__nv_bfloat16, 0>(args.device, a, mq, mk, mv, stream)
+       : poly == 1 ? launch_pair_t<__nv_bfloat16, 1>(args.device, a, mq, mk, mv, stream)
+                   : launch_pair_t<__nv_bfloat16, 2>(args.device, a, mq, mk, mv, stream);
   } else {
-    rc = poly <= 0 ? launch_pair_t<__half, 0>(args, a, mq, mk, mv, stream)
-       : poly == 1 ? launch_pair_t<__half, 1>(args, a, mq, mk, mv, stream)
-                   : launch_pair_t<__half, 2>(args, a, mq, mk, mv, stream);
+    rc = poly <= 0 ? launch_pair_t<__half, 0>(args.device, a, mq, mk, mv, stream)
+       : poly == 1 ? launch_pair_t<__half, 1>(args.device, a, mq, mk, mv, stream)
+                   : launch_pair_t<__half, 2>(args.device, a, mq, mk, mv, stream);
   }
   if (rc != HI_OK || a.n_splits == 1) return rc;
 
@@ -765,6 +788,62 @@ int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
   m.part_o = a.part_o;
   m.part_ml = a.part_ml;
   return launch_merge_partials(m, args.dtype, kP2D, stream);
+}
+
+// ---- un-paged varlen attention (hi_varlen_attention): the vision-encoder form of mha_varlen_fwd ------------------------------
+bool varlen_pair_supported(const HiVarlenArgs& v) {
+  const int group = v.n_kv_heads > 0 ? v.n_qo_heads / v.n_kv_heads : 0;
+  return (v.dtype == HI_F16 || v.dtype == HI_BF16) && v.head_dim >= 8 && v.head_dim <= kP2D && (v.head_dim % 8) == 0 &&
+         group >= 1 && group <= kP2TileM && (v.q_row_stride % 8) == 0 && (v.k_row_stride % 8) == 0 &&
+         (v.v_row_stride % 8) == 0 && (v.out_row_stride % 8) == 0 && aligned_to(v.q, 16) && aligned_to(v.k, 16) &&
+         aligned_to(v.v, 16) && aligned_to(v.out, 16);
+}
+
+int launch_varlen_pair(const HiVarlenArgs& v, cudaStream_t stream) {
+  if (!varlen_pair_supported(v)) {
+    set_error("varlen_attention: needs fp16/bf16, head_dim a multiple of 8 up to 128 and 16-byte aligned rows (got dtype %d head_dim %d)", v.dtype, v.head_dim);
+    return HI_ERR_UNSUPPORTED;
+  }
+  P2Args a{};
+  a.out = v.out;
+  a.out_row_stride = v.out_row_stride;
+  a.q_cu = v.cu_seqlens_q;
+  a.kv_cu = v.cu_seqlens_k;
+  a.n_qo_heads = v.n_qo_heads;
+  a.n_kv_heads = v.n_kv_heads;
+  a.group = v.n_qo_heads / v.n_kv_heads;
+  a.block_size = kP2TileN;  // a "page" is one 64-key step of consecutive rows
+  a.tq = kP2TileM / a.group;
+  a.scale_log2 = v.softmax_scale * 1.4426950408889634f;
+  a.head_dim = v.head_dim;
+  a.causal = v.causal ? 1 : 0;
+  a.n_halves = v.head_dim > 64 ? 2 : 1;
+  a.n_kk = (v.head_dim + 15) / 16;
+  a.idesc_pv = ptx::make_idesc_f16(v.dtype == HI_BF16, false, true, kP2TileM, a.n_kk * 16);
+  a.n_splits = 1;  // sequences of a vision batch are plentiful and short: no split-KV
+  a.tiles_per_split = (v.max_kv_len + kP2TileN - 1) / kP2TileN;
+  a.max_pairs = (v.max_q_len + 2 * a.tq - 1) / (2 * a.tq);
+  const int64_t n_items = static_cast<int64_t>(a.max_pairs) * v.n_kv_heads * v.n_seqs;
+  if (n_items > 0x7fffffff) {
+    set_error("varlen_attention: %lld work items exceed the int32 range", (long long)n_items);
+    return HI_ERR_INVALID_ARGUMENT;
+  }
+  a.n_items = static_cast<int>(n_items);
+  a.work_counter = nullptr;
+  if (v.workspace != nullptr && v.workspace_bytes >= 512) {
+    a.work_counter = reinterpret_cast<unsigned int*>(static_cast<char*>(v.workspace) + ((v.workspace_bytes - 256) & ~int64_t(255)));
+    HI_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned int), stream));
+  }
+  CUtensorMap mq, mk, mv;
+  int rc = make_map_d(&mq, v.dtype, v.q, v.n_q_tokens, v.n_qo_heads, v.head_dim, v.q_row_stride, a.group, a.tq);
+  if (rc != HI_OK) return rc;
+  rc = make_map_d(&mk, v.dtype, v.k, v.n_k_tokens, v.n_kv_heads, v.head_dim, v.k_row_stride, 1, kP2TileN);
+  if (rc != HI_OK) return rc;
+  rc = make_map_d(&mv, v.dtype, v.v, v.n_k_tokens, v.n_kv_heads, v.head_dim, v.v_row_stride, 1, kP2TileN);
+  if (rc != HI_OK) return rc;
+  if (const char* env = getenv("HI_PAIR_DEBUG")) a.debug = atoi(env);
+  return v.dtype == HI_BF16 ? launch_pair_t<__nv_bfloat16, 0, true>(v.device, a, mq, mk, mv, stream)
+                            : launch_pair_t<__half, 0, true>(v.device, a, mq, mk, mv, stream);
 }
 
 }  // namespace hi

@@ -23,6 +23,7 @@ struct MigrateArgs {
   int64_t run_bytes;       // contiguous bytes of one (plane, block)
   int64_t src_plane_bytes; // src n_blocks * run_bytes
   int64_t dst_plane_bytes;
+  int64_t plane_begin;     // first (layer, kv) plane moved by this launch
   int64_t pieces_per_run;  // run_bytes / kPieceBytes (rounded up)
   int64_t total_pieces;
 };
@@ -38,8 +39,9 @@ __global__ void __launch_bounds__(kMigrateThreads) migrate_gather_kernel(const M
   for (int64_t piece = blockIdx.x; piece < a.total_pieces; piece += gridDim.x) {
     const int64_t run = piece / a.pieces_per_run;
     const int64_t off = (piece - run * a.pieces_per_run) * kPieceBytes;
-    const int64_t plane = run / a.n;
-    const int64_t i = run - plane * a.n;
+    const int64_t plane_rel = run / a.n;
+    const int64_t i = run - plane_rel * a.n;
+    const int64_t plane = a.plane_begin + plane_rel;
     const int64_t sb = __ldg(a.src_blocks + i);
     const int64_t db = __ldg(a.dst_blocks + i);
     const char* __restrict__ src = a.src_pool + plane * a.src_plane_bytes + sb * a.run_bytes + off;
@@ -73,10 +75,19 @@ static std::vector<IpcEntry> g_ipc_entries;
 
 extern "C" int hi_migrate_blocks(const int32_t* src_blocks, const int32_t* dst_blocks, int64_t n, const void* src_pool,
                                  void* dst_pool, HiPoolGeom src, HiPoolGeom dst, int device, void* stream) {
+  return hi_migrate_blocks_layers(src_blocks, dst_blocks, n, src_pool, dst_pool, src, dst, 0, src.n_layers, device, stream);
+}
+
+extern "C" int hi_migrate_blocks_layers(const int32_t* src_blocks, const int32_t* dst_blocks, int64_t n, const void* src_pool,
+                                        void* dst_pool, HiPoolGeom src, HiPoolGeom dst, int64_t layer_begin, int64_t layer_end,
+                                        int device, void* stream) {
   using namespace hi;
   reset_launch_count();
   HI_CHECK_ARG(n >= 0, "migrate_blocks: negative block count");
-  if (n == 0) return HI_OK;
+  HI_CHECK_ARG(layer_begin >= 0 && layer_begin <= layer_end && layer_end <= src.n_layers,
+               "migrate_blocks: layer range [%lld, %lld) outside the pool's %lld layers", (long long)layer_begin,
+               (long long)layer_end, (long long)src.n_layers);
+  if (n == 0 || layer_begin == layer_end) return HI_OK;
   HI_CHECK_ARG(src_blocks && dst_blocks && src_pool && dst_pool, "migrate_blocks: null pointer");
   HI_CHECK_ARG(src.n_layers == dst.n_layers && src.n_tokens == dst.n_tokens && src.run_bytes == dst.run_bytes,
                "migrate_blocks: pools differ in more than n_blocks (layers %lld/%lld, tokens %lld/%lld, run bytes %lld/%lld)",
@@ -93,7 +104,8 @@ extern "C" int hi_migrate_blocks(const int32_t* src_blocks, const int32_t* dst_b
   a.src_pool = static_cast<const char*>(src_pool);
   a.dst_pool = static_cast<char*>(dst_pool);
   a.n = n;
-  a.planes = src.n_layers * src.n_tokens;
+  a.planes = (layer_end - layer_begin) * src.n_tokens;
+  a.plane_begin = layer_begin * src.n_tokens;
   a.run_bytes = src.run_bytes;
   a.src_plane_bytes = src.n_blocks * src.run_bytes;
   a.dst_plane_bytes = dst.n_blocks * dst.run_bytes;

@@ -33,6 +33,18 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(ScatterArgs a) {
   for (int i = threadIdx.x; i < n_vec; i += blockDim.x) dst[i] = src[i];
 }
 
+// The inverse: out[token] = cache[slot_ids[token]] (image_token_cache[slot_ids, :], parameters_builder.py:48-55).
+template <typename Vec>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const int32_t* __restrict__ slot_ids, const char* __restrict__ cache,
+                                                          char* __restrict__ out, int64_t out_row_stride_bytes, int64_t row_bytes) {
+  const int64_t token = blockIdx.x;
+  const int64_t slot = slot_ids[token];
+  const Vec* __restrict__ src = reinterpret_cast<const Vec*>(cache + slot * row_bytes);
+  Vec* __restrict__ dst = reinterpret_cast<Vec*>(out + token * out_row_stride_bytes);
+  const int n_vec = static_cast<int>(row_bytes / sizeof(Vec));
+  for (int i = threadIdx.x; i < n_vec; i += blockDim.x) dst[i] = src[i];
+}
+
 static int launch_scatter(const ScatterArgs& a, int n_tensors, int64_t n_tokens, int device, cudaStream_t stream) {
   if (n_tokens == 0) return HI_OK;
   HI_CUDA(cudaSetDevice(device));
@@ -106,4 +118,42 @@ extern "C" int hi_set_image_cache(const int32_t* slot_ids, const void* image_tok
   a.src_row_stride_bytes[0] = a.src_row_stride_bytes[1] = token_row_stride * es;
   a.row_bytes = row_elems * es;
   return launch_scatter(a, 1, n_tokens, device, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int hi_get_image_cache(const int32_t* slot_ids, const void* image_cache, void* out, int64_t n_tokens,
+                                  int64_t row_elems, int64_t out_row_stride, int dtype, int device, void* stream_) {
+  using namespace hi;
+  reset_launch_count();
+  const int es = dtype_size(dtype);
+  HI_CHECK_SUPPORTED(es != 0, "get_image_cache: unsupported dtype %d", dtype);
+  HI_CHECK_ARG(n_tokens >= 0 && row_elems > 0, "get_image_cache: bad extents");
+  HI_CHECK_ARG(n_tokens == 0 || (slot_ids && image_cache && out), "get_image_cache: null pointer");
+  HI_CHECK_ARG(out_row_stride >= row_elems, "get_image_cache: row stride smaller than the row");
+  if (n_tokens == 0) return HI_OK;
+  HI_CUDA(cudaSetDevice(device));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int64_t row_bytes = row_elems * es, stride_bytes = out_row_stride * es;
+  const uintptr_t bits = static_cast<uintptr_t>(row_bytes) | static_cast<uintptr_t>(stride_bytes) |
+                         reinterpret_cast<uintptr_t>(image_cache) | reinterpret_cast<uintptr_t>(out);
+  const char* src = static_cast<const char*>(image_cache);
+  char* dst = static_cast<char*>(out);
+  const unsigned grid = static_cast<unsigned>(n_tokens);
+  auto threads_for = [&](size_t vec) {
+    const int64_t n = row_bytes / static_cast<int64_t>(vec);
+    int t = static_cast<int>(n < 256 ? n : 256);
+    t = (t + 31) / 32 * 32;
+    return t < 32 ? 32 : t;
+  };
+  if (bits % 16 == 0) {
+    gather_rows_kernel<uint4><<<grid, threads_for(16), 0, stream>>>(slot_ids, src, dst, stride_bytes, row_bytes);
+  } else if (bits % 8 == 0) {
+    gather_rows_kernel<uint2><<<grid, threads_for(8), 0, stream>>>(slot_ids, src, dst, stride_bytes, row_bytes);
+  } else if (bits % 4 == 0) {
+    gather_rows_kernel<uint32_t><<<grid, threads_for(4), 0, stream>>>(slot_ids, src, dst, stride_bytes, row_bytes);
+  } else {
+    gather_rows_kernel<uint16_t><<<grid, threads_for(2), 0, stream>>>(slot_ids, src, dst, stride_bytes, row_bytes);
+  }
+  note_launch();
+  HI_CUDA(cudaGetLastError());
+  return HI_OK;
 }

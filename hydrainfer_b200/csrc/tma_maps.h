@@ -12,6 +12,11 @@ namespace hi {
 int make_map(CUtensorMap* map, int dtype, const void* base, int64_t rows, int64_t heads, int64_t row_stride_elems,
              int box_heads, int box_rows);
 
+// Same for rows of `head_dim` (a multiple of 8, <= 128) elements per head: the box is still 64 dims wide and TMA zero-fills
+// whatever lies beyond head_dim.
+int make_map_d(CUtensorMap* map, int dtype, const void* base, int64_t rows, int64_t heads, int head_dim, int64_t row_stride_elems,
+               int box_heads, int box_rows);
+
 // Cached map of a paged pool [n_slots, heads, 128]; box = one page of one head and one 64-dim half.
 int pool_map(CUtensorMap* out, int dtype, const void* base, int64_t n_slots, int heads, int block_size);
 

@@ -48,6 +48,39 @@ class IPCHandleMemoryBackend(CommunicationBackend):
             )
 
 
+    def migrate_layers(self, src_virtual_cache: VirtualTokenCache, dst_virtual_cache: VirtualTokenCache, layer_begin: int, layer_end: int,
+                       wait_event: "torch.cuda.Event | None" = None) -> "torch.cuda.Event":
+        """Layer-pipelined pull (extension): moves layers [layer_begin, layer_end) of the request on the migrate
+        stream, after `wait_event` (recorded by the producer once those layers' KV exists), and returns an event that
+        completes when they have landed — the caller releases the source pages / starts decode on it instead of the
+        reference's end-of-step stream synchronize."""
+        assert src_virtual_cache.memory_handle is not None, "the source virtual cache carries no IPC handle"
+        with torch.cuda.stream(self.migrate_stream):
+            if wait_event is not None:
+                self.migrate_stream.wait_event(wait_event)
+            block_migration.migrate_blocks_layers(
+                src_virtual_cache.block_table, dst_virtual_cache.block_table, src_virtual_cache.memory_handle, self.cache,
+                src_virtual_cache.n_blocks_of_cache_manager, layer_begin, layer_end)
+            done = torch.cuda.Event()
+            done.record(self.migrate_stream)
+        return done
+
+    def push_blocks(self, src_virtual_cache: VirtualTokenCache, dst_virtual_cache: VirtualTokenCache, layer_begin: int = 0, layer_end: int = -1,
+                    wait_event: "torch.cuda.Event | None" = None) -> "torch.cuda.Event":
+        """Sender-side variant: this process owns the SOURCE pool (self.cache) and writes the pages into the receiver's pool
+        through its IPC mapping (dst_virtual_cache.memory_handle).  Returns the completion event on the migrate stream."""
+        assert dst_virtual_cache.memory_handle is not None, "the destination virtual cache carries no IPC handle"
+        with torch.cuda.stream(self.migrate_stream):
+            if wait_event is not None:
+                self.migrate_stream.wait_event(wait_event)
+            block_migration.push_blocks(
+                src_virtual_cache.block_table, dst_virtual_cache.block_table, self.cache, dst_virtual_cache.memory_handle,
+                dst_virtual_cache.n_blocks_of_cache_manager, layer_begin, layer_end)
+            done = torch.cuda.Event()
+            done.record(self.migrate_stream)
+        return done
+
+
 class NCCLBackend(CommunicationBackend):
     """Packed send/recv over torch.distributed. Works with any backend that supports send/recv on the pool's device
     (nccl on GPUs; the packing logic is covered on CPU tensors with gloo in tests through `pack`/`unpack` hooks)."""

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HI_B200_ABI_VERSION 3
+#define HI_B200_ABI_VERSION 4
 
 typedef enum HiStatus {
   HI_OK = 0,
@@ -71,6 +71,14 @@ int hi_set_image_cache(const int32_t* slot_ids /*[dev] [n_tokens]*/,
                        const void* image_tokens /*[dev]*/, void* image_cache /*[dev]*/,
                        int64_t n_tokens, int64_t row_elems /* n_heads*head_dim */,
                        int64_t token_row_stride /*elements*/,
+                       int dtype, int device, void* stream);
+
+/* Image-embedding read-back — replaces the advanced-indexing gather `image_token_cache[slot_ids, :]` of
+ * LanguageModelParametersBuilder.add (hydrainfer/engine/parameters_builder.py:48-55), the consumer side of
+ * set_image_cache:   out[t, :] = cache[slot_ids[t], :]   (bit-exact copy; cache viewed as [n_slots, row_elems]). */
+int hi_get_image_cache(const int32_t* slot_ids /*[dev] [n_tokens]*/, const void* image_cache /*[dev]*/,
+                       void* out /*[dev] [n_tokens, row_elems], row stride out_row_stride*/,
+                       int64_t n_tokens, int64_t row_elems, int64_t out_row_stride /*elements*/,
                        int dtype, int device, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -174,6 +182,41 @@ int64_t hi_attention_workspace_bytes(int32_t n_tokens, int32_t n_qo_heads, int32
 
 int hi_paged_attention(const HiAttnArgs* args, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Un-paged varlen attention — the OTHER form of mha_varlen_fwd (flash_api.cpp:216-355 with block_table == None):
+ * k and v are plain [n_k_tokens, n_kv_heads, head_dim] tensors and sequence b owns rows cu_seqlens_k[b] .. [b+1].
+ * This is what the vision encoders call: FlashAttentionMutliHeadAttentionHandler2.forward and
+ * QwenFlashAttentionMutliHeadAttentionHandler2.forward (hydrainfer/layer/multihead_attention.py:118-160, 183-211)
+ * pass window (-1, -1) = NOT causal; it computes what TorchMultiHeadAttentionHandler (:48-73) and
+ * QwenTorchMultiHeadAttentionHandler (:241-256) compute:
+ *
+ *       o[i, h] = softmax_j(scale * q[i, h] . k[j, h / group]) @ v[:, h / group]      j over the sequence's keys,
+ *       restricted to j <= i + L_b - q_b when `causal`.
+ *
+ * tcgen05 pair-tile kernel; fp16 / bf16, head_dim any multiple of 8 up to 128 (CLIP 64, SigLIP 72, Qwen2-VL 80, 128).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct HiVarlenArgs {
+  const void* q;             /* [dev] [n_q_tokens, n_qo_heads, head_dim], head stride == head_dim */
+  const void* k;             /* [dev] [n_k_tokens, n_kv_heads, head_dim] */
+  const void* v;             /* [dev] [n_k_tokens, n_kv_heads, head_dim] */
+  void* out;                 /* [dev] [n_q_tokens, n_qo_heads, head_dim]; written in place */
+  int64_t q_row_stride, k_row_stride, v_row_stride, out_row_stride; /* elements between consecutive tokens */
+  const int32_t* cu_seqlens_q; /* [dev] [n_seqs + 1] */
+  const int32_t* cu_seqlens_k; /* [dev] [n_seqs + 1] */
+  int32_t n_seqs, n_q_tokens, n_k_tokens;
+  int32_t max_q_len, max_kv_len;
+  int32_t n_qo_heads, n_kv_heads, head_dim;
+  int32_t dtype;             /* HiDtype */
+  int32_t causal;            /* window_size_right == 0 in the reference's call */
+  float softmax_scale;
+  int32_t device;
+  void* workspace;           /* [dev] optional (>= 512 bytes enables dynamic work distribution) */
+  int64_t workspace_bytes;
+  int64_t reserved[2];
+} HiVarlenArgs;
+
+int hi_varlen_attention(const HiVarlenArgs* args, void* stream);
+
 /* Query tokens per work item of the prefill kernel for this head geometry (0 if that kernel does not cover it). */
 int32_t hi_attention_tile_tokens(int32_t n_qo_heads, int32_t n_kv_heads);
 
@@ -207,6 +250,15 @@ typedef struct HiPoolGeom {
 int hi_migrate_blocks(const int32_t* src_blocks /*[dev] [n]*/, const int32_t* dst_blocks /*[dev] [n]*/,
                       int64_t n, const void* src_pool /*[dev] local or peer-mapped*/, void* dst_pool /*[dev]*/,
                       HiPoolGeom src, HiPoolGeom dst, int device, void* stream);
+
+/* The same copy restricted to layers [layer_begin, layer_end): a sender that has finished layer l of a prefill can ship
+ * that layer's pages while layer l + 1 is still computing (the reference moves whole requests after the last layer,
+ * hydrainfer/engine/executor.py migrate path).  The launch may equally run on the SOURCE GPU with dst_pool peer-mapped
+ * (push): the kernel only needs both pointers to be addressable from `device`. */
+int hi_migrate_blocks_layers(const int32_t* src_blocks /*[dev] [n]*/, const int32_t* dst_blocks /*[dev] [n]*/,
+                             int64_t n, const void* src_pool /*[dev]*/, void* dst_pool /*[dev]*/,
+                             HiPoolGeom src, HiPoolGeom dst, int64_t layer_begin, int64_t layer_end,
+                             int device, void* stream);
 
 /* get_ipc_mem_handle (block_migration.cpp:55-59).  handle_out receives the 64 bytes of
  * cudaIpcMemHandle_t of the ALLOCATION containing ptr; *offset_out the byte offset of ptr inside it

@@ -14,6 +14,8 @@ imports matplotlib / seaborn, which this image lacks; nothing on the path uses t
   TokenCacheBlockManager.v2p                         hydrainfer/memory/token_cache_manger.py:126-133
   RotaryEmbedding -> TorchRotaryEmbeddingHandler     hydrainfer/layer/rotary_embedding.py:19-99, 136-148
   ROPECausalGroupedQueryPageAttention.forward        hydrainfer/model/model_forward.py:66-86
+  MultiHeadAttention -> TorchMultiHeadAttentionHandler          hydrainfer/layer/multihead_attention.py:40-73, 163-176
+  QwenMultiHeadAttention -> QwenTorchMultiHeadAttentionHandler  hydrainfer/layer/multihead_attention.py:235-270
 """
 from __future__ import annotations
 
@@ -73,6 +75,52 @@ ROPE_CASES = [
     ("bf16_f32table_interleaved_rd24", 5, 4, 4, 32, 24, 10000., True, 512, torch.bfloat16, torch.float32),
     ("f16_f32table_half", 3, 8, 8, 128, 128, 1000000., False, 4096, torch.float16, torch.float32),
 ]
+
+
+# (name, batch, seq_len, n_heads, head_dim, dtype) — tests/layer/test_multihead_attention-style equal-length image batches:
+# CLIP-L (d 64, 577 tokens, scaled down), SigLIP (d 72), a d=128 tower; seq lengths straddle the 64-key step and 128-row tile
+MHA_CASES = [
+    ("clip_d64_bf16", 3, 150, 4, 64, torch.bfloat16),
+    ("siglip_d72_fp16", 2, 81, 3, 72, torch.float16),
+    ("d128_bf16", 2, 200, 2, 128, torch.bfloat16),
+]
+# (name, segment lengths, n_heads, head_dim, dtype) — Qwen2-VL vision tower: packed images of different sizes, d = 80
+QWEN_MHA_CASES = [
+    ("qwen_d80_bf16", [64, 196, 100, 1, 130], 4, 80, torch.bfloat16),
+    ("qwen_d80_fp16", [256, 36], 2, 80, torch.float16),
+]
+
+
+def mha_goldens() -> None:
+    """Un-paged vision attention: the reference's two Torch handlers (the CPU end of its handler chains) vs the oracle."""
+    import hydrainfer.layer.multihead_attention as ref_mha
+    for idx, (name, batch, seq_len, heads, d, dtype) in enumerate(MHA_CASES):
+        g = torch.Generator().manual_seed(300 + idx)
+        q, k, v = (torch.randn(batch, seq_len, heads * d, generator=g).to(dtype) for _ in range(3))
+        # the chain's fused handlers have no device check (flash_attn imports here and would be called with CPU tensors), so the
+        # Torch handler — the chain's last link and the reference's own test oracle — is run directly
+        module = ref_mha.TorchMultiHeadAttentionHandler(ref_mha.MultiHeadAttentionConfig(n_heads=heads, head_dim=d))
+        ref = module(q, k, v, ref_mha.MultiHeadAttentionParameters(return_scores=False)).o
+        mine = oracle.multi_head_attention(q, k, v, heads, d)
+        assert torch.equal(mine, ref), f"mha {name}: oracle differs from the reference"
+        cu = list(range(0, (batch + 1) * seq_len, seq_len))
+        fp32 = oracle.varlen_attention_fp32(q.view(-1, heads, d), k.view(-1, heads, d), v.view(-1, heads, d), cu, cu)
+        np.savez_compressed(GOLDEN / f"mha_{name}.npz", dtype=DTYPE_NAMES[dtype], geometry=np.array([batch, seq_len, heads, d]), seed=300 + idx,
+                            query=to_np(q), key=to_np(k), value=to_np(v), ref_out=to_np(ref))
+        print(f"  mha_{name:24s} max |reference(dtype) - fp32 recompute| = {float((ref.float().view(-1, heads * d) - fp32).abs().max()):.3e}")
+    for idx, (name, segs, heads, d, dtype) in enumerate(QWEN_MHA_CASES):
+        g = torch.Generator().manual_seed(400 + idx)
+        total = sum(segs)
+        q, k, v = (torch.randn(total, heads, d, generator=g).to(dtype) for _ in range(3))
+        cu = torch.tensor([0] + list(np.cumsum(segs)), dtype=torch.int32)
+        module = ref_mha.QwenTorchMultiHeadAttentionHandler(ref_mha.MultiHeadAttentionConfig(n_heads=heads, head_dim=d))
+        ref = module(q, k, v, total, cu)
+        mine = oracle.qwen_multi_head_attention(q, k, v, total, cu.tolist(), d)
+        assert torch.equal(mine, ref), f"qwen mha {name}: oracle differs from the reference"
+        fp32 = oracle.varlen_attention_fp32(q, k, v, cu.tolist(), cu.tolist())
+        np.savez_compressed(GOLDEN / f"mha_{name}.npz", dtype=DTYPE_NAMES[dtype], geometry=np.array([len(segs), total, heads, d]), seed=400 + idx,
+                            cu_seqlens=cu.numpy(), query=to_np(q), key=to_np(k), value=to_np(v), ref_out=to_np(ref))
+        print(f"  mha_{name:24s} max |reference(dtype) - fp32 recompute| = {float((ref.float() - fp32).abs().max()):.3e}")
 
 
 def rope_goldens(ca, mem) -> None:
@@ -249,8 +297,9 @@ def main() -> None:
                         v2p_table=np.array(table), v2p_vids=np.array(vids), v2p_slots=np.array(ref_slots))
 
     rope_goldens(ca, mem)
+    mha_goldens()
 
-    print("oracle == reference on every case (bit-exact outputs, caches, metadata, allocator, v2p, rotary, ROPE attention)")
+    print("oracle == reference on every case (bit-exact outputs, caches, metadata, allocator, v2p, rotary, ROPE attention, vision attention)")
     for name, err in report:
         print(f"  {name:28s} max |reference(dtype) - fp32 recompute| = {err:.3e}")
     total = sum(p.stat().st_size for p in GOLDEN.glob("*.npz"))

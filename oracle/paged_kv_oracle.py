@@ -8,8 +8,9 @@ Parity pin: oracle/make_golden.py imports the REAL reference from /root/referenc
 and checks every function below against it on seeded inputs, then freezes the reference's outputs as fixtures in
 tests/golden/*.npz; tests/test_oracle_golden.py re-checks the oracle against those fixtures wherever the reference is
 absent (the GPU box).  Pinned this way: attention (Torch handler), set_kv_cache / set_image_cache (Python fallbacks),
-BlockAllocator, AttentionParametersBuilder metadata, v2p, rotary embedding (Torch handler, both table dtypes) and the
-ROPE attention module (model_forward.py).  NOT pinned ("parity unpinned"): migrate_blocks — the
+BlockAllocator, AttentionParametersBuilder metadata, v2p, rotary embedding (Torch handler, both table dtypes), the
+ROPE attention module (model_forward.py) and the un-paged vision attention (both Torch handlers of
+multihead_attention.py).  NOT pinned ("parity unpinned"): migrate_blocks — the
 reference implementation is CUDA-only C++ with no test or fixture anywhere in the reference tree; its
 index arithmetic is restated from the source alone.
 
@@ -45,6 +46,67 @@ def set_image_cache(slot_ids: Tensor, image_tokens: Tensor, image_cache: Tensor)
     csrc/kernel/cache_kernels/cache_kernels.cu:17-53."""
     slot_view = image_cache.view(-1, image_cache.shape[-2], image_cache.shape[-1])
     slot_view[slot_ids.long(), :, :] = image_tokens
+
+
+def get_image_cache(slot_ids: Tensor, image_cache: Tensor) -> Tensor:
+    """hydrainfer/engine/parameters_builder.py:50-54: image_token_cache.view(-1, n_heads * head_dim)[slot_ids, :]."""
+    return image_cache.view(-1, image_cache.shape[-2] * image_cache.shape[-1])[slot_ids.long(), :]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Un-paged vision attention (SURVEY §8f-4)
+# ---------------------------------------------------------------------------------------------------------------
+def multi_head_attention(query: Tensor, key: Tensor, value: Tensor, n_heads: int, head_dim: int) -> Tensor:
+    """TorchMultiHeadAttentionHandler.forward (hydrainfer/layer/multihead_attention.py:48-73): [batch, seq, hidden] inputs
+    cast to fp32, q scaled by 1/sqrt(d) BEFORE the product (:60), bmm, softmax, bmm, cast back to the input dtype (:66)."""
+    batch_size, seq_len, hidden_size = query.shape
+    dtype = query.dtype
+
+    def heads(t: Tensor) -> Tensor:
+        return t.view(-1, seq_len, n_heads, head_dim).transpose(1, 2).contiguous().to(torch.float).view(-1, seq_len, head_dim)
+
+    q, k, v = heads(query), heads(key), heads(value)
+    q = q * (1. / math.sqrt(head_dim))
+    score = torch.softmax(torch.bmm(q, k.transpose(1, 2)), dim=-1)
+    o = torch.bmm(score, v).view(batch_size, n_heads, seq_len, head_dim).transpose(1, 2).contiguous()
+    return o.view(batch_size, seq_len, hidden_size).to(dtype)
+
+
+def qwen_multi_head_attention(q: Tensor, k: Tensor, v: Tensor, seq_length: int, cu_seqlens, head_dim: int) -> Tensor:
+    """QwenTorchMultiHeadAttentionHandler.forward (hydrainfer/layer/multihead_attention.py:241-256): packed
+    [seq_length, n_heads, head_dim] inputs, block-diagonal additive mask of finfo.min outside each cu_seqlens segment
+    (:243-245), products in the INPUT dtype, softmax in fp32 then cast back (:251), -> [seq_length, hidden]."""
+    mask = torch.full([1, seq_length, seq_length], torch.finfo(q.dtype).min, dtype=q.dtype)
+    for i in range(1, len(cu_seqlens)):
+        mask[..., int(cu_seqlens[i - 1]):int(cu_seqlens[i]), int(cu_seqlens[i - 1]):int(cu_seqlens[i])] = 0
+    qh, kh, vh = q.transpose(0, 1), k.transpose(0, 1), v.transpose(0, 1)
+    w = torch.matmul(qh, kh.transpose(1, 2)) / math.sqrt(head_dim)
+    w = w + mask
+    w = torch.nn.functional.softmax(w, dim=-1, dtype=torch.float32).to(q.dtype)
+    return torch.matmul(w, vh).transpose(0, 1).reshape(seq_length, -1)
+
+
+def varlen_attention_fp32(q: Tensor, k: Tensor, v: Tensor, cu_seqlens_q, cu_seqlens_k, causal: bool = False) -> Tensor:
+    """fp32 recompute of what mha_varlen_fwd computes in its un-paged form (csrc/kernel/flash_attn/flash_api.cpp:216-355
+    with block_table None): q [Tq, Hq, d], k/v [Tk, Hkv, d]; per sequence softmax(q k^T / sqrt(d)) v, optionally with the
+    bottom-right aligned causal mask.  The tolerance target of the GPU tests.  Returns [Tq, Hq * d] fp32."""
+    tq, hq, d = q.shape
+    group = hq // k.shape[1]
+    out = torch.zeros(tq, hq, d, dtype=torch.float32)
+    for b in range(len(cu_seqlens_q) - 1):
+        q0, q1, k0, k1 = int(cu_seqlens_q[b]), int(cu_seqlens_q[b + 1]), int(cu_seqlens_k[b]), int(cu_seqlens_k[b + 1])
+        if q1 == q0 or k1 == k0:
+            continue
+        qb = q[q0:q1].float()
+        kb = k[k0:k1].float().repeat_interleave(group, dim=1)
+        vb = v[k0:k1].float().repeat_interleave(group, dim=1)
+        s = torch.einsum("qhd,khd->hqk", qb, kb) / math.sqrt(d)
+        if causal:
+            i = torch.arange(q1 - q0)[:, None]
+            j = torch.arange(k1 - k0)[None, :]
+            s = s.masked_fill((j - i) > ((k1 - k0) - (q1 - q0)), float("-inf"))
+        out[q0:q1] = torch.einsum("hqk,khd->qhd", torch.softmax(s, dim=-1), vb)
+    return out.view(tq, hq * d)
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -30,7 +30,7 @@ def test_binding_table_matches_header():
 
 
 def test_abi_version_and_error_string():
-    assert _lib.lib.hi_abi_version() == 3
+    assert _lib.lib.hi_abi_version() == 4
     assert isinstance(_lib.lib.hi_last_error(), bytes)
 
 
@@ -40,10 +40,14 @@ def test_struct_layout_matches_header():
     assert ctypes.sizeof(_lib.HiPoolGeom) == 32
     # HiRopeArgs: 3 ptrs + 3 i64 + 5 ptrs + i64 + 12 i32
     assert ctypes.sizeof(_lib.HiRopeArgs) == 3 * 8 + 3 * 8 + 5 * 8 + 8 + 12 * 4
+    # HiVarlenArgs: 4 ptrs + 4 i64 + 2 ptrs + 10 i32 + f32 + i32 + ptr + i64 + 2 i64 (api.cu static_asserts the same 160)
+    assert ctypes.sizeof(_lib.HiVarlenArgs) == 4 * 8 + 4 * 8 + 2 * 8 + 10 * 4 + 4 + 4 + 8 + 8 + 16 == 160
 
 
 def test_argument_validation_needs_no_gpu():
     # null args are rejected before any CUDA call
     assert _lib.lib.hi_paged_attention(None, None) == -1
+    assert b"null args" in _lib.lib.hi_last_error()
+    assert _lib.lib.hi_varlen_attention(None, None) == -1
     assert b"null args" in _lib.lib.hi_last_error()
     assert _lib.lib.hi_attention_workspace_bytes(64, 32, 128, 2048) > 0

@@ -52,6 +52,73 @@ def test_migrate_blocks_same_device(geom, dtype):
     assert torch.equal(src_d.cpu(), src), "source pool was modified"
 
 
+def test_layer_ranges_compose_to_the_whole_request():
+    """migrate_blocks_layers over a partition of the layers == one migrate_blocks; each call touches only its layers."""
+    bm = _bm()
+    L, T, bs, H, d, nb_src, nb_dst, n = 6, 2, 16, 4, 128, 30, 25, 11
+    src, dst = _pools((L, T, nb_src, bs, H, d), (L, T, nb_dst, bs, H, d), torch.bfloat16, seed=4)
+    g = torch.Generator().manual_seed(5)
+    src_bt = torch.randperm(nb_src, generator=g)[:n].tolist()
+    dst_bt = torch.randperm(nb_dst, generator=g)[:n].tolist()
+    ref = dst.clone()
+    oracle.migrate_blocks(src_bt, dst_bt, src, ref)
+    src_d, dst_d = src.to(DEV), dst.to(DEV)
+    handle = bm.get_ipc_mem_handle(src_d)
+    bm.migrate_blocks_layers(src_bt, dst_bt, handle, dst_d, nb_src, 2, 5)
+    torch.cuda.synchronize()
+    got = dst_d.cpu()
+    assert torch.equal(got[2:5], ref[2:5]) and torch.equal(got[:2], dst[:2]) and torch.equal(got[5:], dst[5:])
+    bm.migrate_blocks_layers(src_bt, dst_bt, handle, dst_d, nb_src, 0, 2)
+    bm.migrate_blocks_layers(src_bt, dst_bt, handle, dst_d, nb_src, 5, 6)
+    bm.migrate_blocks_layers(src_bt, dst_bt, handle, dst_d, nb_src, 3, 3)  # empty range: no-op
+    torch.cuda.synchronize()
+    assert torch.equal(dst_d.cpu(), ref)
+    with pytest.raises(RuntimeError):
+        bm.migrate_blocks_layers(src_bt, dst_bt, handle, dst_d, nb_src, 4, 7)
+
+
+def test_push_from_the_sender_matches_pull():
+    bm = _bm()
+    L, T, bs, H, d, nb_src, nb_dst, n = 3, 2, 16, 8, 128, 20, 26, 9
+    src, dst = _pools((L, T, nb_src, bs, H, d), (L, T, nb_dst, bs, H, d), torch.float16, seed=8)
+    g = torch.Generator().manual_seed(6)
+    src_bt = torch.randperm(nb_src, generator=g)[:n].tolist()
+    dst_bt = torch.randperm(nb_dst, generator=g)[:n].tolist()
+    ref = dst.clone()
+    oracle.migrate_blocks(src_bt, dst_bt, src, ref)
+    src_d, dst_d = src.to(DEV), dst.to(DEV)
+    bm.push_blocks(src_bt, dst_bt, src_d, bm.get_ipc_mem_handle(dst_d), nb_dst)
+    torch.cuda.synchronize()
+    assert torch.equal(dst_d.cpu(), ref) and torch.equal(src_d.cpu(), src)
+
+
+def test_layer_pipelined_backend_events():
+    """IPCHandleMemoryBackend.migrate_layers: per-layer pulls gated on producer events, completion events instead of a stream sync."""
+    from hydrainfer_b200.memory.communication import IPCHandleMemoryBackend
+    from hydrainfer_b200.memory.token_cache import VirtualTokenCache
+    L, T, bs, H, d, nb = 4, 2, 16, 4, 128, 12
+    src = torch.zeros(L, T, nb, bs, H, d, device=DEV, dtype=torch.bfloat16)
+    dst = torch.zeros(L, T, nb, bs, H, d, device=DEV, dtype=torch.bfloat16)
+    bm = _bm()
+    src_vc = VirtualTokenCache(vid=0, n_blocks_of_cache_manager=nb, n_cache_tokens=3 * bs, block_table=[7, 2, 9], memory_handle=bm.get_ipc_mem_handle(src), rank=0)
+    dst_vc = VirtualTokenCache(vid=1, n_blocks_of_cache_manager=nb, n_cache_tokens=3 * bs, block_table=[1, 0, 5], memory_handle=None, rank=0)
+    backend = IPCHandleMemoryBackend(torch.cuda.Stream(), dst, nb)
+    compute = torch.cuda.Stream()
+    done = []
+    for layer in range(L):  # the "prefill" writes layer l on its own stream, then that layer is shipped while l + 1 is produced
+        with torch.cuda.stream(compute):
+            src[layer, :, [7, 2, 9]] = float(layer + 1)
+            ready = torch.cuda.Event()
+            ready.record(compute)
+        done.append(backend.migrate_layers(src_vc, dst_vc, layer, layer + 1, wait_event=ready))
+    for ev in done:
+        ev.synchronize()
+    for layer in range(L):
+        assert bool((dst[layer, :, [1, 0, 5]] == layer + 1).all()), f"layer {layer} did not arrive after its producer"
+    untouched = [b for b in range(nb) if b not in (1, 0, 5)]
+    assert bool((dst[:, :, untouched] == 0).all())
+
+
 def test_round_trip_restores_blocks():
     bm = _bm()
     L, T, bs, H, d = 4, 2, 16, 8, 128
@@ -143,6 +210,18 @@ def test_same_process_peer_device_migration():
     bm.migrate_blocks([3, 5, 7], [0, 1, 2], handle, dst, 16)
     torch.cuda.synchronize("cuda:1")
     assert torch.equal(dst[:, :, [0, 1, 2]].cpu(), src[:, :, [3, 5, 7]].cpu())
+
+
+@needs_2gpu
+def test_same_process_peer_device_push():
+    """Sender-side variant over NVLink: the kernel runs on cuda:0 and writes cuda:1's pool through peer access."""
+    bm = _bm()
+    src = torch.randn(2, 2, 16, 16, 4, 128, device="cuda:0").to(torch.bfloat16)
+    dst = torch.zeros(2, 2, 12, 16, 4, 128, device="cuda:1", dtype=torch.bfloat16)
+    bm.push_blocks([3, 5, 7], [0, 11, 2], src, bm.get_ipc_mem_handle(dst), 12, 1, 2)
+    torch.cuda.synchronize("cuda:0")
+    assert torch.equal(dst[1][:, [0, 11, 2]].cpu(), src[1][:, [3, 5, 7]].cpu())
+    assert dst[0].abs().max().item() == 0
 
 
 def _ipc_worker(rank, port, out_dir):

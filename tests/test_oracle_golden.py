@@ -82,3 +82,64 @@ def test_migrate_blocks_restatement_properties():
     back = torch.zeros_like(src)
     oracle.migrate_blocks([1, 4, 2], [6, 0, 3], dst, back)
     assert torch.equal(back[:, :, [6, 0, 3]], src[:, :, [6, 0, 3]])
+
+
+def _mha_cases(qwen: bool):
+    return sorted(p for p in GOLDEN.glob("mha_*.npz") if ("qwen" in p.stem) == qwen)
+
+
+def test_vision_attention_matches_reference():
+    """Un-paged attention of the vision towers: oracle vs the frozen outputs of the reference's Torch handlers
+    (multihead_attention.py:40-73 equal-length batches, :235-256 packed cu_seqlens form)."""
+    from conftest import _TORCH_DTYPES
+    assert _mha_cases(False) and _mha_cases(True)
+    for path in _mha_cases(False):
+        z = np.load(path)
+        dtype = _TORCH_DTYPES[str(z["dtype"])]
+        batch, seq_len, heads, d = (int(v) for v in z["geometry"])
+        q, k, v, ref = (_from_np(z[n], dtype) for n in ("query", "key", "value", "ref_out"))
+        assert torch.equal(oracle.multi_head_attention(q, k, v, heads, d), ref), path.stem
+        cu = list(range(0, (batch + 1) * seq_len, seq_len))
+        fp32 = oracle.varlen_attention_fp32(q.view(-1, heads, d), k.view(-1, heads, d), v.view(-1, heads, d), cu, cu)
+        assert (ref.float().view(-1, heads * d) - fp32).abs().max() < 2e-2  # the dtype-rounded reference sits inside the GPU tolerance
+    for path in _mha_cases(True):
+        z = np.load(path)
+        dtype = _TORCH_DTYPES[str(z["dtype"])]
+        _, total, heads, d = (int(v) for v in z["geometry"])
+        q, k, v, ref = (_from_np(z[n], dtype) for n in ("query", "key", "value", "ref_out"))
+        cu = [int(x) for x in z["cu_seqlens"]]
+        assert torch.equal(oracle.qwen_multi_head_attention(q, k, v, total, cu, d), ref), path.stem
+        fp32 = oracle.varlen_attention_fp32(q, k, v, cu, cu)
+        assert (ref.float() - fp32).abs().max() < 3e-2
+
+
+def test_varlen_fp32_causal_agrees_with_paged_oracle():
+    """The causal form of the un-paged recompute is the same function as the (pinned) paged recompute on contiguous pages."""
+    g = torch.Generator().manual_seed(11)
+    hq, hkv, d, bs = 4, 2, 32, 16
+    lens = [(5, 20), (16, 16), (1, 33)]
+    q = torch.randn(sum(a for a, _ in lens), hq, d, generator=g)
+    n_blocks = sum((kv + bs - 1) // bs for _, kv in lens)
+    kc, vc = torch.randn(n_blocks, bs, hkv, d, generator=g), torch.randn(n_blocks, bs, hkv, d, generator=g)
+    q_cu, kv_cu, tables, cu_blocks, ks, vs, blk = [0], [0], [], [0], [], [], 0
+    for ql, kv in lens:
+        nb = (kv + bs - 1) // bs
+        tables += list(range(blk, blk + nb))
+        ks.append(kc[blk:blk + nb].reshape(-1, hkv, d)[:kv])
+        vs.append(vc[blk:blk + nb].reshape(-1, hkv, d)[:kv])
+        blk += nb
+        q_cu.append(q_cu[-1] + ql), kv_cu.append(kv_cu[-1] + kv), cu_blocks.append(cu_blocks[-1] + nb)
+    paged = oracle.paged_attention_fp32(q, kc, vc, q_cu, kv_cu, torch.tensor(tables, dtype=torch.int32), cu_blocks, hq, hkv, d)
+    flat = oracle.varlen_attention_fp32(q, torch.cat(ks), torch.cat(vs), q_cu, kv_cu, causal=True)
+    assert torch.allclose(paged, flat, atol=1e-6, rtol=1e-6)
+
+
+def test_get_image_cache_restatement():
+    z = np.load(GOLDEN / "image_cache.npz")
+    n_blocks, bs, heads, d = (int(v) for v in z["geometry"])
+    cache = _from_np(z["cache"], torch.float16)
+    tokens = _from_np(z["tokens"], torch.float16)
+    slots = torch.from_numpy(z["slots"])
+    oracle.set_image_cache(slots, tokens, cache)
+    # read-back of what the (pinned) scatter wrote: parameters_builder.py:50-54
+    assert torch.equal(oracle.get_image_cache(slots, cache), tokens.view(-1, heads * d))
