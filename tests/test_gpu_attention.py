@@ -332,8 +332,11 @@ def test_unsupported_arguments_raise():
     i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=DEV)
     args = [out, q3, batch.key_cache, batch.value_cache, i32([0, 1]), i32([0, 20]), i32(batch.block_tables), i32([0, 2]), None, 1, 20, 0.088, 0, -1, 0, 0]
     mha_varlen_fwd(*args)
-    bad = list(args); bad[6] = None
-    with pytest.raises(RuntimeError, match="paged-KV"):
+    bad = list(args); bad[6] = None  # block_table None selects the un-paged form, where a 4-D paged cache is not a valid k
+    with pytest.raises(RuntimeError, match=r"k must be \[n_tokens"):
+        mha_varlen_fwd(*bad)
+    bad = list(args); bad[7] = None
+    with pytest.raises(RuntimeError, match="cu_block_lens"):
         mha_varlen_fwd(*bad)
     bad = list(args); bad[12] = 30.0
     with pytest.raises(RuntimeError, match="softcap"):
