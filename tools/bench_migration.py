@@ -81,7 +81,7 @@ def main():
             src_bt = torch.randperm(pool_blocks, generator=g)[:n_move].tolist()
             dst_bt = torch.randperm(pool_blocks, generator=g)[:n_move].tolist()
             handle = bm.get_ipc_mem_handle(pool)
-            patterns = ["same_gpu"] if world == 1 else ["pairs", "fanout"] + (["p2d"] if world >= 4 and world % 2 == 0 else [])
+            patterns = ["same_gpu"] if world == 1 else ["pairs", "pairs_push", "fanout"] + (["p2d"] if world >= 4 and world % 2 == 0 else [])
             half = world // 2
             handles = [handle]
             if world > 1:
@@ -94,6 +94,13 @@ def main():
                     receiver = rank % 2 == 1
                     src_rank = rank - 1 if receiver else rank
                     dst_pool, src_handle = pool if not receiver else torch.zeros_like(pool), handles[src_rank]
+                elif pattern == "pairs_push":  # the SENDER (even rank) runs the kernel and writes the partner's pool through its mapping
+                    receiver = rank % 2 == 1
+                    src_rank = rank - 1 if receiver else rank
+                    dst_pool = pool if not receiver else torch.zeros_like(pool)
+                    dst_handles = [None] * world
+                    dist.all_gather_object(dst_handles, bm.get_ipc_mem_handle(dst_pool) if receiver else None)
+                    src_handle = None
                 elif pattern == "fanout":
                     receiver = rank != 0
                     src_rank = 0
@@ -105,6 +112,10 @@ def main():
                     part = (n_move + half - 1) // half
 
                 def run():
+                    if pattern == "pairs_push":
+                        if not receiver and rank + 1 < world:
+                            bm.push_blocks(src_bt, dst_bt, pool, dst_handles[rank + 1], pool_blocks)
+                        return
                     if not receiver:
                         return
                     if pattern == "p2d":
@@ -129,8 +140,8 @@ def main():
                     chk = min(8, n_move)
                     if pattern == "p2d":
                         chk = min(chk, part)
-                    if pattern in ("pairs", "p2d"):
-                        to_rank = rank + 1 if pattern == "pairs" else rank + half
+                    if pattern in ("pairs", "pairs_push", "p2d"):
+                        to_rank = rank + half if pattern == "p2d" else rank + 1
                         if receiver:
                             buf = torch.empty_like(pool[:, :, :chk])
                             dist.recv(buf, src=src_rank)
