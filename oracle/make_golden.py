@@ -2,6 +2,7 @@
 checks oracle/paged_kv_oracle.py against it on the way.  Run in the build container only:
 
     python oracle/make_golden.py            # writes fixtures, prints the oracle-vs-reference report
+    python oracle/make_golden.py --only-rope   # the rotary fixtures only
 
 The reference's Python torch path runs on CPU once four plotting modules are stubbed (hydrainfer/utils/statistic.py:2-7
 imports matplotlib / seaborn, which this image lacks; nothing on the path uses them).  Functions exercised:
@@ -152,7 +153,10 @@ def rope_goldens(ca, mem) -> None:
         np.savez_compressed(GOLDEN / f"rope_{name}.npz", dtype=DTYPE_NAMES[dtype], table_dtype=DTYPE_NAMES[table_dtype],
                             geometry=np.array([t, hq, hkv, d, rd, max_pos]), theta=theta, interleaved=int(inter),
                             query=to_np(q), key=to_np(k), positions=pos.numpy(), ref_query=to_np(ref_q), ref_key=to_np(ref_k),
-                            table_checksum=np.array([float(tt.double().sum())]))
+                            table_checksum=np.array([float(tt.double().sum())]),
+                            # the cos/sin rows the case reads, as the reference's cache holds them: libm's cosf/sinf differ by an ulp
+                            # between host CPUs, so the GPU tests take these rows from here instead of recomputing them on the box
+                            table_rows=to_np(tt[pos.long()]))
 
     # ---- the ROPE attention module, driven like a decoder layer drives it (identity projections: q/k/v are slices of a fused tensor)
     name, seq_lens, hq, hkv, d, bs, dtype = "ropeattn_qwen_bf16", [(1, 40), (9, 33), (1, 16)], 28, 4, 128, 16, torch.bfloat16
@@ -188,7 +192,7 @@ def rope_goldens(ca, mem) -> None:
                         geometry=np.array([hq, hkv, d, bs, batch.n_blocks, max_pos]), theta=theta, seed=700, qkv=to_np(qkv), positions=positions.numpy(),
                         key_cache=to_np(batch.key_cache), value_cache=to_np(batch.value_cache), owned_blocks=blocks.numpy(),
                         ref_key_cache_owned=to_np(kc[blocks]), ref_value_cache_owned=to_np(vc[blocks]), ref_out=to_np(ref_out),
-                        ref_fp32=fp32.numpy(), ref_query_rot=to_np(q_rot),
+                        ref_fp32=fp32.numpy(), ref_query_rot=to_np(q_rot), table=to_np(table),
                         new_cache_slots=np.array(meta.new_cache_slots), block_tables=np.array(meta.block_tables),
                         q_cu_seq_lens=np.array(meta.q_cu_seq_lens), cu_blocks_lens=np.array(meta.cu_blocks_lens))
 
@@ -213,6 +217,9 @@ def main() -> None:
     ca, mem = import_reference()
     GOLDEN.mkdir(parents=True, exist_ok=True)
     report = []
+    if "--only-rope" in sys.argv:  # rewrite rope_*.npz / ropeattn_*.npz only (every case is seeded on its own)
+        rope_goldens(ca, mem)
+        return
 
     for idx, (name, seq_lens, hq, hkv, d, bs, dtype, fused) in enumerate(ATTENTION_CASES):
         batch = make_batch(seq_lens, hq, hkv, d, bs, dtype=dtype, seed=100 + idx, fused_qkv=fused)

@@ -1,0 +1,10 @@
+#!/bin/bash
+# GPU pass 7: full gpu suite + smoke + both bench arms on the current tree (re-entry sanity pass).
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -n 6 gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
+tail -n 8 gpurun_out/smoke.log
+timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cut -c1-1500 gpurun_out/bench.json; tail -n 3 gpurun_out/bench.err
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"; cut -c1-800 gpurun_out/bench_ref.json
+timeout 600 python tools/bench_configs.py --flashinfer > gpurun_out/configs.jsonl 2> gpurun_out/configs.err; echo "configs rc=$?"; tail -n 3 gpurun_out/configs.err
