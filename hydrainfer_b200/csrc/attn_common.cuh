@@ -25,6 +25,9 @@ struct SimtArgs {
   float scale_log2;  // softmax_scale * log2(e)
   float* part_o;     // [n_tokens * Hq * n_chunks][D]
   float* part_ml;    // [n_tokens * Hq * n_chunks][2]
+  // Merge only: > 0 when the producer handled query rows in tiles of this many tokens per sequence and wrote a tile whose
+  // LAST row needs a single chunk straight to `out` (normalised); the merge leaves those rows alone.
+  int direct_tile_tokens;
 };
 
 // One merged row = LSE-weighted sum of its valid chunks; chunk c covers 16-token tiles [c*chunk_tiles, (c+1)*chunk_tiles).

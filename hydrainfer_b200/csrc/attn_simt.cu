@@ -481,15 +481,26 @@ __global__ void __launch_bounds__(kSimtThreads) paged_attn_stream_kernel(const S
   merge_half_warps_and_store<T, D, G>(a, reinterpret_cast<float*>(stage), m, lsum, o, t, qh0, chunk);
 }
 
-// LSE-weighted reduction of the per-chunk partials of one (row, head): the split-merge step.
+// LSE-weighted reduction of the per-chunk partials of one (row, head): the split-merge step.  D/4 threads own one
+// (row, head); a CTA carries kMergeThreads / (D/4) heads of one row, so a prefill batch (thousands of rows x heads) is a
+// few thousand CTAs instead of one 32-thread CTA per (row, head).
+constexpr int kMergeThreads = 128;
 template <typename T, int D>
-__global__ void __launch_bounds__(D / 4) merge_partials_kernel(const SimtArgs a) {
+__global__ void __launch_bounds__(kMergeThreads) merge_partials_kernel(const SimtArgs a) {
+  constexpr int kLanes = D / 4;
   const int t = blockIdx.x;
-  const int head = blockIdx.y;
+  const int head = blockIdx.y * (kMergeThreads / kLanes) + threadIdx.x / kLanes;
+  if (head >= a.n_qo_heads) return;
   const int b = find_seq(a.q_cu, a.n_seqs, t);
   const int q_start = __ldg(a.q_cu + b);
   const int q_len = __ldg(a.q_cu + b + 1) - q_start;
   const int kv_len = __ldg(a.kv_cu + b + 1) - __ldg(a.kv_cu + b);
+  if (a.direct_tile_tokens > 0) {
+    // the producer wrote this row's tile directly when the tile's last row fits in one chunk
+    const int i_last = min(q_len, ((t - q_start) / a.direct_tile_tokens + 1) * a.direct_tile_tokens) - 1;
+    const int vis_last = kv_len - q_len + i_last + 1;
+    if (((vis_last + 15) >> 4) <= a.chunk_tiles) return;
+  }
   const int vis = kv_len - q_len + (t - q_start) + 1;
   const int tiles_total = (vis + 15) >> 4;
   const int n_valid = (tiles_total + a.chunk_tiles - 1) / a.chunk_tiles;
@@ -499,7 +510,7 @@ __global__ void __launch_bounds__(D / 4) merge_partials_kernel(const SimtArgs a)
   for (int c = 0; c < n_valid; ++c) mm = fmaxf(mm, a.part_ml[(base + c) * 2]);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   float l = 0.f;
-  const int d4 = threadIdx.x;
+  const int d4 = threadIdx.x % kLanes;
   for (int c = 0; c < n_valid; ++c) {
     const float w = fast_exp2(a.part_ml[(base + c) * 2] - mm);
     l = fmaf(w, a.part_ml[(base + c) * 2 + 1], l);
@@ -516,6 +527,11 @@ __global__ void __launch_bounds__(D / 4) merge_partials_kernel(const SimtArgs a)
   orow[2] = Elem<T>::from_f32(acc.z * inv);
   orow[3] = Elem<T>::from_f32(acc.w * inv);
 }
+template <typename T, int D>
+static dim3 merge_grid(const SimtArgs& a) {
+  constexpr int kHeadsPerCta = kMergeThreads / (D / 4);
+  return dim3(a.n_tokens, (a.n_qo_heads + kHeadsPerCta - 1) / kHeadsPerCta);
+}
 
 // ---- host side ----------------------------------------------------------------------------------------------------
 
@@ -530,11 +546,10 @@ int64_t simt_workspace_bytes(int head_dim) {
 
 // Split-merge launch shared with the tile kernel's split-KV mode (a.n_tokens rows, a.n_chunks partials per row and head).
 int launch_merge_partials(const SimtArgs& a, int dtype, int head_dim, cudaStream_t stream) {
-  const dim3 grid(a.n_tokens, a.n_qo_heads);
   if (head_dim == 128 && dtype == HI_BF16) {
-    merge_partials_kernel<__nv_bfloat16, 128><<<grid, 32, 0, stream>>>(a);
+    merge_partials_kernel<__nv_bfloat16, 128><<<merge_grid<__nv_bfloat16, 128>(a), kMergeThreads, 0, stream>>>(a);
   } else if (head_dim == 128 && dtype == HI_F16) {
-    merge_partials_kernel<__half, 128><<<grid, 32, 0, stream>>>(a);
+    merge_partials_kernel<__half, 128><<<merge_grid<__half, 128>(a), kMergeThreads, 0, stream>>>(a);
   } else {
     set_error("merge_partials: unsupported head_dim %d / dtype %d", head_dim, dtype);
     return HI_ERR_UNSUPPORTED;
@@ -565,7 +580,7 @@ static int launch_simt_g(const SimtArgs& a, cudaStream_t stream) {
   note_launch();
   HI_CUDA(cudaGetLastError());
   if (a.n_chunks > 1) {
-    merge_partials_kernel<T, D><<<dim3(a.n_tokens, a.n_qo_heads), D / 4, 0, stream>>>(a);
+    merge_partials_kernel<T, D><<<merge_grid<T, D>(a), kMergeThreads, 0, stream>>>(a);
     note_launch();
     HI_CUDA(cudaGetLastError());
   }

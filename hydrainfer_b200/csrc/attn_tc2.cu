@@ -122,6 +122,7 @@ struct P2Item {
   int j_begin;   // first 64-key step of this split
   int nt[2];     // steps walked for tile t (local step j is global step j_begin + j)
   int n_all;     // max(nt[0], nt[1]); 0 = nothing to do
+  bool direct[2];  // tile t sees all its keys in this one split: its rows go straight to `out`, not to the fp32 partials
   int blk0, n_pages;
 };
 
@@ -158,6 +159,7 @@ __device__ __forceinline__ void p2_decode_item(const P2Args& a, int k, P2Item& i
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
     const int first = it.i0 + t * a.tq;
+    it.direct[t] = true;
     if (pair < 0 || first >= it.q_len) {
       it.nt[t] = 0;
     } else {
@@ -165,6 +167,7 @@ __device__ __forceinline__ void p2_decode_item(const P2Args& a, int k, P2Item& i
       const int kv_end = (VL && !a.causal) ? it.kv_len : i_last + (it.kv_len - it.q_len) + 1;  // keys [0, kv_end) are visible to the tile
       const int n_vis = (kv_end + kP2TileN - 1) / kP2TileN;
       it.nt[t] = max(0, min(n_vis - it.j_begin, a.tiles_per_split));
+      it.direct[t] = n_vis <= a.tiles_per_split;  // the same rule merge_partials_kernel applies (direct_tile_tokens)
     }
   }
   it.n_all = max(it.nt[0], it.nt[1]);
@@ -597,7 +600,8 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       const int d_out = VL ? a.head_dim : kP2D;
       T* orow = static_cast<T*>(a.out) + static_cast<int64_t>(it.q_start + i) * a.out_row_stride + head * d_out;
       const int64_t pidx = (static_cast<int64_t>(it.q_start + i) * a.n_qo_heads + head) * a.n_splits + it.sp;
-      if (a.n_splits > 1 && row_valid) {
+      const bool direct = t ? it.direct[1] : it.direct[0];
+      if (!direct && row_valid) {
         a.part_ml[pidx * 2 + 0] = m_used;
         a.part_ml[pidx * 2 + 1] = l;
       }
@@ -613,7 +617,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
           ptx::mbar_arrive(bar(L::bOEmpty + t));
         }
         if (warp_active && row_valid) {
-          if (a.n_splits > 1) {
+          if (!direct) {
             float4* dst = reinterpret_cast<float4*>(a.part_o + pidx * kP2D + c * 32);
 #pragma unroll
             for (int e = 0; e < 32; e += 4)
@@ -718,7 +722,11 @@ int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
   if (args.qk_work_hint > 0 && a.work_items != nullptr) {
     // CTA-steps: every work item walks its visible keys in 64-key steps, once per KV head
     const double total_steps = static_cast<double>(args.qk_work_hint) / kP2TileN * args.n_kv_heads;
-    int chunk = static_cast<int>(total_steps / (2.0 * kSms)) + 1;
+    // Items are claimed heaviest first, so a launch is balanced once no item is longer than one SM's share of the work: the
+    // chunk is that share.  (Measured on B200, BASELINE config 3: the chunked-prefill rows alone want 2 chunks - 0.154 ms
+    // against 0.159 / 0.160 with 1 / 3 - and the mixed batch none - 0.192 ms against 0.213 / 0.220 with 2 / 3; a chunk of
+    // half a share split both into 3 and paid for it in partial traffic and merge work.)
+    int chunk = static_cast<int>(total_steps / kSms) + 1;
     if (chunk < kMinTilesPerSplit) chunk = kMinTilesPerSplit;
     if (chunk < max_kv_tiles) n_splits = (max_kv_tiles + chunk - 1) / chunk;
   } else if (base_ctas < 2 * kSms) {
@@ -787,6 +795,7 @@ int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
   m.chunk_tiles = a.tiles_per_split * (kP2TileN / 16);
   m.part_o = a.part_o;
   m.part_ml = a.part_ml;
+  m.direct_tile_tokens = a.tq;
   return launch_merge_partials(m, args.dtype, kP2D, stream);
 }
 

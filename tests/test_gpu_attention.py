@@ -226,6 +226,23 @@ def test_tile_kernel_split_kv_and_ring_depth_variants(monkeypatch, splits, stage
         check_batch(batch, [TC, DEC, PAIR], f"splits={splits} stages={stages} heads={heads}")
 
 
+@pytest.mark.parametrize("splits", ["2", "3", "5"])
+def test_pair_kernel_direct_and_split_tiles_share_a_launch(monkeypatch, splits):
+    """With split-KV on, a query tile whose keys all fall into the first chunk is written straight to `out` and skipped by the
+    merge; tiles that span chunks go through the fp32 partials.  One launch holds both kinds (early vs late tiles of the same
+    prefill, short vs long sequences); the workspace is filled with NaN bit patterns first, so a merge that read a partial
+    nobody wrote, or skipped a row that needed it, cannot pass."""
+    from hydrainfer_b200._C.kernel import flash_attn
+    monkeypatch.setenv("HI_TC_SPLITS", splits)
+    seq_lens = [(600, 600), (300, 2000), (1, 3000), (64, 64), (1, 40), (200, 1100)]
+    for heads in ((28, 4), (8, 8), (16, 1)):
+        batch = make_batch(seq_lens, heads[0], heads[1], 128, 16, dtype=torch.bfloat16, seed=43)
+        flash_attn._workspace(torch.device(DEV), 128).fill_(0xFF)
+        check_batch(batch, [PAIR], f"direct+split tiles splits={splits} heads={heads}")
+        flash_attn._workspace(torch.device(DEV), 128).fill_(0xFF)
+        check_batch(batch, [TC, DEC] if heads[0] // heads[1] <= 16 else [TC], f"merge of the other tcgen05 paths splits={splits} heads={heads}")
+
+
 def test_host_plan_ragged_prefill_through_the_layer(monkeypatch):
     """AttentionParametersBuilder's plan (cost-sorted work items + work hint) drives the pair kernel's grid and split-KV chunk:
     a ragged chunked-prefill + decode batch must give the same answer with and without it, for forced split counts too."""
