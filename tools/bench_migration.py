@@ -67,11 +67,15 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    only_geoms = [g for g in os.environ.get("HI_MIG_GEOMS", "").split(",") if g]   # e.g. llava7b,qwen2vl7b (bounds an 8-GPU pass)
+    only_sizes = [int(x) for x in os.environ.get("HI_MIG_SIZES", "").split(",") if x]
     for gname, geom in GEOMS.items():
+        if only_geoms and gname not in only_geoms:
+            continue
         bytes_per_block = geom["n_layers"] * geom["n_tokens"] * geom["block_size"] * geom["n_heads"] * geom["head_size"] * 2
         for n_move in (16, 64, 256, 1024, 4096):
             payload = n_move * bytes_per_block
-            if payload > 36 * 2**30:
+            if payload > 36 * 2**30 or (only_sizes and n_move not in only_sizes):
                 continue
             pool_blocks = n_move + max(8, n_move // 8)
             shape = (geom["n_layers"], geom["n_tokens"], pool_blocks, geom["block_size"], geom["n_heads"], geom["head_size"])
