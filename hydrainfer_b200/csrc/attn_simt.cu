@@ -21,6 +21,7 @@
 //
 // HBM traffic per row and KV head: 2 * vis * D * sizeof(T) bytes of K and V, read exactly once.
 #include <cfloat>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "attn_common.cuh"
@@ -600,7 +601,9 @@ static int launch_simt_td(SimtArgs& a, const HiAttnArgs& args, cudaStream_t stre
   const int64_t ctas_per_chunk = static_cast<int64_t>(a.n_tokens) * a.n_kv_heads * (a.group / G);
   const int max_tiles = (args.max_kv_len + 15) / 16;
   int want_chunks = static_cast<int>((kTargetCtas + ctas_per_chunk - 1) / ctas_per_chunk);
-  const int max_chunks = (max_tiles + kMinChunkTiles - 1) / kMinChunkTiles;
+  int min_chunk_tiles = kMinChunkTiles;
+  if (const char* env = getenv("HI_SIMT_MIN_CHUNK_TILES")) min_chunk_tiles = atoi(env) > 0 ? atoi(env) : min_chunk_tiles;  // tuning override
+  const int max_chunks = (max_tiles + min_chunk_tiles - 1) / min_chunk_tiles;
   if (want_chunks > max_chunks) want_chunks = max_chunks;
   if (want_chunks < 1) want_chunks = 1;
   a.chunk_tiles = (max_tiles + want_chunks - 1) / want_chunks;

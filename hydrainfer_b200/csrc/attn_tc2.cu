@@ -126,8 +126,10 @@ struct P2Item {
   int blk0, n_pages;
 };
 
-template <bool VL = false>
-__device__ __forceinline__ void p2_decode_item(const P2Args& a, int k, P2Item& it) {
+// Decoding an item is two levels of dependent global loads (plan entry -> sequence metadata): p2_item_head issues the first,
+// p2_item_body the second and the arithmetic, so a role can put other work between them (the softmax warps overlap them with
+// the wait for the last P.V and with their epilogue).
+__device__ __forceinline__ int p2_item_head(const P2Args& a, int k, P2Item& it) {
   int pair;
   if (a.work_items != nullptr) {
     it.sp = k % a.n_splits;
@@ -140,8 +142,13 @@ __device__ __forceinline__ void p2_decode_item(const P2Args& a, int k, P2Item& i
     const int slot = (k / a.n_splits) % a.max_pairs;
     it.kvh = (k / (a.n_splits * a.max_pairs)) % a.n_kv_heads;
     it.b = k / (a.n_splits * a.max_pairs * a.n_kv_heads);
-    pair = -1 - slot;  // resolved below: the sequence's latest (heaviest) pair first
+    pair = -1 - slot;  // resolved in the body: the sequence's latest (heaviest) pair first
   }
+  return pair;
+}
+
+template <bool VL = false>
+__device__ __forceinline__ void p2_item_body(const P2Args& a, int pair, P2Item& it) {
   it.q_start = __ldg(a.q_cu + it.b);
   it.q_len = __ldg(a.q_cu + it.b + 1) - it.q_start;
   it.kv_len = __ldg(a.kv_cu + it.b + 1) - __ldg(a.kv_cu + it.b);
@@ -171,6 +178,12 @@ __device__ __forceinline__ void p2_decode_item(const P2Args& a, int k, P2Item& i
     }
   }
   it.n_all = max(it.nt[0], it.nt[1]);
+}
+
+template <bool VL = false>
+__device__ __forceinline__ void p2_decode_item(const P2Args& a, int k, P2Item& it) {
+  const int pair = p2_item_head(a, k, it);
+  p2_item_body<VL>(a, pair, it);
 }
 
 // Work distribution.  Items are claimed DYNAMICALLY from a global counter (the list is sorted heaviest first by the host
@@ -493,13 +506,25 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     const int g = r - tok * a.group;
     uint32_t gs = 0, n_act = 0, n_pv2 = 0, n_it = 0;
 
-    for (;;) {
+    // The NEXT item is decoded while this one finishes: its index is fetched after the last step (warp 8 published it several
+    // steps ago), the plan entry is loaded behind the wait for the last P.V and the sequence metadata behind the epilogue, so
+    // the two levels of global-load latency are off the path between two items' softmax work.
+    P2Item nxt;
+    bool more = false;
+    {
       const int k = next_item(n_it++, false);
-      if (k >= a.n_items) break;
-      P2Item it;
-      p2_decode_item<VL>(a, k, it);
+      more = k < a.n_items;
+      if (more) p2_decode_item<VL>(a, k, nxt);
+    }
+    while (more) {
+      const P2Item it = nxt;
       const int n_mine = t ? it.nt[1] : it.nt[0];
-      if (n_mine == 0) continue;
+      if (n_mine == 0) {
+        const int k = next_item(n_it++, false);
+        more = k < a.n_items;
+        if (more) p2_decode_item<VL>(a, k, nxt);
+        continue;
+      }
       trace(1, n_it, n_mine);
       const int first = it.i0 + t * a.tq;
       const int i = first + tok;                       // query position within the sequence
@@ -592,7 +617,14 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       }
 
       // ---- epilogue: O / l -> out (or the fp32 split-KV partial) ---------------------------------------------------------
+      int pair_nxt = 0;
+      {
+        const int k = next_item(n_it++, false);
+        more = k < a.n_items;
+        if (more) pair_nxt = p2_item_head(a, k, nxt);
+      }
       ptx::mbar_wait(bar(L::bOFull + t), n_act & 1u);
+      if (more) p2_item_body<VL>(a, pair_nxt, nxt);
       ptx::tc_fence_after_sync();
       trace(5, n_it, 0);
       const float inv_l = 1.f / l;

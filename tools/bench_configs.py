@@ -130,6 +130,10 @@ def main():
     cases = [
         ("cfg2", [(1, 2048)] * 64, 32, 32, [SIMT, TC]),
         ("cfg2_b8", [(1, 2048)] * 8, 32, 32, [SIMT, TC]),
+        ("cfg2_b1", [(1, 2048)] * 1, 32, 32, [SIMT]),
+        ("cfg2_b4", [(1, 2048)] * 4, 32, 32, [SIMT]),
+        ("cfg2_b16", [(1, 2048)] * 16, 32, 32, [SIMT]),
+        ("cfg2_b32", [(1, 2048)] * 32, 32, 32, [SIMT]),
         ("cfg2_ctx8k", [(1, 8192)] * 16, 32, 32, [SIMT, TC]),
         ("cfg3d", cfg3_dec, 28, 4, [SIMT, TC, DEC]),
         ("cfg3p", cfg3_pre, 28, 4, [TC, PAIR]),
