@@ -435,12 +435,25 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         ptx::mma_commit(bar(L::bVEmpty + st));
       };
       uint32_t g = 0, gs = 0, n_act = 0, n_it = 0;
-      for (;;) {
+      // The next item is decoded during the last two steps of the current one (plan entry at the top of step n-2, sequence
+      // metadata at the top of step n-1: both loads complete behind the waits for P), so Q.K(0) and Q.K(1) of the next item
+      // follow the last P.V without a decode in between.
+      P2Item nxt;
+      bool more_items = false;
+      int pair_nxt = 0;
+      {
         const int k = next_item(n_it++, true);
-        if (k >= a.n_items) break;
-        P2Item it;
-        p2_decode_item<VL>(a, k, it);
-        if (it.n_all == 0) continue;
+        more_items = k < a.n_items;
+        if (more_items) p2_decode_item<VL>(a, k, nxt);
+      }
+      while (more_items) {
+        const P2Item it = nxt;
+        if (it.n_all == 0) {
+          const int k = next_item(n_it++, true);
+          more_items = k < a.n_items;
+          if (more_items) p2_decode_item<VL>(a, k, nxt);
+          continue;
+        }
         const int n_t = t ? it.nt[1] : it.nt[0];
         const int n_all = it.n_all;
         trace(1, n_it, n_t);
@@ -466,6 +479,12 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
           const int s = gj & 3, s2 = (gj + 2) & 3, buf = (gs + j) & 1;
           const bool has_pv = j < n_t;
           const bool more = j + 2 < n_all;
+          if (j == max(n_all - 2, 0)) {  // warp 8 published the next index when it finished this item's K loads, steps ago
+            const int k = next_item(n_it++, true);
+            more_items = k < a.n_items;
+            if (more_items) pair_nxt = p2_item_head(a, k, nxt);
+          }
+          if (j == n_all - 1 && more_items) p2_item_body<VL>(a, pair_nxt, nxt);
           ptx::mbar_wait(bar(L::bVFull + s), (gj >> 2) & 1u);
           if (more) ptx::mbar_wait(bar(L::bKFull + s2), ((gj + 2) >> 2) & 1u);
           if (has_pv) {

@@ -1,5 +1,5 @@
 #!/bin/bash
-# GPU pass 11: softmax warps decode the next work item behind the last P.V and the epilogue; same-box A/B against the
+# GPU pass 11: MMA warps decode the next work item during their last two steps; same-box A/B against the previous build.
 # previous build (variant "base").
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_attention.py tests/test_gpu_vision_attention.py -m gpu -x -q > gpurun_out/pytest_p11.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_p11.log
