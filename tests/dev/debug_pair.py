@@ -7,7 +7,7 @@ from pathlib import Path
 
 import torch
 
-ROOT = Path(__file__).resolve().parents[1]
+ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 from hydrainfer_b200 import _lib  # noqa: E402
 from hydrainfer_b200._C.kernel.flash_attn import mha_varlen_fwd  # noqa: E402

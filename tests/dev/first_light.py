@@ -1,12 +1,12 @@
 """Dev tool (GPU box): small attention cases per kernel path with error breakdowns, each group in its own subprocess so a
-trapped kernel cannot take the other groups down.  Usage: python tools/first_light.py [group]"""
+trapped kernel cannot take the other groups down.  Usage: python tests/dev/first_light.py [group]"""
 import math
 import os
 import subprocess
 import sys
 from pathlib import Path
 
-ROOT = Path(__file__).resolve().parents[1]
+ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 
 GROUPS = {

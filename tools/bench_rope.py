@@ -19,7 +19,7 @@ sys.path.insert(0, str(ROOT))
 
 from hydrainfer_b200._C.kernel.kv_cache_kernels import set_kv_cache  # noqa: E402
 from hydrainfer_b200._C.kernel.position_embedding import apply_rotary_pos_emb, rope_set_kv_cache  # noqa: E402
-from oracle import paged_kv_oracle as oracle  # noqa: E402  (table construction only; nothing timed)
+from hydrainfer_b200.layer.rotary_embedding import B200RotaryEmbeddingHandler  # noqa: E402
 
 DEV = "cuda:0"
 HBM_PEAK = 6537.0
@@ -56,7 +56,7 @@ def time_rotating(fns, iters=30, warmup=3):
 def main() -> None:
     d, bs, dtype, max_pos = 128, 16, torch.bfloat16, 32768
     inv_freq = 1. / torch.pow(torch.tensor(1e6), torch.arange(0, d, 2, dtype=torch.float) / d)
-    table = oracle.rotary_cos_sin_table(d, max_pos, inv_freq).to(dtype).to(DEV)
+    table = B200RotaryEmbeddingHandler(d, max_pos, inv_freq, False).cos_sin_cache.to(dtype).to(DEV)
     out_path = ROOT / "gpurun_out" / "rope.jsonl"
     out_path.parent.mkdir(exist_ok=True)
     lines = []

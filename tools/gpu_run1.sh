@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 nvidia-smi > gpurun_out/nvsmi.txt 2>&1
 python -c "import torch; print(torch.__version__, torch.cuda.get_device_name(0))" > gpurun_out/env.txt 2>&1
-timeout 1000 python tools/first_light.py > gpurun_out/first_light.log 2>&1
+timeout 1000 python tests/dev/first_light.py > gpurun_out/first_light.log 2>&1
 timeout 600 python -m pytest tests/test_gpu_append.py -m gpu -q > gpurun_out/t_append.log 2>&1
 timeout 600 python -m pytest tests/test_gpu_migration.py -m gpu -q > gpurun_out/t_migr.log 2>&1
 HI_TEST_SKIP_TC=1 timeout 900 python -m pytest tests/test_gpu_attention.py -m gpu -q > gpurun_out/t_attn_simt.log 2>&1

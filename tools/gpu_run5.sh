@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out; rm -f gpurun_out/configs.jsonl
-timeout 300 python tools/first_light.py dec > gpurun_out/first_light_dec.log 2>&1
+timeout 300 python tests/dev/first_light.py dec > gpurun_out/first_light_dec.log 2>&1
 timeout 900 python -m pytest tests/test_gpu_attention.py -m gpu -q > gpurun_out/t_attn_all.log 2>&1
 timeout 900 python tools/bench_configs.py --only cfg3d,cfg3p,cfg3mix,pre1k,pre4k,pre8k,pre_mha2k,pre_mha8k,cfg4_2k,cfg4_4k,cfg4_shard8 > gpurun_out/configs.log 2>&1
 for sp in 1 2 4 8 16; do
