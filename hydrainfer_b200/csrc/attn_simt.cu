@@ -483,15 +483,15 @@ __global__ void __launch_bounds__(kSimtThreads) paged_attn_stream_kernel(const S
 }
 
 // LSE-weighted reduction of the per-chunk partials of one (row, head): the split-merge step.  D/4 threads own one
-// (row, head); a CTA carries kMergeThreads / (D/4) heads of one row, so a prefill batch (thousands of rows x heads) is a
-// few thousand CTAs instead of one 32-thread CTA per (row, head).
+// (row, head); a CTA belongs to one row, finds the row's sequence once and walks the row's heads kMergeThreads / (D/4) at a
+// time with a stride of gridDim.y, so a prefill batch (thousands of rows x heads) is one wave of CTAs - one per row - and
+// rows the producer wrote directly cost one metadata lookup, while a small decode batch still gets a CTA per 4 heads.
 constexpr int kMergeThreads = 128;
 template <typename T, int D>
 __global__ void __launch_bounds__(kMergeThreads) merge_partials_kernel(const SimtArgs a) {
   constexpr int kLanes = D / 4;
+  constexpr int kHeadsPerCta = kMergeThreads / kLanes;
   const int t = blockIdx.x;
-  const int head = blockIdx.y * (kMergeThreads / kLanes) + threadIdx.x / kLanes;
-  if (head >= a.n_qo_heads) return;
   const int b = find_seq(a.q_cu, a.n_seqs, t);
   const int q_start = __ldg(a.q_cu + b);
   const int q_len = __ldg(a.q_cu + b + 1) - q_start;
@@ -505,33 +505,40 @@ __global__ void __launch_bounds__(kMergeThreads) merge_partials_kernel(const Sim
   const int vis = kv_len - q_len + (t - q_start) + 1;
   const int tiles_total = (vis + 15) >> 4;
   const int n_valid = (tiles_total + a.chunk_tiles - 1) / a.chunk_tiles;
-
-  const int64_t base = (static_cast<int64_t>(t) * a.n_qo_heads + head) * a.n_chunks;
-  float mm = -INFINITY;
-  for (int c = 0; c < n_valid; ++c) mm = fmaxf(mm, a.part_ml[(base + c) * 2]);
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  float l = 0.f;
   const int d4 = threadIdx.x % kLanes;
-  for (int c = 0; c < n_valid; ++c) {
-    const float w = fast_exp2(a.part_ml[(base + c) * 2] - mm);
-    l = fmaf(w, a.part_ml[(base + c) * 2 + 1], l);
-    const float4 v = *reinterpret_cast<const float4*>(a.part_o + (base + c) * D + d4 * 4);
-    acc.x = fmaf(w, v.x, acc.x);
-    acc.y = fmaf(w, v.y, acc.y);
-    acc.z = fmaf(w, v.z, acc.z);
-    acc.w = fmaf(w, v.w, acc.w);
+
+  for (int head = blockIdx.y * kHeadsPerCta + threadIdx.x / kLanes; head < a.n_qo_heads; head += gridDim.y * kHeadsPerCta) {
+    const int64_t base = (static_cast<int64_t>(t) * a.n_qo_heads + head) * a.n_chunks;
+    float mm = -INFINITY;
+    for (int c = 0; c < n_valid; ++c) mm = fmaxf(mm, a.part_ml[(base + c) * 2]);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float l = 0.f;
+    for (int c = 0; c < n_valid; ++c) {
+      const float w = fast_exp2(a.part_ml[(base + c) * 2] - mm);
+      l = fmaf(w, a.part_ml[(base + c) * 2 + 1], l);
+      const float4 v = *reinterpret_cast<const float4*>(a.part_o + (base + c) * D + d4 * 4);
+      acc.x = fmaf(w, v.x, acc.x);
+      acc.y = fmaf(w, v.y, acc.y);
+      acc.z = fmaf(w, v.z, acc.z);
+      acc.w = fmaf(w, v.w, acc.w);
+    }
+    const float inv = 1.f / l;
+    T* orow = static_cast<T*>(a.out) + static_cast<int64_t>(t) * a.out_row_stride + head * D + d4 * 4;
+    orow[0] = Elem<T>::from_f32(acc.x * inv);
+    orow[1] = Elem<T>::from_f32(acc.y * inv);
+    orow[2] = Elem<T>::from_f32(acc.z * inv);
+    orow[3] = Elem<T>::from_f32(acc.w * inv);
   }
-  const float inv = 1.f / l;
-  T* orow = static_cast<T*>(a.out) + static_cast<int64_t>(t) * a.out_row_stride + head * D + d4 * 4;
-  orow[0] = Elem<T>::from_f32(acc.x * inv);
-  orow[1] = Elem<T>::from_f32(acc.y * inv);
-  orow[2] = Elem<T>::from_f32(acc.z * inv);
-  orow[3] = Elem<T>::from_f32(acc.w * inv);
 }
 template <typename T, int D>
 static dim3 merge_grid(const SimtArgs& a) {
   constexpr int kHeadsPerCta = kMergeThreads / (D / 4);
-  return dim3(a.n_tokens, (a.n_qo_heads + kHeadsPerCta - 1) / kHeadsPerCta);
+  const int head_groups = (a.n_qo_heads + kHeadsPerCta - 1) / kHeadsPerCta;
+  // ~2 waves of 128-thread CTAs at most: many rows -> one CTA per row walking all its heads
+  int y = (2 * 148 * 16 + a.n_tokens - 1) / a.n_tokens;
+  if (y > head_groups) y = head_groups;
+  if (y < 1) y = 1;
+  return dim3(a.n_tokens, y);
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------
