@@ -54,6 +54,9 @@ constexpr uint32_t kP2TmemCols = 512;
 constexpr uint32_t kP2ColTile = 256;          // columns per query tile: S[0] at +0, S[1] at +64, O at +128
 constexpr uint32_t kP2ColO = 128;
 constexpr float kP2Rescale = 8.0f;
+constexpr int kP2ClaimAhead = 8;              // 64-key steps of the current item left (for the K producer) when the next item is claimed;
+                                              // swept on B200: 4, 8 and 16 are equivalent, 32 loses 2.5 % on the config-3 mixed batch, whole-item
+                                              // lookahead 26 %
 
 struct P2Args {
   void* out;
@@ -210,6 +213,13 @@ __device__ __forceinline__ int p2_claim_item(const P2Args& a, int round, int lan
 constexpr int kTraceRoles = 6, kTraceCap = 8192;
 static __device__ unsigned long long g_pair_trace[kTraceRoles * kTraceCap];
 static __device__ unsigned int g_pair_trace_n[kTraceRoles];
+// Per CTA (MMA warp of tile 0): {globaltimer at entry, globaltimer after the last item, items walked, 64-key steps walked}.
+static __device__ unsigned long long g_pair_cta_stats[1024 * 4];
+__device__ __forceinline__ unsigned long long trace_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 #endif
 
 // PF = how many of every 4 (pairs of) exponentials run on the FMA pipes (exp2_poly2) instead of MUFU.EX2.
@@ -304,7 +314,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       int k_next = is_k ? p2_claim_item(a, 0, lane) : 0;
       for (;;) {
         int k;
-        if (is_k) {  // claim one item ahead and publish the current one to the other roles
+        if (is_k) {  // publish the current item to the other roles (the next one is claimed near the end of this one's K loop)
           k = k_next;
           const uint32_t slot = n_it & 3u;
           ptx::mbar_wait(bar(L::bItemEmpty + slot), ((n_it >> 2) & 1u) ^ 1u);
@@ -313,7 +323,6 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
             ptx::mbar_arrive(bar(L::bItemFull + slot));
           }
           __syncwarp();
-          if (k < a.n_items) k_next = p2_claim_item(a, static_cast<int>(n_it) + 1, lane);
         } else {
           k = next_item(n_it, true);
         }
@@ -321,7 +330,10 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         if (k >= a.n_items) break;
         P2Item it;
         p2_decode_item<VL>(a, k, it);
-        if (it.n_all == 0) continue;
+        if (it.n_all == 0) {
+          if (is_k) k_next = p2_claim_item(a, static_cast<int>(n_it), lane);
+          continue;
+        }
         trace(1, n_it, it.n_all);
         if (is_k) {
 #pragma unroll
@@ -350,6 +362,11 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         int n_valid_next = 0;
         int blk_next = pages_of(0, n_valid_next);
         for (int j = 0; j < it.n_all; ++j, ++g) {
+          // The next item is claimed kP2ClaimAhead steps before this warp is done with the current one - early enough to hide
+          // the atomic and the decode, late enough that the claim order follows who really finishes first.  (Claiming at the
+          // start of an item makes the first two rounds of a launch static: every CTA takes two of the heaviest items at t = 0,
+          // measured on the config-3 mixed batch as CTAs ending between 126 and 208 us.)
+          if (is_k && j == max(it.n_all - kP2ClaimAhead, 0)) k_next = p2_claim_item(a, static_cast<int>(n_it), lane);
           const int n_valid = n_valid_next;
           const int blk_lane = blk_next;
           blk_next = pages_of(j + 1, n_valid_next);
@@ -435,6 +452,10 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         ptx::mma_commit(bar(L::bVEmpty + st));
       };
       uint32_t g = 0, gs = 0, n_act = 0, n_it = 0;
+#ifdef HI_PAIR_TRACE
+      const unsigned long long cta_t0 = trace_globaltimer();
+      unsigned int cta_items = 0;
+#endif
       // The next item is decoded during the last two steps of the current one (plan entry at the top of step n-2, sequence
       // metadata at the top of step n-1: both loads complete behind the waits for P), so Q.K(0) and Q.K(1) of the next item
       // follow the last P.V without a decode in between.
@@ -511,7 +532,18 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         g += n_all;
         gs += n_t;
         if (n_t > 0) ++n_act;
+#ifdef HI_PAIR_TRACE
+        ++cta_items;
+#endif
       }
+#ifdef HI_PAIR_TRACE
+      if (t == 0 && lane == 0 && blockIdx.x < 1024) {
+        g_pair_cta_stats[blockIdx.x * 4 + 0] = cta_t0;
+        g_pair_cta_stats[blockIdx.x * 4 + 1] = trace_globaltimer();
+        g_pair_cta_stats[blockIdx.x * 4 + 2] = cta_items;
+        g_pair_cta_stats[blockIdx.x * 4 + 3] = g;
+      }
+#endif
     }
   } else {
     // ================================================ softmax + epilogue ===========================================
@@ -773,11 +805,12 @@ int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
   if (args.qk_work_hint > 0 && a.work_items != nullptr) {
     // CTA-steps: every work item walks its visible keys in 64-key steps, once per KV head
     const double total_steps = static_cast<double>(args.qk_work_hint) / kP2TileN * args.n_kv_heads;
-    // Items are claimed heaviest first, so a launch is balanced once no item is longer than one SM's share of the work: the
-    // chunk is that share.  (Measured on B200, BASELINE config 3: the chunked-prefill rows alone want 2 chunks - 0.154 ms
-    // against 0.159 / 0.160 with 1 / 3 - and the mixed batch none - 0.192 ms against 0.213 / 0.220 with 2 / 3; a chunk of
-    // half a share split both into 3 and paid for it in partial traffic and merge work.)
-    int chunk = static_cast<int>(total_steps / kSms) + 1;
+    // Items are claimed heaviest first and just in time, so a launch is balanced unless one item is much longer than an SM's
+    // share of the work: the chunk is 1.5 shares.  (Measured on B200, BASELINE config 3 with just-in-time claiming: the
+    // chunked-prefill rows alone - longest item 1.44 shares - run 0.1275 ms unsplit against 0.131 / 0.132 / 0.129 ms with
+    // 2 / 3 / 4 chunks, the mixed batch 0.153 ms unsplit against 0.175 / 0.193 with 2 / 3: partial traffic, the merge and the
+    // extra item boundaries cost more than the last few per cent of balance.)
+    int chunk = static_cast<int>(1.5 * total_steps / kSms) + 1;
     if (chunk < kMinTilesPerSplit) chunk = kMinTilesPerSplit;
     if (chunk < max_kv_tiles) n_splits = (max_kv_tiles + chunk - 1) / chunk;
   } else if (base_ctas < 2 * kSms) {
@@ -926,5 +959,10 @@ extern "C" int hi_debug_pair_trace(unsigned long long* records /* [6][8192] */, 
   if (cudaMemcpyFromSymbol(records, hi::g_pair_trace, sizeof(unsigned long long) * hi::kTraceRoles * hi::kTraceCap) != cudaSuccess) return -1;
   if (cudaMemcpyFromSymbol(counts, hi::g_pair_trace_n, sizeof(unsigned int) * hi::kTraceRoles) != cudaSuccess) return -1;
   return 0;
+}
+// Dev builds only: per-CTA {start ns, end ns, items, steps} of the last pair-kernel launch (load balance of the item walk).
+extern "C" int hi_debug_pair_cta_stats(unsigned long long* stats /* [1024][4] */) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(stats, hi::g_pair_cta_stats, sizeof(unsigned long long) * 1024 * 4) == cudaSuccess ? 0 : -1;
 }
 #endif

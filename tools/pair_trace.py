@@ -30,6 +30,9 @@ CASES = {
     "pre8k": ([(8192, 8192)], 28, 4), "cfg3p": ([(512, 512), (512, 2048), (512, 4096), (512, 8192)], 28, 4),
     "mha2k": ([(2048, 2048)] * 4, 32, 32),
 }
+_g = torch.Generator().manual_seed(0)
+_cfg3_dec = [(1, int(L)) for L in torch.randint(256, 8193, (48,), generator=_g).tolist()]
+CASES["cfg3mix"] = (_cfg3_dec + CASES["cfg3p"][0], 28, 4)
 
 
 def main():
@@ -53,6 +56,21 @@ def main():
     for _ in range(3):
         mha_varlen_fwd(out, q3, batch.key_cache, batch.value_cache, *meta, None, batch.q_max, batch.kv_max, 1 / math.sqrt(d), 0, -1, 0, 0, 4, plan, tt, work)
     torch.cuda.synchronize()
+    # ---- load balance of the item walk: per-CTA busy time, items and steps
+    stats = (ctypes.c_ulonglong * (1024 * 4))()
+    fs = _lib.lib.hi_debug_pair_cta_stats
+    fs.argtypes = [ctypes.c_void_p]
+    if fs(ctypes.byref(stats)) == 0:
+        rows = [(stats[4 * i], stats[4 * i + 1], stats[4 * i + 2], stats[4 * i + 3]) for i in range(148) if stats[4 * i + 1] > 0]
+        t_first = min(r[0] for r in rows)
+        ends = sorted((r[1] - t_first) / 1e3 for r in rows)
+        steps = sorted(r[3] for r in rows)
+        print(f"CTAs {len(rows)}: end time us min {ends[0]:.1f} median {ends[len(ends) // 2]:.1f} max {ends[-1]:.1f}; steps per CTA min {steps[0]} median {steps[len(steps) // 2]} max {steps[-1]} "
+              f"sum {sum(steps)}; items per CTA {min(r[2] for r in rows)}..{max(r[2] for r in rows)}")
+        worst = sorted(rows, key=lambda r: r[1])[-5:]
+        print("latest CTAs (end us, items, steps, us per step):", [(round((r[1] - t_first) / 1e3, 1), r[2], r[3], round((r[1] - r[0]) / 1e3 / max(r[3], 1), 3)) for r in worst])
+        best = sorted(rows, key=lambda r: r[1])[:5]
+        print("earliest CTAs (end us, items, steps, us per step):", [(round((r[1] - t_first) / 1e3, 1), r[2], r[3], round((r[1] - r[0]) / 1e3 / max(r[3], 1), 3)) for r in best])
     cap = 8192
     rec = (ctypes.c_ulonglong * (6 * cap))()
     cnt = (ctypes.c_uint * 6)()
