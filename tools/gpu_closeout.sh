@@ -1,5 +1,5 @@
 #!/bin/bash
-# GPU pass 12 (round-1 close-out): full gpu suite incl. the fuzz file, smoke, both bench arms, every config beside flashinfer,
+# GPU pass 12 (round-1 close-out, re-run after the just-in-time claiming change): full gpu suite incl. the fuzz file, smoke, both bench arms, every config beside flashinfer,
 # vision shapes, ncu launch list of the bench step and one --set full capture of the pair kernel on the config-3 mixed batch
 # and on 1k prefill.
 mkdir -p gpurun_out
@@ -9,9 +9,9 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smok
 timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$? lines=$(wc -l < gpurun_out/bench.json)"; cut -c1-300 gpurun_out/bench.json
 timeout 600 python bench.py --impl reference --steps 10 --warmup 3 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"; cut -c1-300 gpurun_out/bench_ref.json
 rm -f gpurun_out/configs.jsonl
-timeout 900 python tools/bench_configs.py --flashinfer > gpurun_out/configs_p12.jsonl 2> gpurun_out/configs_p12.err; echo "configs rc=$?"
-python tools/summarize_configs.py gpurun_out/configs_p12.jsonl | grep -E "cfg3|pre|cfg2_b"
-timeout 300 python tools/bench_vision.py > gpurun_out/vision_p12.jsonl 2> gpurun_out/vision_p12.err; cut -c1-250 gpurun_out/vision_p12.jsonl
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_pass12.csv python bench.py --steps 3 --warmup 3 > gpurun_out/bench_under_ncu.log 2>&1
+timeout 900 python tools/bench_configs.py --flashinfer > gpurun_out/configs_p17.jsonl 2> gpurun_out/configs_p17.err; echo "configs rc=$?"
+python tools/summarize_configs.py gpurun_out/configs_p17.jsonl | grep -E "cfg3|pre|cfg2_b"
+timeout 300 python tools/bench_vision.py > gpurun_out/vision_p17.jsonl 2> gpurun_out/vision_p17.err; cut -c1-250 gpurun_out/vision_p17.jsonl
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_pass17.csv python bench.py --steps 3 --warmup 3 > gpurun_out/bench_under_ncu.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:paged_attn_pair -s 50 -c 1 -f -o gpurun_out/pair_cfg3mix python tools/bench_configs.py --only cfg3mix > gpurun_out/ncu_pair_cfg3mix.log 2>&1; tail -n 2 gpurun_out/ncu_pair_cfg3mix.log | cut -c1-200
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:paged_attn_pair -s 30 -c 1 -f -o gpurun_out/pair_pre1k python tools/bench_configs.py --only pre1k > gpurun_out/ncu_pair_pre1k.log 2>&1; tail -n 2 gpurun_out/ncu_pair_pre1k.log | cut -c1-200
