@@ -136,6 +136,10 @@ def main():
         ("cfg2_b32", [(1, 2048)] * 32, 32, 32, [SIMT]),
         ("cfg2_ctx8k", [(1, 8192)] * 16, 32, 32, [SIMT, TC]),
         ("cfg3d", cfg3_dec, 28, 4, [SIMT, TC, DEC]),
+        ("gqa_b4_8k", [(1, 8192)] * 4, 28, 4, [DEC]),
+        ("gqa_b8_2k", [(1, 2048)] * 8, 28, 4, [DEC]),
+        ("gqa_b16_rag", [(1, 300 + 500 * i) for i in range(16)], 28, 4, [DEC]),
+        ("gqa72_b64_rag", [(1, 256 + 120 * i) for i in range(64)], 64, 8, [DEC]),
         ("cfg3p", cfg3_pre, 28, 4, [TC, PAIR]),
         ("cfg3mix", cfg3_dec + cfg3_pre, 28, 4, [AUTO, TC, PAIR]),
         ("pre256", [(256, 256)] * 32, 28, 4, [TC, PAIR]),
