@@ -98,7 +98,7 @@ extern "C" int hi_paged_attention(const HiAttnArgs* p, void* stream_) {
   HI_CUDA(cudaSetDevice(a.device));
 
   int path = a.path;
-  if (const char* env = getenv("HI_ATTN_PATH")) {  // test / profiling override: "simt" or "tc"
+  if (const char* env = tuning_env("HI_ATTN_PATH")) {  // test / profiling override: "simt" or "tc"
     if (env[0] == 's') path = HI_ATTN_SIMT;
     if (env[0] == 't') path = HI_ATTN_TCGEN05;
     if (env[0] == 'd') path = HI_ATTN_TCGEN05_DECODE;

@@ -416,7 +416,7 @@ int launch_attn_decode_tc(const HiAttnArgs& args, cudaStream_t stream) {
   }
   const int max_splits = (max_tiles + kMinTilesPerSplit - 1) / kMinTilesPerSplit;
   if (n_splits > max_splits) n_splits = max_splits;
-  if (const char* env = getenv("HI_DEC_SPLITS")) n_splits = atoi(env);
+  if (const char* env = tuning_env("HI_DEC_SPLITS")) n_splits = atoi(env);
   if (n_splits < 1) n_splits = 1;
   const int64_t per_split = static_cast<int64_t>(args.n_tokens) * args.n_qo_heads * (kDecD + 2) * 4;
   while (n_splits > 1 && (args.workspace == nullptr || per_split * n_splits > args.workspace_bytes)) --n_splits;

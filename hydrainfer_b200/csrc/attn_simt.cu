@@ -609,7 +609,7 @@ static int launch_simt_td(SimtArgs& a, const HiAttnArgs& args, cudaStream_t stre
   const int max_tiles = (args.max_kv_len + 15) / 16;
   int want_chunks = static_cast<int>((kTargetCtas + ctas_per_chunk - 1) / ctas_per_chunk);
   int min_chunk_tiles = kMinChunkTiles;
-  if (const char* env = getenv("HI_SIMT_MIN_CHUNK_TILES")) min_chunk_tiles = atoi(env) > 0 ? atoi(env) : min_chunk_tiles;  // tuning override
+  if (const char* env = tuning_env("HI_SIMT_MIN_CHUNK_TILES")) min_chunk_tiles = atoi(env) > 0 ? atoi(env) : min_chunk_tiles;  // tuning override
   const int max_chunks = (max_tiles + min_chunk_tiles - 1) / min_chunk_tiles;
   if (want_chunks > max_chunks) want_chunks = max_chunks;
   if (want_chunks < 1) want_chunks = 1;

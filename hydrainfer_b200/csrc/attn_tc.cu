@@ -546,7 +546,7 @@ int launch_attn_tc(const HiAttnArgs& args, cudaStream_t stream) {
   a.tq = kTileM / a.group;
   a.scale_log2 = args.softmax_scale * 1.4426950408889634f;
   {
-    const char* env = getenv("HI_TC_SERIALIZE");
+    const char* env = tuning_env("HI_TC_SERIALIZE");
     a.serialize = (env != nullptr && env[0] == '1') ? 1 : 0;
   }
 
@@ -561,7 +561,7 @@ int launch_attn_tc(const HiAttnArgs& args, cudaStream_t stream) {
     n_splits = static_cast<int>((kSplitTargetCtas + base_ctas - 1) / base_ctas);
     const int max_splits = (max_kv_tiles + kMinTilesPerSplit - 1) / kMinTilesPerSplit;
     if (n_splits > max_splits) n_splits = max_splits;
-    if (const char* env = getenv("HI_TC_SPLITS")) n_splits = atoi(env);  // tuning override
+    if (const char* env = tuning_env("HI_TC_SPLITS")) n_splits = atoi(env);  // tuning override
     if (n_splits < 1) n_splits = 1;
     // shrink to what the workspace can hold
     const int64_t per_split = static_cast<int64_t>(args.n_tokens) * args.n_qo_heads * (kHeadDim + 2) * 4;
@@ -587,7 +587,7 @@ int launch_attn_tc(const HiAttnArgs& args, cudaStream_t stream) {
   // Ring depth 1 = two co-resident CTAs per SM whose QK / softmax / PV phases overlap each other; measured better than
   // one CTA per SM with a 2- or 3-deep ring for both prefill and decode tiles (profiles/r01_notes.md).
   int stages = 1;
-  if (const char* env = getenv("HI_TC_STAGES")) stages = atoi(env);
+  if (const char* env = tuning_env("HI_TC_STAGES")) stages = atoi(env);
   if (args.dtype == HI_BF16) {
     rc = stages == 3 ? launch_tc_t<__nv_bfloat16, 3>(args, a, mq, mk, mv, stream)
        : stages == 2 ? launch_tc_t<__nv_bfloat16, 2>(args, a, mq, mk, mv, stream)

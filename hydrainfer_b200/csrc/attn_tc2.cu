@@ -761,7 +761,7 @@ static int launch_pair_t(int device, const P2Args& a, const CUtensorMap& mq, con
   static int n_sms = 0;
   if (n_sms == 0) HI_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device));
   int ctas = a.n_items < n_sms ? a.n_items : n_sms;
-  if (const char* env = getenv("HI_PAIR_CTAS")) ctas = atoi(env) > 0 ? atoi(env) : ctas;  // tuning / test override
+  if (const char* env = tuning_env("HI_PAIR_CTAS")) ctas = atoi(env) > 0 ? atoi(env) : ctas;  // tuning / test override
   const dim3 grid(ctas, 1, 1);
   timing_mark_start(stream);
   paged_attn_pair_kernel<T, NK, NV, PF, VL><<<grid, kP2Threads, L::kDynamicBytes, stream>>>(mq, mk, mv, a);
@@ -818,7 +818,7 @@ int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
     const int max_splits = (max_kv_tiles + kMinTilesPerSplit - 1) / kMinTilesPerSplit;
     if (n_splits > max_splits) n_splits = max_splits;
   }
-  if (const char* env = getenv("HI_TC_SPLITS")) n_splits = atoi(env);  // tuning / test override
+  if (const char* env = tuning_env("HI_TC_SPLITS")) n_splits = atoi(env);  // tuning / test override
   if (n_splits < 1) n_splits = 1;
   {
     const int64_t per_split = static_cast<int64_t>(args.n_tokens) * args.n_qo_heads * (kP2D + 2) * 4;
@@ -837,7 +837,7 @@ int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
   a.work_counter = nullptr;
   {
     const int64_t partial_bytes = a.n_splits > 1 ? static_cast<int64_t>(args.n_tokens) * args.n_qo_heads * a.n_splits * (kP2D + 2) * 4 : 0;
-    const char* env = getenv("HI_PAIR_STATIC");  // tuning / test override: static boustrophedon assignment
+    const char* env = tuning_env("HI_PAIR_STATIC");  // tuning / test override: static boustrophedon assignment
     if (args.workspace != nullptr && args.workspace_bytes >= partial_bytes + 512 && !(env != nullptr && env[0] == '1')) {
       a.work_counter = reinterpret_cast<unsigned int*>(static_cast<char*>(args.workspace) + ((args.workspace_bytes - 256) & ~int64_t(255)));
       HI_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned int), stream));
@@ -853,9 +853,9 @@ int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
   rc = pool_map(&mv, args.dtype, args.value_cache, n_slots, args.n_kv_heads, args.block_size);
   if (rc != HI_OK) return rc;
 
-  if (const char* env = getenv("HI_PAIR_DEBUG")) a.debug = atoi(env);
+  if (const char* env = tuning_env("HI_PAIR_DEBUG")) a.debug = atoi(env);
   int poly = 0;  // exponentials per 4 moved from MUFU to the FMA pipes (measured: no gain while the softmax warps have idle issue slots)
-  if (const char* env = getenv("HI_PAIR_POLY")) poly = atoi(env);  // tuning override
+  if (const char* env = tuning_env("HI_PAIR_POLY")) poly = atoi(env);  // tuning override
   if (args.dtype == HI_BF16) {
     rc = poly <= 0 ? launch_pair_t<__nv_bfloat16, 0>(args.device, a, mq, mk, mv, stream)
        : poly == 1 ? launch_pair_t<__nv_bfloat16, 1>(args.device, a, mq, mk, mv, stream)
@@ -934,7 +934,7 @@ int launch_varlen_pair(const HiVarlenArgs& v, cudaStream_t stream) {
   if (rc != HI_OK) return rc;
   rc = make_map_d(&mv, v.dtype, v.v, v.n_k_tokens, v.n_kv_heads, v.head_dim, v.v_row_stride, 1, kP2TileN);
   if (rc != HI_OK) return rc;
-  if (const char* env = getenv("HI_PAIR_DEBUG")) a.debug = atoi(env);
+  if (const char* env = tuning_env("HI_PAIR_DEBUG")) a.debug = atoi(env);
   return v.dtype == HI_BF16 ? launch_pair_t<__nv_bfloat16, 0, true>(v.device, a, mq, mk, mv, stream)
                             : launch_pair_t<__half, 0, true>(v.device, a, mq, mk, mv, stream);
 }

@@ -8,10 +8,18 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/hi_b200.h"
 
 namespace hi {
+
+// Tuning / test overrides come from the environment; an empty value means "not set" (HI_X= in a shell loop must not turn
+// into atoi("") == 0).
+inline const char* tuning_env(const char* name) {
+  const char* e = getenv(name);
+  return (e != nullptr && e[0] != '\0') ? e : nullptr;
+}
 
 // ---- error plumbing -------------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
