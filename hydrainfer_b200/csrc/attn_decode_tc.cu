@@ -396,10 +396,15 @@ int launch_attn_decode_tc(const HiAttnArgs& args, cudaStream_t stream) {
   a.block_size = args.block_size;
   a.scale_log2 = args.softmax_scale * 1.4426950408889634f;
 
-  // split-KV.  Measured on B200 (profiles/r01_notes.md): with >= 1 CTA per SM and sequences of similar length the kernel
-  // already streams at the HBM roofline and splitting only adds tail waves and merge traffic; ragged batches (longest
-  // sequence well above the mean) and launches with fewer CTAs than SMs want ~600 CTAs of equal work.
-  constexpr int kMinTilesPerSplit = 2;  // never finer than 256 tokens
+  // split-KV.  With >= 1 CTA per SM and sequences of similar length the kernel already streams at the HBM roofline and
+  // splitting only adds tail waves and merge traffic; ragged batches (longest sequence well above the mean) and launches
+  // with fewer CTAs than SMs are cut into ~300 CTAs of equal work, never finer than 4 tiles (512 tokens) and never coarser
+  // than 16 (larger launches run several waves and want the finer grain for balance).  Swept on B200 with the host out of
+  // the picture (CUDA graph of 10 calls, profiles/r01_decode_tc_split_sweep.txt): 4 x 8k rows 16.8 us at 16 splits (22.0 at
+  // 32, 86 unsplit), 16 ragged rows 32.2 us at 8 (36.9 at 16), the 48 ragged config-3 rows 69.3 us at 3 (75.5 at 6), 64 ragged
+  // rows of the 72B shape 175.8 us at 4-6 (179 at 3).
+  constexpr int kMinTilesPerSplit = 4, kMaxTilesPerSplit = 16;
+  constexpr double kTargetCtas = 300.0;
   const int64_t base_ctas = static_cast<int64_t>(args.n_tokens) * args.n_kv_heads;
   const int max_tiles = (args.max_kv_len + kDecTile - 1) / kDecTile;
   // mean tiles per row from the block-table size (rows of one sequence share its blocks: exact for decode batches)
@@ -410,8 +415,9 @@ int launch_attn_decode_tc(const HiAttnArgs& args, cudaStream_t stream) {
   int n_splits = 1;
   if (base_ctas < 148 || max_tiles > 1.3 * mean_tiles) {
     const double total_work = mean_tiles * static_cast<double>(base_ctas);  // tile-CTA units
-    int tps = static_cast<int>(total_work / 600.0 + 0.999);
+    int tps = static_cast<int>(total_work / kTargetCtas + 0.999);
     if (tps < kMinTilesPerSplit) tps = kMinTilesPerSplit;
+    if (tps > kMaxTilesPerSplit) tps = kMaxTilesPerSplit;
     n_splits = (max_tiles + tps - 1) / tps;
   }
   const int max_splits = (max_tiles + kMinTilesPerSplit - 1) / kMinTilesPerSplit;

@@ -544,7 +544,8 @@ static dim3 merge_grid(const SimtArgs& a) {
 // ---- host side ----------------------------------------------------------------------------------------------------
 
 constexpr int kTargetCtas = 148 * 32;  // enough CTAs that the last partial wave is a few % of the launch
-constexpr int kMinChunkTiles = 16;     // never split finer than 256 tokens
+constexpr int kMinChunkTiles = 32;     // never split finer than 512 tokens (graph-timed sweep on B200, ctx 2048 MHA: batch 1 / 4 /
+                                       // 8 / 16 run 10.5 / 31.8 / 50.3 / 88.4 us at 32 against 11.1 / 33.1 / 51.0 / 90.5 at 16)
 
 int64_t simt_workspace_bytes(int head_dim) {
   // Partials exist only when n_chunks > 1, i.e. when rows*heads/G < kTargetCtas; then

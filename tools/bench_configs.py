@@ -53,6 +53,36 @@ def time_call(fn, iters=20, warmup=3):
     return ts[len(ts) // 2], ts[0]
 
 
+def time_graph(fn, calls=10, replays=7):
+    """GPU time per call with the host out of the picture: `calls` invocations captured into one CUDA graph, replayed
+    `replays` times, median.  For launches shorter than the Python + launch cost of a call (small decode batches) the
+    per-call event timing above measures the host, not the kernels."""
+    stream = torch.cuda.Stream()
+    stream.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(stream):
+        fn()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            for _ in range(calls):
+                fn()
+    torch.cuda.synchronize()
+    graph.replay()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(replays):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        graph.replay()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e) / calls)
+    return sorted(ts)[len(ts) // 2]
+
+
+USE_GRAPH = False
+
+
 def run_case(name, seq_lens, hq, hkv, paths, out_lines, flashinfer_cmp=False, dtype=torch.bfloat16):
     d, bs = 128, 16
     batch = make_batch(seq_lens, hq, hkv, d, bs, dtype=dtype, device=DEV, gen_device=DEV, seed=0)
@@ -79,8 +109,15 @@ def run_case(name, seq_lens, hq, hkv, paths, out_lines, flashinfer_cmp=False, dt
         except RuntimeError as e:
             results[pname] = {"error": str(e)[:200]}
             continue
+        if USE_GRAPH:
+            try:
+                med = best = time_graph(fn)
+            except RuntimeError as e:
+                results[pname] = {"error": "graph: " + str(e)[:200]}
+                continue
         results[pname] = {"ms": med, "ms_best": best, "GBs": nbytes / med / 1e6, "hbm_frac": nbytes / med / 1e6 / HBM_PEAK,
-                          "TFLOPs": flops / med / 1e9, "tc_frac": flops / med / 1e9 / TC_PEAK, "tokens_per_s": t / med * 1e3}
+                          "TFLOPs": flops / med / 1e9, "tc_frac": flops / med / 1e9 / TC_PEAK, "tokens_per_s": t / med * 1e3,
+                          "timing": "cuda graph of 10 calls" if USE_GRAPH else "events around each call"}
         results[pname + "_out"] = out.float().abs().mean().item()
     if flashinfer_cmp:
         try:
@@ -121,7 +158,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
     ap.add_argument("--flashinfer", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="time our paths as a CUDA graph of 10 calls (GPU time without host launch cost)")
     args = ap.parse_args()
+    global USE_GRAPH
+    USE_GRAPH = args.graph
     only = set(args.only.split(",")) if args.only else None
     SIMT, TC, AUTO, DEC, PAIR = ("simt", 1), ("tc", 2), ("auto", 0), ("dec", 3), ("pair", 4)
     g = torch.Generator().manual_seed(0)
