@@ -243,6 +243,32 @@ def test_pair_kernel_direct_and_split_tiles_share_a_launch(monkeypatch, splits):
         check_batch(batch, [TC, DEC] if heads[0] // heads[1] <= 16 else [TC], f"merge of the other tcgen05 paths splits={splits} heads={heads}")
 
 
+@pytest.mark.parametrize("static", ["0", "1"])
+@pytest.mark.parametrize("ctas", ["1", "3", "148"])
+def test_pair_kernel_item_walk_variants(monkeypatch, static, ctas):
+    """The persistent pair kernel walks its work items with a dynamic counter (items claimed just in time) or, without a
+    workspace counter, in a static boustrophedon order; a launch may have far fewer CTAs than items (many rounds per CTA).
+    Same answer in every combination, with and without the host plan."""
+    from hydrainfer_b200.layer import AttentionParametersBuilder, CausalGroupedQueryPageAttention, CausalGroupedQueryPageAttentionConfig
+    from hydrainfer_b200.memory import KVCache
+    monkeypatch.setenv("HI_PAIR_STATIC", static)
+    monkeypatch.setenv("HI_PAIR_CTAS", ctas)
+    seq_lens = [(1, 700), (130, 130), (75, 900), (1, 64), (300, 300), (1, 1), (40, 1300)]
+    for heads in ((28, 4), (8, 8)):
+        batch = make_batch(seq_lens, heads[0], heads[1], 128, 16, dtype=torch.bfloat16, seed=44)
+        fp32 = check_batch(batch, [PAIR], f"item walk static={static} ctas={ctas} heads={heads} (no plan)")
+        builder = AttentionParametersBuilder(heads[0], heads[1], 128, 16, torch.device(DEV))
+        for req in batch.requests():
+            builder.add_request(*req)
+        builder.add_kv_cache(KVCache(batch.key_cache.to(DEV), batch.value_cache.to(DEV)))
+        params = builder.build_attention_parameters()[0]
+        layer = CausalGroupedQueryPageAttention(CausalGroupedQueryPageAttentionConfig(heads[0], heads[1], 128))
+        layer.handler.path = PAIR
+        out = layer(batch.query.to(DEV), batch.key.to(DEV), batch.value.to(DEV), params).o
+        torch.cuda.synchronize()
+        assert_close_to_fp32(out, fp32, batch.dtype, f"item walk static={static} ctas={ctas} heads={heads} (plan)")
+
+
 def test_host_plan_ragged_prefill_through_the_layer(monkeypatch):
     """AttentionParametersBuilder's plan (cost-sorted work items + work hint) drives the pair kernel's grid and split-KV chunk:
     a ragged chunked-prefill + decode batch must give the same answer with and without it, for forced split counts too."""
