@@ -14,8 +14,13 @@ from ... import _lib
 _workspaces: dict[torch.device, Tensor] = {}
 
 
+_workspace_need: dict[int, int] = {}
+
+
 def _workspace(dev: torch.device, head_dim: int) -> Tensor:
-    need = _lib.lib.hi_attention_workspace_bytes(0, 0, head_dim, 0)
+    need = _workspace_need.get(head_dim)
+    if need is None:
+        need = _workspace_need[head_dim] = int(_lib.lib.hi_attention_workspace_bytes(0, 0, head_dim, 0))
     ws = _workspaces.get(dev)
     if ws is None or ws.numel() < need:
         ws = torch.empty(need, dtype=torch.uint8, device=dev)  # persistent, like flashinfer's workspace (executor.py:99)
@@ -50,23 +55,29 @@ def mha_varlen_fwd(out: Tensor, q: Tensor, k: Tensor, v: Tensor, cu_seqlens_q: T
     if alibi_slopes is not None or softcap != 0 or window_size_left != -1 or window_size_right != 0:
         raise RuntimeError("mha_varlen_fwd: alibi / softcap / sliding window are not used by the paged attention layer and are not implemented")
     dev = _lib.require_cuda(out, q, k, v, cu_seqlens_q, cu_seqlens_k, block_table_, cu_block_lens)
-    if q.dim() != 3 or out.shape != q.shape or q.stride(-1) != 1 or q.stride(-2) != q.size(-1) or out.stride(-1) != 1 or out.stride(-2) != out.size(-1):
+    # (this function runs once per layer per step: the checks below are written to cost a few microseconds in all)
+    q_shape, k_shape = q.shape, k.shape
+    if len(q_shape) != 3 or out.shape != q_shape:
         raise RuntimeError("mha_varlen_fwd: q and out must be [n_tokens, n_heads, head_dim], contiguous over the last two dims")
-    if k.dim() != 4 or k.shape != v.shape or not k.is_contiguous() or not v.is_contiguous():
+    n_tokens, n_qo_heads, head_dim = q_shape
+    if not (q.is_contiguous() or (q.stride(2) == 1 and q.stride(1) == head_dim)) or not (out.is_contiguous() or (out.stride(2) == 1 and out.stride(1) == head_dim)):
+        raise RuntimeError("mha_varlen_fwd: q and out must be [n_tokens, n_heads, head_dim], contiguous over the last two dims")
+    if len(k_shape) != 4 or k_shape != v.shape or not k.is_contiguous() or not v.is_contiguous():
         raise RuntimeError("mha_varlen_fwd: k and v must be contiguous paged caches [n_blocks, block_size, n_kv_heads, head_dim]")
-    if not (q.dtype == out.dtype == k.dtype == v.dtype):
+    dtype = q.dtype
+    if out.dtype != dtype or k.dtype != dtype or v.dtype != dtype:
         raise RuntimeError("mha_varlen_fwd: dtype mismatch")
-    for name, t in (("cu_seqlens_q", cu_seqlens_q), ("cu_seqlens_k", cu_seqlens_k), ("block_table", block_table_), ("cu_block_lens", cu_block_lens)):
-        if t.dtype != torch.int32 or not t.is_contiguous():
-            raise RuntimeError(f"mha_varlen_fwd: {name} must be a contiguous int32 tensor")
-    n_tokens, n_qo_heads, head_dim = q.shape
-    n_blocks, block_size, n_kv_heads, kd = k.shape
+    i32 = torch.int32
+    if (cu_seqlens_q.dtype != i32 or cu_seqlens_k.dtype != i32 or block_table_.dtype != i32 or cu_block_lens.dtype != i32
+            or not (cu_seqlens_q.is_contiguous() and cu_seqlens_k.is_contiguous() and block_table_.is_contiguous() and cu_block_lens.is_contiguous())):
+        raise RuntimeError("mha_varlen_fwd: cu_seqlens_q, cu_seqlens_k, block_table and cu_block_lens must be contiguous int32 tensors")
+    n_blocks, block_size, n_kv_heads, kd = k_shape
     if kd != head_dim or n_qo_heads % n_kv_heads != 0:
-        raise RuntimeError(f"mha_varlen_fwd: head mismatch q {tuple(q.shape)} cache {tuple(k.shape)}")
+        raise RuntimeError(f"mha_varlen_fwd: head mismatch q {tuple(q_shape)} cache {tuple(k_shape)}")
     n_seqs = cu_seqlens_q.shape[0] - 1
     if cu_seqlens_k.shape[0] != n_seqs + 1 or cu_block_lens.shape[0] != n_seqs + 1:
         raise RuntimeError("mha_varlen_fwd: cu_seqlens_q, cu_seqlens_k and cu_block_lens must all have batch + 1 entries")
-    if work_items is not None and (work_items.dtype != torch.int32 or work_items.device != dev or work_items.dim() != 2 or work_items.shape[1] != 2 or not work_items.is_contiguous()):
+    if work_items is not None and (work_items.dtype != i32 or work_items.device != dev or work_items.dim() != 2 or work_items.shape[1] != 2 or not work_items.is_contiguous()):
         raise RuntimeError("mha_varlen_fwd: work_items must be a contiguous int32 device tensor of shape [n_items, 2]")
     ws = _workspace(dev, head_dim)
     row = n_qo_heads * head_dim

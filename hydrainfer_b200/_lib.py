@@ -140,14 +140,25 @@ def dtype_code(dtype: torch.dtype) -> int:
 
 
 def require_cuda(*tensors: torch.Tensor) -> torch.device:
-    dev = tensors[0].device
+    """All tensors on one CUDA device (the shims call this on every launch: integer device indices, no torch.device
+    objects, keep it to a fraction of a microsecond per tensor)."""
+    first = tensors[0]
+    if not first.is_cuda:
+        raise RuntimeError("hi_b200: the CUDA extension only accepts CUDA tensors; there is no CPU fallback")
+    idx = first.get_device()
     for t in tensors:
-        if t.device.type != "cuda":
+        if not t.is_cuda:
             raise RuntimeError("hi_b200: the CUDA extension only accepts CUDA tensors; there is no CPU fallback")
-        if t.device != dev:
-            raise RuntimeError(f"hi_b200: tensors on different devices ({t.device} vs {dev})")
-    return dev
+        if t.get_device() != idx:
+            raise RuntimeError(f"hi_b200: tensors on different devices ({t.device} vs {first.device})")
+    return first.device
+
+
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 
 
 def current_stream_ptr(device: torch.device) -> int:
+    """cudaStream_t of torch's current stream on `device` (what at::cuda::getCurrentCUDAStream() is to the reference)."""
+    if _raw_stream is not None:
+        return _raw_stream(device.index if device.index is not None else torch.cuda.current_device())
     return torch.cuda.current_stream(device).cuda_stream
