@@ -741,6 +741,63 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   }
 }
 
+// ---- plan on the device --------------------------------------------------------------------------------------------------
+// Callers at the bare mha_varlen_fwd seam bring no host plan and their sequence lengths live in device memory.  One CTA builds
+// the list the host plan would have held: every pair of tiles of every sequence as (sequence, pair), heaviest first
+// (counting sort on the number of keys the pair's last token sees, kPlanBuckets buckets, order inside a bucket arbitrary -
+// results never depend on the order), padded up to the host-known bound n_slots = n_seqs + n_tokens / pair_tokens with
+// entries whose pair index lies beyond any sequence (the kernel decodes those as empty items).  Also zeroes the work counter.
+constexpr int kPlanThreads = 1024, kPlanBuckets = 1024;
+__global__ void __launch_bounds__(kPlanThreads) p2_plan_kernel(const int32_t* __restrict__ q_cu, const int32_t* __restrict__ kv_cu, int n_seqs,
+                                                              int pair_tokens, int max_kv_len, int n_slots, int32_t* __restrict__ work_items,
+                                                              unsigned int* __restrict__ work_counter) {
+  __shared__ int hist[kPlanBuckets];
+  __shared__ int total;
+  const int width = max_kv_len / kPlanBuckets + 1;  // keys per bucket
+  for (int i = threadIdx.x; i < kPlanBuckets; i += kPlanThreads) hist[i] = 0;
+  if (threadIdx.x == 0) {
+    total = 0;
+    if (work_counter != nullptr) *work_counter = 0u;
+  }
+  __syncthreads();
+  auto bucket_of = [&](int cost) { return min(max(cost, 0) / width, kPlanBuckets - 1); };
+  // a warp per sequence, its lanes over the sequence's pairs: one 8k-token prefill and a thousand decode rows both take a
+  // few dozen iterations
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = kPlanThreads / 32;
+  for (int b = warp; b < n_seqs; b += n_warps) {
+    const int q = q_cu[b + 1] - q_cu[b], kv = kv_cu[b + 1] - kv_cu[b];
+    const int n_pairs = (q + pair_tokens - 1) / pair_tokens;
+    for (int p = lane; p < n_pairs; p += 32) atomicAdd(&hist[bucket_of(kv - q + min(q, (p + 1) * pair_tokens))], 1);
+    if (lane == 0) atomicAdd(&total, n_pairs);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {  // exclusive scan from the heaviest bucket down: hist[k] becomes the first slot of bucket k
+    int run = 0;
+    for (int k = kPlanBuckets - 1; k >= 0; --k) {
+      const int c = hist[k];
+      hist[k] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  for (int b = warp; b < n_seqs; b += n_warps) {
+    const int q = q_cu[b + 1] - q_cu[b], kv = kv_cu[b + 1] - kv_cu[b];
+    const int n_pairs = (q + pair_tokens - 1) / pair_tokens;
+    for (int p = lane; p < n_pairs; p += 32) {
+      const int pos = atomicAdd(&hist[bucket_of(kv - q + min(q, (p + 1) * pair_tokens))], 1);
+      if (pos < n_slots) {
+        work_items[2 * pos] = b;
+        work_items[2 * pos + 1] = p;
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = total + threadIdx.x; i < n_slots; i += kPlanThreads) {
+    work_items[2 * i] = 0;
+    work_items[2 * i + 1] = 1 << 20;  // beyond the last pair of any sequence: an empty item
+  }
+}
+
 bool attn_pair_supported(const HiAttnArgs& args) {
   const int group = args.n_kv_heads > 0 ? args.n_qo_heads / args.n_kv_heads : 0;
   return (args.dtype == HI_F16 || args.dtype == HI_BF16) && args.head_dim == kP2D && group >= 1 && group <= kP2TileM &&
@@ -786,7 +843,8 @@ int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
   a.kv_cu = args.kv_cu_seq_lens;
   a.block_tables = args.block_tables;
   a.cu_blocks = args.cu_blocks_lens;
-  a.work_items = (args.work_items != nullptr && args.n_work_items > 0 && args.work_tile_tokens == 2 * (kP2TileM / (args.n_qo_heads / args.n_kv_heads))) ? args.work_items : nullptr;
+  const bool host_plan = args.work_items != nullptr && args.n_work_items > 0 && args.work_tile_tokens == 2 * (kP2TileM / (args.n_qo_heads / args.n_kv_heads));
+  a.work_items = host_plan ? args.work_items : nullptr;
   a.n_qo_heads = args.n_qo_heads;
   a.n_kv_heads = args.n_kv_heads;
   a.group = args.n_qo_heads / args.n_kv_heads;
@@ -801,8 +859,23 @@ int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
   constexpr int kSms = 148;
   constexpr int kMinTilesPerSplit = 4;   // never finer than 256 tokens
   const int n_pairs = (args.max_q_len + 2 * a.tq - 1) / (2 * a.tq);
-  const int64_t base_ctas = a.work_items != nullptr ? static_cast<int64_t>(args.n_work_items) * args.n_kv_heads
-                                                    : static_cast<int64_t>(n_pairs) * args.n_kv_heads * args.n_seqs;
+  // Without a host plan the list is built on the device (p2_plan_kernel) in the tail of the workspace, in front of the work
+  // counter; its length is the host-known bound n_seqs + n_tokens / pair_tokens.
+  int64_t n_list = host_plan ? args.n_work_items : 0;
+  int32_t* dev_plan = nullptr;
+  {
+    const char* env = tuning_env("HI_PAIR_DEVICE_PLAN");  // tuning / test override: "0" walks the tiles in sequence order
+    const int64_t bound = static_cast<int64_t>(args.n_seqs) + args.n_tokens / (2 * a.tq);
+    const int64_t plan_bytes = (bound * 8 + 255) & ~int64_t(255);
+    if (!host_plan && args.max_q_len > 1 && args.workspace != nullptr && args.workspace_bytes >= 2 * plan_bytes + (int64_t(1) << 20) &&
+        bound < (int64_t(1) << 24) && !(env != nullptr && env[0] == '0')) {
+      dev_plan = reinterpret_cast<int32_t*>(static_cast<char*>(args.workspace) + ((args.workspace_bytes - 256) & ~int64_t(255)) - plan_bytes);
+      a.work_items = dev_plan;
+      n_list = bound;
+    }
+  }
+  const int64_t plan_tail = dev_plan != nullptr ? ((static_cast<int64_t>(n_list) * 8 + 255) & ~int64_t(255)) : 0;  // workspace bytes the list takes
+  const int64_t base_ctas = a.work_items != nullptr ? n_list * args.n_kv_heads : static_cast<int64_t>(n_pairs) * args.n_kv_heads * args.n_seqs;
   const int max_kv_tiles = (args.max_kv_len + kP2TileN - 1) / kP2TileN;
   int n_splits = 1;
   if (args.qk_work_hint > 0 && a.work_items != nullptr) {
@@ -825,7 +898,7 @@ int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
   if (n_splits < 1) n_splits = 1;
   {
     const int64_t per_split = static_cast<int64_t>(args.n_tokens) * args.n_qo_heads * (kP2D + 2) * 4;
-    while (n_splits > 1 && (args.workspace == nullptr || per_split * n_splits > args.workspace_bytes)) --n_splits;
+    while (n_splits > 1 && (args.workspace == nullptr || per_split * n_splits + plan_tail + 512 > args.workspace_bytes)) --n_splits;
   }
   a.tiles_per_split = (max_kv_tiles + n_splits - 1) / n_splits;
   a.n_splits = (max_kv_tiles + a.tiles_per_split - 1) / a.tiles_per_split;
@@ -834,6 +907,10 @@ int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
     a.part_o = static_cast<float*>(args.workspace);
     a.part_ml = a.part_o + entries * kP2D;
   }
+  if (base_ctas * a.n_splits > 0x7fffffff) {
+    set_error("paged_attention: %lld work items exceed the int32 range", static_cast<long long>(base_ctas * a.n_splits));
+    return HI_ERR_INVALID_ARGUMENT;
+  }
   a.max_pairs = n_pairs;
   a.n_items = static_cast<int>(base_ctas * a.n_splits);
   // dynamic work distribution: a counter in the last 256 bytes of the workspace, zeroed in stream order before the launch
@@ -841,10 +918,16 @@ int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
   {
     const int64_t partial_bytes = a.n_splits > 1 ? static_cast<int64_t>(args.n_tokens) * args.n_qo_heads * a.n_splits * (kP2D + 2) * 4 : 0;
     const char* env = tuning_env("HI_PAIR_STATIC");  // tuning / test override: static boustrophedon assignment
-    if (args.workspace != nullptr && args.workspace_bytes >= partial_bytes + 512 && !(env != nullptr && env[0] == '1')) {
+    if (args.workspace != nullptr && args.workspace_bytes >= partial_bytes + plan_tail + 512 && !(env != nullptr && env[0] == '1')) {
       a.work_counter = reinterpret_cast<unsigned int*>(static_cast<char*>(args.workspace) + ((args.workspace_bytes - 256) & ~int64_t(255)));
-      HI_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned int), stream));
+      if (dev_plan == nullptr) HI_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned int), stream));  // else the plan kernel zeroes it
     }
+  }
+  if (dev_plan != nullptr) {
+    p2_plan_kernel<<<1, kPlanThreads, 0, stream>>>(args.q_cu_seq_lens, args.kv_cu_seq_lens, args.n_seqs, 2 * a.tq, args.max_kv_len,
+                                                   static_cast<int>(n_list), dev_plan, a.work_counter);
+    note_launch();
+    HI_CUDA(cudaGetLastError());
   }
 
   CUtensorMap mq, mk, mv;

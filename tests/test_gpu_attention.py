@@ -269,6 +269,22 @@ def test_pair_kernel_item_walk_variants(monkeypatch, static, ctas):
         assert_close_to_fp32(out, fp32, batch.dtype, f"item walk static={static} ctas={ctas} heads={heads} (plan)")
 
 
+@pytest.mark.parametrize("device_plan", ["1", "0"])
+def test_plan_built_on_the_device_for_the_bare_seam(monkeypatch, device_plan):
+    """mha_varlen_fwd without a host plan (the reference's own call, 16 positional arguments): the tile list is built by a
+    one-CTA kernel from the device-side sequence lengths (counting sort, heaviest first, padded with empty items).  More
+    sequences than the kernel has warps, a prefill with more pairs than a warp has lanes, empty and one-token sequences."""
+    monkeypatch.setenv("HI_PAIR_DEVICE_PLAN", device_plan)
+    seq_lens = [(1, 37 + 61 * i) for i in range(40)] + [(1300, 1300), (1, 1), (2, 2), (90, 400), (700, 2500)]
+    for heads in ((28, 4), (8, 8)):
+        batch = make_batch(seq_lens, heads[0], heads[1], 128, 16, dtype=torch.bfloat16, seed=45)
+        check_batch(batch, [PAIR, 0], f"device plan={device_plan} heads={heads}")
+    for splits in ("2", "3"):
+        monkeypatch.setenv("HI_TC_SPLITS", splits)
+        batch = make_batch(seq_lens[30:], 28, 4, 128, 16, dtype=torch.bfloat16, seed=46)
+        check_batch(batch, [PAIR], f"device plan={device_plan} splits={splits}")
+
+
 def test_host_plan_ragged_prefill_through_the_layer(monkeypatch):
     """AttentionParametersBuilder's plan (cost-sorted work items + work hint) drives the pair kernel's grid and split-KV chunk:
     a ragged chunked-prefill + decode batch must give the same answer with and without it, for forced split counts too."""
