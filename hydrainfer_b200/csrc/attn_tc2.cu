@@ -747,7 +747,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
 // (counting sort on the number of keys the pair's last token sees, kPlanBuckets buckets, order inside a bucket arbitrary -
 // results never depend on the order), padded up to the host-known bound n_slots = n_seqs + n_tokens / pair_tokens with
 // entries whose pair index lies beyond any sequence (the kernel decodes those as empty items).  Also zeroes the work counter.
-constexpr int kPlanThreads = 1024, kPlanBuckets = 1024;
+constexpr int kPlanThreads = 1024, kPlanBuckets = 1024;  // 32 buckets per lane of the scanning warp
 __global__ void __launch_bounds__(kPlanThreads) p2_plan_kernel(const int32_t* __restrict__ q_cu, const int32_t* __restrict__ kv_cu, int n_seqs,
                                                               int pair_tokens, int max_kv_len, int n_slots, int32_t* __restrict__ work_items,
                                                               unsigned int* __restrict__ work_counter) {
@@ -771,11 +771,23 @@ __global__ void __launch_bounds__(kPlanThreads) p2_plan_kernel(const int32_t* __
     if (lane == 0) atomicAdd(&total, n_pairs);
   }
   __syncthreads();
-  if (threadIdx.x == 0) {  // exclusive scan from the heaviest bucket down: hist[k] becomes the first slot of bucket k
-    int run = 0;
-    for (int k = kPlanBuckets - 1; k >= 0; --k) {
-      const int c = hist[k];
-      hist[k] = run;
+  if (warp == 0) {  // exclusive scan from the heaviest bucket down: hist[k] becomes the first slot of bucket k
+    constexpr int kPer = kPlanBuckets / 32;
+    const int top = kPlanBuckets - 1 - lane * kPer;  // lane 0 owns the heaviest kPer buckets
+    int mine = 0;
+#pragma unroll 8
+    for (int i = 0; i < kPer; ++i) mine += hist[top - i];
+    int before = mine;  // inclusive scan over the lanes, then shifted
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, before, off);
+      if (lane >= off) before += up;
+    }
+    int run = before - mine;
+#pragma unroll 8
+    for (int i = 0; i < kPer; ++i) {
+      const int c = hist[top - i];
+      hist[top - i] = run;
       run += c;
     }
   }
