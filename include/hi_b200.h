@@ -170,7 +170,9 @@ typedef struct HiAttnArgs {
    * can also enumerate the query tiles of the batch, sorted by cost, the way flashinfer's plan() does for the reference
    * (causal_attention.py:171-195).  The plan steers work order, grid size and split-KV only; results never depend on it.
    * Tiles are runs of hi_attention_tile_tokens(n_qo_heads, n_kv_heads) consecutive query tokens of one sequence. */
-  const int32_t* work_items; /* [dev] [n_work_items][2] = (sequence, tile index within the sequence), heaviest first; NULL = none */
+  const int32_t* work_items; /* [dev] [n_work_items][2] = (sequence, tile index within the sequence), heaviest first; NULL = none:
+                                batches with prefill rows then get the same list from a one-CTA kernel that sorts the tiles
+                                on the device (in the tail of `workspace`; one extra launch of a few microseconds) */
   int64_t qk_work_hint;      /* sum over the work items of the number of keys the item walks, i.e. of
                                 L_b - q_b + min(q_b, (tile + 1) * tile_tokens); 0 = unknown */
   int32_t n_work_items;
