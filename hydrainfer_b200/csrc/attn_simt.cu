@@ -609,7 +609,10 @@ static int launch_simt_td(SimtArgs& a, const HiAttnArgs& args, cudaStream_t stre
   const int64_t ctas_per_chunk = static_cast<int64_t>(a.n_tokens) * a.n_kv_heads * (a.group / G);
   const int max_tiles = (args.max_kv_len + 15) / 16;
   int want_chunks = static_cast<int>((kTargetCtas + ctas_per_chunk - 1) / ctas_per_chunk);
-  int min_chunk_tiles = kMinChunkTiles;
+  // 512 tokens for a single row (batch 1 wants every SM it can get), 768 once there are a few rows: graph-timed on B200 at
+  // ctx 2048 MHA, batch 4 / 8 / 16 run 28.5 / 47.6 / 86.9 us at 48 tiles against 31.8 / 50.3 / 88.4 at 32, batch 1 10.5 at 32
+  // against 12.6 at 48
+  int min_chunk_tiles = ctas_per_chunk < 64 ? kMinChunkTiles : kMinChunkTiles + 16;
   if (const char* env = tuning_env("HI_SIMT_MIN_CHUNK_TILES")) min_chunk_tiles = atoi(env) > 0 ? atoi(env) : min_chunk_tiles;  // tuning override
   const int max_chunks = (max_tiles + min_chunk_tiles - 1) / min_chunk_tiles;
   if (want_chunks > max_chunks) want_chunks = max_chunks;
