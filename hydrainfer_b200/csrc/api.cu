@@ -48,7 +48,6 @@ int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream);
 bool attn_pair_supported(const HiAttnArgs& args);
 int launch_varlen_pair(const HiVarlenArgs& args, cudaStream_t stream);
 int64_t simt_workspace_bytes(int head_dim);
-int64_t tc_workspace_bytes();
 
 }  // namespace hi
 
@@ -57,11 +56,22 @@ extern "C" int hi_abi_version(void) { return HI_B200_ABI_VERSION; }
 extern "C" int hi_last_launch_count(void) { return hi::g_launches; }
 
 extern "C" int64_t hi_attention_workspace_bytes(int32_t n_tokens, int32_t n_qo_heads, int32_t head_dim, int32_t max_kv_len) {
-  (void)n_tokens;
-  (void)n_qo_heads;
-  (void)max_kv_len;
-  int64_t need = hi::simt_workspace_bytes(head_dim > 0 ? head_dim : 128);
-  if (hi::tc_workspace_bytes() > need) need = hi::tc_workspace_bytes();
+  // Upper bound over every kernel's split rule.  The finest any of them cuts is 256 keys per split (pair / tile kernels; the
+  // decode kernels stop at 512) and the partials of one launch never exceed kMaxPartialBytes (common.cuh); on top come the
+  // device-built plan (at most n_seqs + n_tokens / tile <= 2 * n_tokens entries of 8 bytes, the launcher wants room for it
+  // twice plus 1 MiB) and the work counter in the tail.  Non-positive extents ask for the bound of ANY launch.
+  using namespace hi;
+  const int d = head_dim > 0 ? head_dim : 128;
+  int64_t partial = kMaxPartialBytes;
+  if (n_tokens > 0 && n_qo_heads > 0 && max_kv_len > 0) {
+    const int64_t max_splits = (static_cast<int64_t>(max_kv_len) + 255) / 256;
+    const int64_t per_split = partial_bytes_per_split(n_tokens, n_qo_heads, d);
+    if (per_split > kMaxPartialBytes) partial = 0;                       // cap_splits() leaves such a launch unsplit
+    else if (per_split * max_splits < kMaxPartialBytes) partial = per_split * max_splits;
+  }
+  if (partial < simt_workspace_bytes(d)) partial = simt_workspace_bytes(d);  // the CUDA-core kernel's own bound (attn_simt.cu)
+  const int64_t plan = n_tokens > 0 ? 2 * ((static_cast<int64_t>(n_tokens) * 16 + 255) & ~int64_t(255)) : (int64_t(2) << 20);
+  const int64_t need = partial + plan + (int64_t(1) << 20) + kWorkspaceTailBytes;
   return (need + 255) / 256 * 256;
 }
 
@@ -95,7 +105,7 @@ extern "C" int hi_paged_attention(const HiAttnArgs* p, void* stream_) {
                "paged_attention: tensors must be 16-byte aligned");
   HI_CHECK_ARG((a.q_row_stride * es) % 16 == 0 && (a.out_row_stride * es) % 16 == 0,
                "paged_attention: row strides must be multiples of 16 bytes");
-  HI_CUDA(cudaSetDevice(a.device));
+  HI_DEVICE_GUARD(a.device);
 
   int path = a.path;
   if (const char* env = tuning_env("HI_ATTN_PATH")) {  // test / profiling override: "simt" or "tc"
@@ -145,7 +155,7 @@ extern "C" int hi_varlen_attention(const HiVarlenArgs* p, void* stream_) {
   const int64_t qrow = static_cast<int64_t>(a.n_qo_heads) * a.head_dim, krow = static_cast<int64_t>(a.n_kv_heads) * a.head_dim;
   HI_CHECK_ARG(a.q_row_stride >= qrow && a.out_row_stride >= qrow && a.k_row_stride >= krow && a.v_row_stride >= krow,
                "varlen_attention: row stride smaller than n_heads*head_dim");
-  HI_CUDA(cudaSetDevice(a.device));
+  HI_DEVICE_GUARD(a.device);
   return launch_varlen_pair(a, static_cast<cudaStream_t>(stream_));
 }
 

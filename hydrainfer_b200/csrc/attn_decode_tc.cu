@@ -363,11 +363,8 @@ template <typename T, int GP>
 static int launch_decode_t(const HiAttnArgs& args, const DecArgs& a, const CUtensorMap& mq, const CUtensorMap& mk,
                            const CUtensorMap& mv, cudaStream_t stream) {
   using L = DecSmem<1>;
-  static bool configured = false;
-  if (!configured) {
-    HI_CUDA(cudaFuncSetAttribute(paged_decode_tc_kernel<T, 1, GP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamicBytes));
-    configured = true;
-  }
+  static PerDeviceFlags configured;
+  HI_CUDA(configure_dynamic_smem(configured, paged_decode_tc_kernel<T, 1, GP>, L::kDynamicBytes));
   const dim3 grid(args.n_tokens, args.n_kv_heads, a.n_splits);
   timing_mark_start(stream);
   paged_decode_tc_kernel<T, 1, GP><<<grid, kDecThreads, L::kDynamicBytes, stream>>>(mq, mk, mv, a);
@@ -424,8 +421,15 @@ int launch_attn_decode_tc(const HiAttnArgs& args, cudaStream_t stream) {
   if (n_splits > max_splits) n_splits = max_splits;
   if (const char* env = tuning_env("HI_DEC_SPLITS")) n_splits = atoi(env);
   if (n_splits < 1) n_splits = 1;
-  const int64_t per_split = static_cast<int64_t>(args.n_tokens) * args.n_qo_heads * (kDecD + 2) * 4;
-  while (n_splits > 1 && (args.workspace == nullptr || per_split * n_splits > args.workspace_bytes)) --n_splits;
+  n_splits = cap_splits(n_splits, args.n_tokens, args.n_qo_heads, kDecD);
+  {
+    const int64_t need = partial_bytes_per_split(args.n_tokens, args.n_qo_heads, kDecD) * n_splits;
+    if (n_splits > 1 && (args.workspace == nullptr || need > args.workspace_bytes)) {
+      set_error("paged_attention: workspace of %lld bytes is smaller than the %lld needed for %d KV splits (see hi_attention_workspace_bytes)",
+                (long long)args.workspace_bytes, (long long)need, n_splits);
+      return HI_ERR_WORKSPACE;
+    }
+  }
   a.tiles_per_split = (max_tiles + n_splits - 1) / n_splits;
   a.n_splits = (max_tiles + a.tiles_per_split - 1) / a.tiles_per_split;
   if (a.n_splits > 1) {

@@ -151,6 +151,13 @@ __device__ __forceinline__ void merge_half_warps_and_store(const SimtArgs& a, fl
   }
 }
 
+// out[t, first_elem .. first_elem + n_elems) = 0 by the whole CTA.
+template <typename T>
+__device__ __forceinline__ void zero_row_heads(const SimtArgs& a, int t, int first_elem, int n_elems) {
+  T* orow = static_cast<T*>(a.out) + static_cast<int64_t>(t) * a.out_row_stride + first_elem;
+  for (int i = threadIdx.x; i < n_elems; i += blockDim.x) orow[i] = Elem<T>::from_f32(0.f);
+}
+
 template <typename T, int D, int G>
 __global__ void __launch_bounds__(kSimtThreads) paged_attn_simt_kernel(const SimtArgs a) {
   constexpr int E = D / 16;                                        // head dims per lane
@@ -171,6 +178,10 @@ __global__ void __launch_bounds__(kSimtThreads) paged_attn_simt_kernel(const Sim
   const int vis = kv_len - q_len + (t - q_start) + 1;  // keys 0 .. vis-1 are visible to this row
   const int tiles_total = (vis + 15) >> 4;
   const int tile_begin = chunk * a.chunk_tiles;
+  if (vis <= 0) {  // no visible key (kv_len < q_len: malformed metadata): a defined result instead of whatever `out` held
+    if (chunk == 0) zero_row_heads<T>(a, t, qh0 * D, G * D);
+    return;
+  }
   if (tile_begin >= tiles_total) return;  // merge_partials_kernel recomputes the valid chunk count
   const int tile_end = min(tiles_total, tile_begin + a.chunk_tiles);
   const int n_iters = (tile_end - tile_begin + kHalfWarps - 1) / kHalfWarps;
@@ -362,6 +373,10 @@ __global__ void __launch_bounds__(kSimtThreads) paged_attn_stream_kernel(const S
   const int vis = kv_len - q_len + (t - q_start) + 1;
   const int tiles_total = (vis + 15) >> 4;
   const int tile_begin = chunk * a.chunk_tiles;
+  if (vis <= 0) {
+    if (chunk == 0) zero_row_heads<T>(a, t, qh0 * D, G * D);
+    return;
+  }
   if (tile_begin >= tiles_total) return;
   const int tile_end = min(tiles_total, tile_begin + a.chunk_tiles);
   const int n_iters = (tile_end - tile_begin + kHalfWarps - 1) / kHalfWarps;
@@ -504,7 +519,9 @@ __global__ void __launch_bounds__(kMergeThreads) merge_partials_kernel(const Sim
   }
   const int vis = kv_len - q_len + (t - q_start) + 1;
   const int tiles_total = (vis + 15) >> 4;
-  const int n_valid = (tiles_total + a.chunk_tiles - 1) / a.chunk_tiles;
+  if (tiles_total <= 0) return;  // the producer wrote zeros for a row without visible keys
+  // a max_kv_len smaller than the real lengths must not walk into the partials of the neighbouring rows
+  const int n_valid = min((tiles_total + a.chunk_tiles - 1) / a.chunk_tiles, a.n_chunks);
   const int d4 = threadIdx.x % kLanes;
 
   for (int head = blockIdx.y * kHeadsPerCta + threadIdx.x / kLanes; head < a.n_qo_heads; head += gridDim.y * kHeadsPerCta) {
@@ -574,11 +591,8 @@ static int launch_simt_g(const SimtArgs& a, cudaStream_t stream) {
   constexpr bool kStream = sizeof(T) == 2 && D <= 128;  // 8- or 16-byte lane rows: staged through cp.async
   if constexpr (kStream) {
     constexpr int smem = stream_smem_bytes<T, D>();
-    static bool configured = false;
-    if (!configured) {
-      HI_CUDA(cudaFuncSetAttribute(paged_attn_stream_kernel<T, D, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      configured = true;
-    }
+    static PerDeviceFlags configured;
+    HI_CUDA(configure_dynamic_smem(configured, paged_attn_stream_kernel<T, D, G>, smem));
     timing_mark_start(stream);
     paged_attn_stream_kernel<T, D, G><<<grid, kSimtThreads, smem, stream>>>(a);
   } else {

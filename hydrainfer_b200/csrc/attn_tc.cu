@@ -506,11 +506,8 @@ template <typename T, int NST>
 static int launch_tc_t(const HiAttnArgs& args, const TcArgs& a, const CUtensorMap& mq, const CUtensorMap& mk,
                        const CUtensorMap& mv, cudaStream_t stream) {
   using L = TcSmem<NST>;
-  static bool configured = false;
-  if (!configured) {
-    HI_CUDA(cudaFuncSetAttribute(paged_attn_tc_kernel<T, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamicBytes));
-    configured = true;
-  }
+  static PerDeviceFlags configured;
+  HI_CUDA(configure_dynamic_smem(configured, paged_attn_tc_kernel<T, NST>, L::kDynamicBytes));
   const int q_tiles = (args.max_q_len + a.tq - 1) / a.tq;
   const dim3 grid(q_tiles * a.n_splits, args.n_kv_heads, args.n_seqs);
   timing_mark_start(stream);
@@ -519,12 +516,6 @@ static int launch_tc_t(const HiAttnArgs& args, const TcArgs& a, const CUtensorMa
   note_launch();
   HI_CUDA(cudaGetLastError());
   return HI_OK;
-}
-
-int64_t tc_workspace_bytes() {
-  // split-KV partials of the tcgen05 kernels: rows * heads * n_splits entries of (128 + 2) floats.  192 MiB holds e.g.
-  // 3 chunks of a 4096-token, 28-head ragged prefill batch; launches that would need more use fewer chunks.
-  return static_cast<int64_t>(192) << 20;
 }
 
 int launch_attn_tc(const HiAttnArgs& args, cudaStream_t stream) {
@@ -563,9 +554,13 @@ int launch_attn_tc(const HiAttnArgs& args, cudaStream_t stream) {
     if (n_splits > max_splits) n_splits = max_splits;
     if (const char* env = tuning_env("HI_TC_SPLITS")) n_splits = atoi(env);  // tuning override
     if (n_splits < 1) n_splits = 1;
-    // shrink to what the workspace can hold
-    const int64_t per_split = static_cast<int64_t>(args.n_tokens) * args.n_qo_heads * (kHeadDim + 2) * 4;
-    while (n_splits > 1 && (args.workspace == nullptr || per_split * n_splits > args.workspace_bytes)) --n_splits;
+    n_splits = cap_splits(n_splits, args.n_tokens, args.n_qo_heads, kHeadDim);
+    const int64_t need = partial_bytes_per_split(args.n_tokens, args.n_qo_heads, kHeadDim) * n_splits;
+    if (n_splits > 1 && (args.workspace == nullptr || need > args.workspace_bytes)) {
+      set_error("paged_attention: workspace of %lld bytes is smaller than the %lld needed for %d KV splits (see hi_attention_workspace_bytes)",
+                (long long)args.workspace_bytes, (long long)need, n_splits);
+      return HI_ERR_WORKSPACE;
+    }
   }
   a.tiles_per_split = (max_kv_tiles + n_splits - 1) / n_splits;
   a.n_splits = (max_kv_tiles + a.tiles_per_split - 1) / a.tiles_per_split;

@@ -824,14 +824,11 @@ static int launch_pair_t(int device, const P2Args& a, const CUtensorMap& mq, con
                          const CUtensorMap& mv, cudaStream_t stream) {
   constexpr int NK = 4, NV = 4;  // 4 + 4 steps of 64 keys (16 KiB each) + 64 KiB of Q = 192 KiB
   using L = P2Smem<NK, NV>;
-  static bool configured = false;
-  if (!configured) {
-    HI_CUDA(cudaFuncSetAttribute(paged_attn_pair_kernel<T, NK, NV, PF, VL>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamicBytes));
-    configured = true;
-  }
+  static PerDeviceFlags configured;
+  HI_CUDA(configure_dynamic_smem(configured, paged_attn_pair_kernel<T, NK, NV, PF, VL>, L::kDynamicBytes));
   // persistent: one CTA per SM walks the items with a stride of the grid size
-  static int n_sms = 0;
-  if (n_sms == 0) HI_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device));
+  const int n_sms = sm_count_of(device);
+  HI_CHECK_ARG(n_sms > 0, "paged_attention: cannot read the SM count of device %d", device);
   int ctas = a.n_items < n_sms ? a.n_items : n_sms;
   if (const char* env = tuning_env("HI_PAIR_CTAS")) ctas = atoi(env) > 0 ? atoi(env) : ctas;  // tuning / test override
   const dim3 grid(ctas, 1, 1);
@@ -908,9 +905,14 @@ int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
   }
   if (const char* env = tuning_env("HI_TC_SPLITS")) n_splits = atoi(env);  // tuning / test override
   if (n_splits < 1) n_splits = 1;
-  {
-    const int64_t per_split = static_cast<int64_t>(args.n_tokens) * args.n_qo_heads * (kP2D + 2) * 4;
-    while (n_splits > 1 && (args.workspace == nullptr || per_split * n_splits + plan_tail + 512 > args.workspace_bytes)) --n_splits;
+  n_splits = cap_splits(n_splits, args.n_tokens, args.n_qo_heads, kP2D);
+  if (n_splits > 1) {
+    const int64_t need = partial_bytes_per_split(args.n_tokens, args.n_qo_heads, kP2D) * n_splits + plan_tail + kWorkspaceTailBytes;
+    if (args.workspace == nullptr || need > args.workspace_bytes) {
+      set_error("paged_attention: workspace of %lld bytes is smaller than the %lld needed for %d KV splits (see hi_attention_workspace_bytes)",
+                (long long)args.workspace_bytes, (long long)need, n_splits);
+      return HI_ERR_WORKSPACE;
+    }
   }
   a.tiles_per_split = (max_kv_tiles + n_splits - 1) / n_splits;
   a.n_splits = (max_kv_tiles + a.tiles_per_split - 1) / a.tiles_per_split;

@@ -5,6 +5,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -53,6 +54,87 @@ void timing_mark_stop(cudaStream_t stream);
       return HI_ERR_CUDA;                                                                          \
     }                                                                                              \
   } while (0)
+
+// ---- per-device state ------------------------------------------------------------------------------------------------------
+// One process may drive several GPUs (same-process peer migration, tests, a multi-GPU engine) and several threads (the
+// engine thread and the image-embed thread): everything that is per device / per context lives in arrays indexed
+// by the device ordinal, written with atomics (racing writers store the same value).
+constexpr int kMaxDevices = 64;
+
+// Makes `device` current for the duration of a C-ABI call and restores the caller's current device on the way out, so
+// a launch on cuda:1 never changes what torch (or any other runtime user on this thread) sees as the current device.
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int device) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess) cur = -1;
+    if (cur != device) {
+      ok = device >= 0 && device < kMaxDevices && cudaSetDevice(device) == cudaSuccess;
+      prev = cur;
+    }
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+#define HI_DEVICE_GUARD(device)                                              \
+  ::hi::DeviceGuard device_guard__(device);                                  \
+  do {                                                                       \
+    if (!device_guard__.ok) {                                                \
+      ::hi::set_error("cudaSetDevice(%d) failed: %s", static_cast<int>(device), cudaGetErrorString(cudaGetLastError())); \
+      return HI_ERR_CUDA;                                                    \
+    }                                                                        \
+  } while (0)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: call it once per (kernel instance, device).
+// `flags` is a function-local static of the launching template instance.
+struct PerDeviceFlags {
+  std::atomic<unsigned char> done[kMaxDevices];
+};
+template <typename Kernel>
+inline cudaError_t configure_dynamic_smem(PerDeviceFlags& flags, Kernel kernel, int bytes) {
+  int device = 0;
+  cudaError_t err = cudaGetDevice(&device);
+  if (err != cudaSuccess) return err;
+  if (device < 0 || device >= kMaxDevices) return cudaErrorInvalidDevice;
+  if (flags.done[device].load(std::memory_order_acquire)) return cudaSuccess;
+  err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (err == cudaSuccess) flags.done[device].store(1, std::memory_order_release);
+  return err;
+}
+
+// ---- split-KV scratch ---------------------------------------------------------------------------------------------------------
+// Every kernel's split rule is a function of the launch extents only, never of the size of the caller's workspace: a launch
+// whose partials (n_tokens * n_qo_heads * n_splits entries of head_dim + 2 floats) would exceed kMaxPartialBytes takes fewer
+// splits (such launches have thousands of tiles and do not need them), and a workspace smaller than what the rule asks for
+// is an error (HI_ERR_WORKSPACE), not a quiet change of the split count.  hi_attention_workspace_bytes() is the matching bound.
+constexpr int64_t kMaxPartialBytes = int64_t(256) << 20;
+constexpr int64_t kWorkspaceTailBytes = 512;  // work counter (last 256 bytes, 256-byte aligned) + slack
+inline int64_t partial_bytes_per_split(int64_t n_tokens, int n_qo_heads, int head_dim) {
+  return n_tokens * n_qo_heads * static_cast<int64_t>(head_dim + 2) * 4;
+}
+inline int cap_splits(int n_splits, int64_t n_tokens, int n_qo_heads, int head_dim) {
+  const int64_t per_split = partial_bytes_per_split(n_tokens, n_qo_heads, head_dim);
+  int64_t most = per_split > 0 ? kMaxPartialBytes / per_split : 1;
+  if (most < 1) most = 1;
+  return n_splits > most ? static_cast<int>(most) : n_splits;
+}
+
+// SM count of `device`, cached per device (0 on error).
+inline int sm_count_of(int device) {
+  static std::atomic<int> cache[kMaxDevices];
+  if (device < 0 || device >= kMaxDevices) return 0;
+  int n = cache[device].load(std::memory_order_relaxed);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
+    cache[device].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
 
 inline int dtype_size(int dtype) {
   switch (dtype) {

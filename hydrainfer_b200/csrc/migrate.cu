@@ -96,7 +96,7 @@ extern "C" int hi_migrate_blocks_layers(const int32_t* src_blocks, const int32_t
   HI_CHECK_ARG(src.run_bytes > 0 && src.run_bytes % 16 == 0, "migrate_blocks: run of %lld bytes is not a multiple of 16",
                (long long)src.run_bytes);
   HI_CHECK_ARG(aligned_to(src_pool, 16) && aligned_to(dst_pool, 16), "migrate_blocks: pools must be 16-byte aligned");
-  HI_CUDA(cudaSetDevice(device));
+  HI_DEVICE_GUARD(device);
 
   MigrateArgs a{};
   a.src_blocks = src_blocks;
@@ -112,8 +112,8 @@ extern "C" int hi_migrate_blocks_layers(const int32_t* src_blocks, const int32_t
   a.pieces_per_run = (a.run_bytes + kPieceBytes - 1) / kPieceBytes;
   a.total_pieces = a.planes * n * a.pieces_per_run;
 
-  static int sm_count = 0;
-  if (sm_count == 0) HI_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+  const int sm_count = sm_count_of(device);
+  HI_CHECK_ARG(sm_count > 0, "migrate_blocks: cannot read the SM count of device %d", device);
   // 8 resident CTAs of 256 threads per SM = 128 KiB of loads in flight per SM.
   int64_t grid = static_cast<int64_t>(sm_count) * 8;
   if (grid > a.total_pieces) grid = a.total_pieces;
@@ -127,7 +127,7 @@ extern "C" int hi_ipc_get_handle(const void* ptr, uint8_t handle_out[64], int64_
   using namespace hi;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
   HI_CHECK_ARG(ptr && handle_out && offset_out, "ipc_get_handle: null pointer");
-  HI_CUDA(cudaSetDevice(device));
+  HI_DEVICE_GUARD(device);
   cudaIpcMemHandle_t h;
   HI_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(ptr)));
   std::memcpy(handle_out, &h, 64);
@@ -161,7 +161,7 @@ extern "C" int hi_ipc_open_handle(const uint8_t handle[64], int64_t offset, int 
       return HI_OK;
     }
   }
-  HI_CUDA(cudaSetDevice(device));
+  HI_DEVICE_GUARD(device);
   cudaIpcMemHandle_t h;
   std::memcpy(&h, handle, 64);
   void* base = nullptr;
@@ -190,7 +190,8 @@ extern "C" int hi_ipc_close_all(void) {
   std::lock_guard<std::mutex> lock(g_ipc_mu);
   int rc = HI_OK;
   for (const IpcEntry& e : g_ipc_entries) {
-    if (cudaSetDevice(e.device) != cudaSuccess || cudaIpcCloseMemHandle(e.base) != cudaSuccess) {
+    DeviceGuard guard(e.device);
+    if (!guard.ok || cudaIpcCloseMemHandle(e.base) != cudaSuccess) {
       (void)cudaGetLastError();
       set_error("ipc_close_all: cudaIpcCloseMemHandle failed");
       rc = HI_ERR_CUDA;
@@ -216,7 +217,7 @@ extern "C" int hi_enable_peer_access(int device, int peer_device) {
     set_error("enable_peer_access: device %d cannot access device %d", device, peer_device);
     return HI_ERR_PEER_UNSUPPORTED;
   }
-  HI_CUDA(cudaSetDevice(device));
+  HI_DEVICE_GUARD(device);
   const cudaError_t err = cudaDeviceEnablePeerAccess(peer_device, 0);
   if (err == cudaErrorPeerAccessAlreadyEnabled) {
     (void)cudaGetLastError();

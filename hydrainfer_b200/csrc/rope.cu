@@ -271,7 +271,7 @@ extern "C" int hi_rope_append(const HiRopeArgs* p, void* stream_) {
     HI_CHECK_ARG(r.v && r.key_cache && r.value_cache, "rope_append: slot ids given without v / caches");
     HI_CHECK_ARG(r.v_row_stride >= static_cast<int64_t>(r.n_kv_heads) * r.head_dim, "rope_append: v row stride smaller than the row");
   }
-  HI_CUDA(cudaSetDevice(r.device));
+  HI_DEVICE_GUARD(r.device);
   RopeArgs a{};
   a.q = static_cast<char*>(r.q);
   a.k = static_cast<char*>(r.k);

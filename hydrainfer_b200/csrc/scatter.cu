@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const int32_t* __restr
 
 static int launch_scatter(const ScatterArgs& a, int n_tensors, int64_t n_tokens, int device, cudaStream_t stream) {
   if (n_tokens == 0) return HI_OK;
-  HI_CUDA(cudaSetDevice(device));
+  HI_DEVICE_GUARD(device);
   // Widest vector every row start and the row length are aligned to.
   uintptr_t bits = static_cast<uintptr_t>(a.row_bytes);
   for (int t = 0; t < n_tensors; ++t) {
@@ -130,7 +130,7 @@ extern "C" int hi_get_image_cache(const int32_t* slot_ids, const void* image_cac
   HI_CHECK_ARG(n_tokens == 0 || (slot_ids && image_cache && out), "get_image_cache: null pointer");
   HI_CHECK_ARG(out_row_stride >= row_elems, "get_image_cache: row stride smaller than the row");
   if (n_tokens == 0) return HI_OK;
-  HI_CUDA(cudaSetDevice(device));
+  HI_DEVICE_GUARD(device);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int64_t row_bytes = row_elems * es, stride_bytes = out_row_stride * es;
   const uintptr_t bits = static_cast<uintptr_t>(row_bytes) | static_cast<uintptr_t>(stride_bytes) |

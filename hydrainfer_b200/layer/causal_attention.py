@@ -18,7 +18,7 @@ from typing import Optional
 import torch
 from torch import Tensor, nn
 
-from .._C.kernel.flash_attn import mha_varlen_fwd
+from .._C.kernel.flash_attn import append_and_attend, mha_varlen_fwd
 from ..memory.kv_cache import KVCache
 
 
@@ -254,15 +254,27 @@ class B200CausalGroupedQueryPageAttentionHandler(nn.Module):
             raise RuntimeError("hydrainfer_b200: attention needs CUDA tensors; no CPU handler is linked")
         key_cache, value_cache = attention_params.kv_cache.get_kv_cache()
         output = torch.empty((query.shape[0], self.n_qo_heads, self.head_dim), dtype=query.dtype, device=query.device)
-        mha_varlen_fwd(
-            output, query, key_cache, value_cache,
-            attention_params.q_cu_seq_lens, attention_params.kv_cu_seq_lens,
-            attention_params.block_tables, attention_params.cu_blocks_lens,
-            None, attention_params.q_max_seq_len, attention_params.kv_max_seq_len,
-            1.0 / math.sqrt(self.head_dim), 0, -1, 0, 0, self.path,
-            attention_params.work_items, attention_params.work_tile_tokens, attention_params.qk_work,
-        )
+        try:
+            mha_varlen_fwd(
+                output, query, key_cache, value_cache,
+                attention_params.q_cu_seq_lens, attention_params.kv_cu_seq_lens,
+                attention_params.block_tables, attention_params.cu_blocks_lens,
+                None, attention_params.q_max_seq_len, attention_params.kv_max_seq_len,
+                1.0 / math.sqrt(self.head_dim), 0, -1, 0, 0, self.path,
+                getattr(attention_params, "work_items", None), getattr(attention_params, "work_tile_tokens", 0),
+                getattr(attention_params, "qk_work", 0),
+            )
+        except RuntimeError as e:
+            # a geometry the kernels do not cover (HI_ERR_UNSUPPORTED: head_dim outside {64, 128, 256}, odd strides, ...)
+            # goes down the chain when this handler heads the reference's own list; with no next handler it is an error
+            if self.next_handler is not None and _is_unsupported(e):
+                return self.next_handler(query, attention_params)
+            raise
         return CausalGroupedQueryPageAttentionOutput(o=output.view(-1, self.n_qo_heads * self.head_dim))
+
+
+def _is_unsupported(e: RuntimeError) -> bool:
+    return "hi_b200 error -2" in str(e)
 
 
 class CausalGroupedQueryPageAttention(nn.Module):
@@ -275,6 +287,7 @@ class CausalGroupedQueryPageAttention(nn.Module):
         self.n_qo_heads = config.n_qo_heads
         self.n_kv_heads = config.n_kv_heads
         self.head_dim = config.head_dim
+        self.softmax_scale = 1.0 / math.sqrt(config.head_dim)
         self.handlers = [B200CausalGroupedQueryPageAttentionHandler(config)]
         self.handler = self.handlers[0]
 
@@ -283,5 +296,14 @@ class CausalGroupedQueryPageAttention(nn.Module):
         query = query.view(n_tokens, self.n_qo_heads, self.head_dim)
         key = key.view(n_tokens, self.n_kv_heads, self.head_dim)
         value = value.view(n_tokens, self.n_kv_heads, self.head_dim)
+        handler = self.handler
+        if type(handler) is B200CausalGroupedQueryPageAttentionHandler and handler.next_handler is None and query.is_cuda:
+            # append + attend in ONE call into the compiled module (the two steps of :402-405 back to back on the current stream)
+            p = attention_params
+            key_cache, value_cache = p.kv_cache.get_kv_cache()
+            o = append_and_attend(query, key, value, p.new_cache_slots, key_cache, value_cache, p.q_cu_seq_lens, p.kv_cu_seq_lens,
+                                  p.block_tables, p.cu_blocks_lens, p.q_max_seq_len, p.kv_max_seq_len, self.softmax_scale, handler.path,
+                                  p.work_items, p.work_tile_tokens, p.qk_work)
+            return CausalGroupedQueryPageAttentionOutput(o=o.view(n_tokens, self.n_qo_heads * self.head_dim))
         attention_params.kv_cache.set_kv_cache(attention_params.new_cache_slots, key, value)
-        return self.handler(query, attention_params)
+        return handler(query, attention_params)

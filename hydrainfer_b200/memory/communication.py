@@ -17,7 +17,6 @@ import torch
 import torch.distributed as dist
 from torch import Tensor
 
-from .. import _lib
 from .._C.data_transfer import block_migration
 from .token_cache import VirtualTokenCache
 
@@ -97,16 +96,7 @@ class NCCLBackend(CommunicationBackend):
         return torch.empty((n_layers, n_tokens, n, block_size, n_heads, head_size), dtype=self.cache.dtype, device=self.cache.device)
 
     def _gather_cuda(self, src: Tensor, dst: Tensor, src_blocks: list[int], dst_blocks: list[int]) -> None:
-        dev = self.cache.device
-        n = len(src_blocks)
-        n_layers, n_tokens, _, block_size, n_heads, head_size = self.cache.shape
-        run_bytes = block_size * n_heads * head_size * self.cache.element_size()
-        tables = torch.tensor([src_blocks, dst_blocks], dtype=torch.int32, device=dev)
-        _lib.check(_lib.lib.hi_migrate_blocks(
-            tables[0].data_ptr(), tables[1].data_ptr(), n, src.data_ptr(), dst.data_ptr(),
-            _lib.HiPoolGeom(n_layers, n_tokens, src.shape[2], run_bytes), _lib.HiPoolGeom(n_layers, n_tokens, dst.shape[2], run_bytes),
-            dev.index or 0, _lib.current_stream_ptr(dev)))
-        tables.record_stream(torch.cuda.current_stream(dev))
+        block_migration.copy_blocks(src_blocks, dst_blocks, src, dst)
 
     def migrate_blocks(self, src_virtual_cache: VirtualTokenCache, dst_virtual_cache: VirtualTokenCache, is_send: bool):
         block_table = src_virtual_cache.block_table if is_send else dst_virtual_cache.block_table
