@@ -11,8 +11,17 @@ Multi-GPU: sequences are independent, every rank runs its own batch of 64 on its
 collective); value = tokens of all ranks / max-over-ranks device time.
 
 Prints ONE JSON line (rank 0): metric decode-attn tokens/s (+ roofline on the split-KV kernel, cpu_baseline, e2e,
-clocks, migration GB/s as an extra).  `--impl reference` times the CPU restatement of the reference's torch path
-(oracle/, kind "port") on the box's host cores instead.
+clocks) and, as extras on the same line, the other halves of BASELINE.json's metric and configs:
+  "prefill"        N = 1: BASELINE config 3 (Qwen2-VL-7B 28q/4kv) — pre1k, pre8k, cfg3p (chunked prefill), cfg3mix (48 decode rows +
+                   4 chunked prefills) through the layer API; ms, TFLOP/s from 4*Hq*d*sum[q(L-q)+q(q+1)/2], fraction of the measured
+                   bf16 peak (burst and sustained), the tcgen05 kernel alone via hi_set_kernel_timing_events
+  "cfg4"           BASELINE config 4 (Qwen2-VL-72B 64q/8kv decode, batch 256, ctx 2048 / 4096): batch 256 at N = 1, 256/N sequences per
+                   rank at N > 1 (STRONG scaling, sequence i -> rank i mod N), aggregate tokens/s and per-GPU HBM fraction
+  "migrate_sweep"  BASELINE config 5: {16, 256, 4096} blocks per request x {LLaVA-7B, Qwen2-VL-7B} pools; same GPU at N = 1, disjoint
+                   NVLink pairs at N > 1, next to a cudaMemcpyPeerAsync of the same bytes timed in the same run; every moved block
+                   is verified against checksums of the source blocks
+  "migrate"        the 256-block LLaVA point of that sweep (kept as its own key: SCALE_r01 carried it)
+`--impl reference` times the CPU restatement of the reference's torch path (oracle/, kind "port") on the box's host cores instead.
 """
 from __future__ import annotations
 
@@ -334,8 +343,14 @@ def run_ours(args) -> None:
         torch.cuda.synchronize(dev)
     clocks = sampler.stop() if rank == 0 else {}
 
-    # ---- migration extra: KV-migrate GB/s (same metric family, BASELINE.json) -----------------------------------------------
-    migrate = measure_migration(rank, world, local, dev)
+    # ---- extras: the other configs of BASELINE.json (not part of `value`) -----------------------------------------------------
+    del batch, kv_cache, params, qkv_dev
+    torch.cuda.empty_cache()
+    extras_t0 = time.time()
+    prefill = measure_prefill(dev) if world == 1 and not args.no_extras else None
+    cfg4 = measure_cfg4(rank, world, dev) if not args.no_extras else None
+    migrate, migrate_sweep = measure_migration_sweep(rank, world, local, dev) if not args.no_extras else (None, None)
+    extras_s = time.time() - extras_t0
 
     # ---- aggregate over ranks: MAX time, SUM tokens ---------------------------------------------------------------------------
     stats = torch.tensor([ms_total, e2e_s, statistics.mean(kernel_ms), e2e_serial_s], dtype=torch.float64, device=dev)
@@ -358,6 +373,7 @@ def run_ours(args) -> None:
                 traffic = None
         # the reference's CPU path on this box's host cores: rank 0, N = 1 only (at N > 1 the other ranks' processes share the cores)
         cpu = cpu_reference_run(BATCH, 10, 3, budget_s=45.0) if world == 1 else None
+        ref_gpu = reference_gpu_baseline(dev, args.steps, args.warmup) if world == 1 and not args.no_extras else None
         line = {
             "metric": "decode-attn tokens/s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -374,7 +390,8 @@ def run_ours(args) -> None:
                     "result_equals_resident_path": e2e_checked},
             "gpu_launches": launches,
             "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"), "reasons": clocks.get("reasons", []), "samples": clocks.get("samples", 0)},
-            "migrate": migrate,
+            "migrate": migrate, "migrate_sweep": migrate_sweep, "prefill": prefill, "cfg4": cfg4,
+            "reference_gpu_baseline": ref_gpu, "extras_seconds": extras_s,
         }
         emit_result(line)
     if world > 1:
@@ -382,59 +399,336 @@ def run_ours(args) -> None:
         dist.destroy_process_group()
 
 
-def measure_migration(rank: int, world: int, local: int, dev: torch.device) -> dict:
-    """block_migration GB/s.  N=1: pool -> pool on the same GPU (HBM bound).  N>1: disjoint pairs (2i -> 2i+1) pull
-    through CUDA-IPC peer mappings over NVLink, all pairs at once; payload bytes one direction / max device time."""
+# ---- extras ----------------------------------------------------------------------------------------------------------------------
+def load_tensor_peaks() -> tuple[float, float, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            return float(d["bf16_tflops"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "measured (MEASURED_PEAKS.json bf16_tflops / bf16_tflops_sustained)"
+        except Exception:
+            pass
+    return 1600.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+def _hi_events(n: int):
+    from hydrainfer_b200 import _lib
+    evs = []
+    for _ in range(n):
+        h = ctypes.c_void_p()
+        _lib.check(_lib.lib.hi_event_create(ctypes.byref(h)))
+        evs.append(h)
+    return evs
+
+
+def _layer_case(seq_lens, hq, hkv, dev, seed):
+    """A batch of the given (q, kv) lengths + the layer call over it (KV append + attention through the public layer API)."""
+    from hydrainfer_b200.layer import AttentionParametersBuilder, CausalGroupedQueryPageAttention, CausalGroupedQueryPageAttentionConfig
+    from hydrainfer_b200.memory import KVCache
+    from hydrainfer_b200.workloads import make_batch
+    batch = make_batch(seq_lens, hq, hkv, D, BS, dtype=DTYPE, device=dev, gen_device=dev, seed=seed)
+    layer = CausalGroupedQueryPageAttention(CausalGroupedQueryPageAttentionConfig(hq, hkv, D))
+    builder = AttentionParametersBuilder(hq, hkv, D, BS, dev)
+    for req in batch.requests():
+        builder.add_request(*req)
+    builder.add_kv_cache(KVCache(batch.key_cache, batch.value_cache))
+    params = builder.build_attention_parameters()[0]
+
+    def step():
+        return layer(batch.query, batch.key, batch.value, params).o
+
+    return batch, step
+
+
+def cfg3_lengths():
+    """48 decode sequences with L ~ U{256..8192} (seed 0) + 4 chunked-prefill sequences with q = 512."""
+    g = torch.Generator().manual_seed(0)
+    dec = [(1, int(L)) for L in torch.randint(256, 8193, (48,), generator=g).tolist()]
+    pre = [(512, 512), (512, 2048), (512, 4096), (512, 8192)]
+    return dec, pre
+
+
+def measure_prefill(dev: torch.device, reps: int = 10, warm: int = 3) -> dict:
+    """BASELINE config 3 (Qwen2-VL-7B head geometry) on one GPU: the tensor-bound half of the metric."""
+    from hydrainfer_b200 import _lib
+    hq, hkv = 28, 4
+    dec, pre = cfg3_lengths()
+    cases = {"pre1k": [(1024, 1024)] * 8, "pre8k": [(8192, 8192)], "cfg3p": pre, "cfg3mix": dec + pre}
+    burst, sustained, src = load_tensor_peaks()
+    hbm, _ = load_peaks()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB of L2, written between timed calls
+    out = {"peak_tflops_burst": burst, "peak_tflops_sustained": sustained, "peak_source": src,
+           "flops": "4*Hq*d*sum_i[q_i*(L_i-q_i) + q_i*(q_i+1)/2] (causal, QK^T + PV, 2 flop/MAC; SURVEY §8d)",
+           "timing": f"CUDA events around each layer call (KV append + attention), median of {reps} after {warm} warm-up, L2 flushed (256 MiB write) between calls; kernel_ms = the tcgen05 kernel alone (hi_set_kernel_timing_events)",
+           "geometry": "Qwen2-VL-7B: 28 q / 4 kv heads, d=128, block 16, bf16"}
+    for name, seq_lens in cases.items():
+        batch, step = _layer_case(seq_lens, hq, hkv, dev, seed=0)
+        flops = sum(4 * hq * D * (q * (L - q) + q * (q + 1) / 2) for q, L in seq_lens)
+        decode_bytes = sum(2 * L * hkv * D * 2 + 2 * hq * D * 2 for q, L in seq_lens if q == 1)
+        for _ in range(warm):
+            step()
+        torch.cuda.synchronize(dev)
+        call_ms, kern_ms = [], []
+        stream = torch.cuda.current_stream(dev)
+        for _ in range(reps):
+            flush.zero_()
+            evs = _hi_events(2)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            _lib.lib.hi_set_kernel_timing_events(evs[0], evs[1])
+            s.record(stream)
+            step()
+            e.record(stream)
+            torch.cuda.synchronize(dev)
+            call_ms.append(s.elapsed_time(e))
+            ms = ctypes.c_float()
+            _lib.check(_lib.lib.hi_event_elapsed_ms(evs[0], evs[1], ctypes.byref(ms)))
+            kern_ms.append(ms.value)
+            for h in evs:
+                _lib.lib.hi_event_destroy(h)
+        cm, km = statistics.median(call_ms), statistics.median(kern_ms)
+        entry = {"seqs": len(seq_lens), "tokens": batch.n_tokens, "ms": cm, "kernel_ms": km, "flops": flops,
+                 "tflops": flops / km / 1e9, "frac": flops / km / 1e9 / burst, "frac_sustained": flops / km / 1e9 / sustained,
+                 "tflops_call": flops / cm / 1e9, "frac_call": flops / cm / 1e9 / burst, "tokens_per_s": batch.n_tokens / cm * 1e3}
+        if decode_bytes:
+            entry["decode_rows_kv_bytes"] = decode_bytes
+            entry["note"] = "mixed batch: the 48 decode rows stream %.0f MB of KV inside the same launch (%.0f us at the measured HBM rate)" % (
+                decode_bytes / 1e6, decode_bytes / (hbm * 1e3))
+        out[name] = entry
+        del batch, step
+        torch.cuda.empty_cache()
+    return out
+
+
+def measure_cfg4(rank: int, world: int, dev: torch.device) -> dict:
+    """BASELINE config 4: Qwen2-VL-72B head geometry (64q / 8kv), decode, batch 256 in total, sequence i -> rank i mod N."""
     import torch.distributed as dist
+    from hydrainfer_b200.workloads import shard_round_robin
+    hq, hkv, total = 64, 8, 256
+    hbm, _ = load_peaks()
+    out = {"geometry": "Qwen2-VL-72B: 64 q / 8 kv heads, d=128, block 16, bf16; one attention layer call (KV append + paged decode attention)",
+           "batch_total": total, "scaling": "strong", "n_gpus": world,
+           "timing": "GPU time per layer call from a CUDA graph of 8 calls (replayed 7 times, median), MAX over ranks; eager_ms = the same call issued from Python, 20 back to back"}
+    for ctx in (2048, 4096):
+        mine = shard_round_robin(total, rank, world)
+        batch, step = _layer_case([(1, ctx)] * len(mine), hq, hkv, dev, seed=1000 + rank)
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize(dev)
+        # eager
+        inner, ts = 20, []
+        for _ in range(5):
+            torch.cuda.synchronize(dev)
+            if world > 1:
+                dist.barrier()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(inner):
+                step()
+            e.record()
+            torch.cuda.synchronize(dev)
+            ts.append(s.elapsed_time(e) / inner)
+        eager_ms = statistics.median(ts)
+        # graph
+        calls = 8
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            step()
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                for _ in range(calls):
+                    step()
+        torch.cuda.synchronize(dev)
+        graph.replay()
+        ts = []
+        for _ in range(7):
+            torch.cuda.synchronize(dev)
+            if world > 1:
+                dist.barrier()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            graph.replay()
+            e.record()
+            torch.cuda.synchronize(dev)
+            ts.append(s.elapsed_time(e) / calls)
+        graph_ms = statistics.median(ts)
+        tms = torch.tensor([graph_ms, eager_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        graph_ms, eager_ms = (float(x) for x in tms.tolist())
+        bytes_per_token = 2 * ctx * hkv * D * 2 + 2 * hq * D * 2
+        per_gpu_gbs = len(mine) * bytes_per_token / graph_ms / 1e6
+        out[f"ctx{ctx}"] = {"seqs_per_gpu": len(mine), "ms": graph_ms, "eager_ms": eager_ms, "tokens_per_s": total / graph_ms * 1e3,
+                            "tokens_per_s_eager": total / eager_ms * 1e3, "per_gpu_gbs": per_gpu_gbs, "hbm_frac": per_gpu_gbs / hbm,
+                            "bytes_per_token": bytes_per_token}
+        del graph, batch, step
+        torch.cuda.empty_cache()
+    return out
+
+
+MIGRATION_POOLS = {
+    "llava7b": dict(n_layers=32, n_tokens=2, block_size=16, n_heads=32, head_size=128),   # 128 KiB runs, 8 MiB per block
+    "qwen2vl7b": dict(n_layers=28, n_tokens=2, block_size=16, n_heads=4, head_size=128),  # 16 KiB runs, 896 KiB per block
+}
+
+
+def _block_checksums(pool: torch.Tensor, blocks: list[int]) -> torch.Tensor:
+    """One int64 per block: position-weighted wrap-around sum over every 32-bit word of the block in every (layer, K/V) plane.
+    Any missing, misplaced or altered word changes it; computed in slabs so 32 GiB requests do not need 64 GiB of temporaries."""
+    L, T, NB = pool.shape[0], pool.shape[1], pool.shape[2]
+    words = pool.view(torch.int32).view(L, T, NB, -1)
+    W = words.shape[-1]
+    w_word = (torch.arange(W, device=pool.device, dtype=torch.int64) % 8191) + 1
+    w_plane = (torch.arange(L * T, device=pool.device, dtype=torch.int64) * 1000003 + 17).view(L, T, 1)
+    idx = torch.tensor(blocks, dtype=torch.int64, device=pool.device)
+    out = torch.empty(len(blocks), dtype=torch.int64, device=pool.device)
+    slab = max(1, (256 << 20) // (L * T * W * 8))
+    for i in range(0, len(blocks), slab):
+        sel = words[:, :, idx[i:i + slab]].to(torch.int64)          # [L, T, n, W]
+        out[i:i + slab] = ((sel * w_word).sum(dim=-1) * w_plane).sum(dim=(0, 1))
+    return out
+
+
+def measure_migration(rank: int, world: int, local: int, dev: torch.device, pool_name: str, n_move: int, reps: int = 5) -> dict:
+    """block_migration GB/s for one (pool geometry, blocks per request) point.  N=1: pool -> pool on the same GPU (HBM bound).
+    N>1: disjoint pairs (2i -> 2i+1) pull through CUDA-IPC peer mappings over NVLink, all pairs at once; payload bytes one
+    direction / max-over-ranks device time.  The same payload is also moved by ONE cudaMemcpyPeerAsync (N>1) / cudaMemcpyAsync
+    (N=1) in the same run - the copy-engine figure this kernel is compared with - and every moved block is verified."""
+    import torch.distributed as dist
+    from hydrainfer_b200 import _lib
     from hydrainfer_b200._C.data_transfer import block_migration as bm
-    geom = dict(n_layers=32, n_tokens=2, block_size=16, n_heads=32, head_size=128)  # LLaVA-7B pool: 8 MiB per block
-    pool_blocks, n_move = 320, 256  # 2 GiB moved per request
+    geom = MIGRATION_POOLS[pool_name]
+    pool_blocks = n_move + max(16, n_move // 8)
+    shape = (geom["n_layers"], geom["n_tokens"], pool_blocks, geom["block_size"], geom["n_heads"], geom["head_size"])
     bytes_per_block = geom["n_layers"] * geom["n_tokens"] * geom["block_size"] * geom["n_heads"] * geom["head_size"] * 2
-    pool = torch.empty((geom["n_layers"], geom["n_tokens"], pool_blocks, geom["block_size"], geom["n_heads"], geom["head_size"]), dtype=DTYPE, device=dev)
-    pool.normal_()
-    g = torch.Generator().manual_seed(100 + rank)
+    payload = n_move * bytes_per_block
+    pool = torch.empty(shape, dtype=DTYPE, device=dev)
+    pool.view(torch.int32).random_(-2**31, 2**31 - 1, generator=torch.Generator(device=dev).manual_seed(100 + rank))  # every bit pattern, incl. NaNs
+    g = torch.Generator().manual_seed(200 + n_move)  # the same tables on every rank
     src_bt = torch.randperm(pool_blocks, generator=g)[:n_move].tolist()
     dst_bt = torch.randperm(pool_blocks, generator=g)[:n_move].tolist()
     handle = bm.get_ipc_mem_handle(pool)
-    pattern = "same-GPU pool->pool (HBM)"
-    is_receiver = True
-    src_handle = handle
+    is_receiver, peer_local = True, local
     if world > 1:
         handles = [None] * world
         dist.all_gather_object(handles, handle)
-        pattern = f"{world // 2} disjoint pair(s) 2i->2i+1 over NVLink P2P (CUDA IPC pull)"
         is_receiver = (rank % 2 == 1)
         src_handle = handles[rank - 1] if is_receiver else handle
+        peer_local = local - 1
         dst_pool = pool
-    if world == 1:
+        pattern = f"{world // 2} disjoint pair(s) 2i->2i+1 over NVLink P2P (CUDA IPC pull), all at once"
+    else:
+        src_handle = handle
         dst_pool = torch.empty_like(pool)
-    times = []
-    reps = 5
-    for i in range(reps + 2):
+        dst_pool.view(torch.int32).random_(-2**31, 2**31 - 1, generator=torch.Generator(device=dev).manual_seed(7))
+        pattern = "same-GPU pool->pool (HBM)"
+
+    def sync_all():
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
+
+    def timed(fn) -> float:
+        ts = []
+        for i in range(reps + 2):
+            sync_all()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            if is_receiver:
+                fn()
+            e.record()
+            torch.cuda.synchronize(dev)
+            if i >= 2:
+                ts.append(s.elapsed_time(e))
+        t = torch.tensor([statistics.median(ts) if is_receiver else 0.0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # verification material BEFORE the copy: checksums of the source blocks, computed by the rank that owns them
+    src_sums = _block_checksums(pool, src_bt)
+    if world > 1:
+        gathered = [torch.empty_like(src_sums) for _ in range(world)]
+        dist.all_gather(gathered, src_sums)
+        expect = gathered[rank - 1] if is_receiver else None
+    else:
+        expect = src_sums
+    ms = timed(lambda: bm.migrate_blocks(src_bt, dst_bt, src_handle, dst_pool, pool_blocks))
+    ok = True
+    if is_receiver:
+        ok = bool(torch.equal(_block_checksums(dst_pool, dst_bt), expect))
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    ok = bool(flag.item())
+
+    # the copy-engine comparator: the same number of bytes as ONE contiguous copy, same source GPU, same destination GPU
+    flat_dst = torch.empty(min(payload, pool.numel() * 2), dtype=torch.uint8, device=dev)
+    copy_bytes = flat_dst.numel()
+    src_ptr = ctypes.c_void_p(pool.data_ptr())
+    if world > 1 and is_receiver:
+        raw = (ctypes.c_uint8 * 64).from_buffer_copy(bytes(int(b) & 0xFF for b in src_handle[:64]))
+        off = int.from_bytes(bytes(int(b) & 0xFF for b in src_handle[64:]), "little") if len(src_handle) == 72 else 0
+        _lib.check(_lib.lib.hi_ipc_open_handle(raw, off, local, ctypes.byref(src_ptr)))
+    stream_ptr = _lib.current_stream_ptr(dev)
+    copy_ms = timed(lambda: _lib.check(_lib.lib.hi_peer_copy(flat_dst.data_ptr(), local, src_ptr.value, peer_local, copy_bytes, stream_ptr)))
+    pairs = max(1, world // 2)
+    del pool, dst_pool, flat_dst
+    torch.cuda.empty_cache()
+    gbs = payload / (ms * 1e-3) / 1e9
+    copy_gbs = copy_bytes / (copy_ms * 1e-3) / 1e9
+    return {"pool": pool_name, "blocks_per_request": n_move, "bytes_per_request": payload, "run_bytes": bytes_per_block // (geom["n_layers"] * geom["n_tokens"]),
+            "ms": ms, "gbs_per_pair": gbs, "gbs_aggregate": pairs * gbs, "pattern": pattern,
+            "bit_exact": ok, "verified": f"all {n_move} moved blocks: position-weighted 64-bit checksums of the destination blocks == those the source rank computed",
+            "memcpy_peer_gbs": copy_gbs, "memcpy_peer_ms": copy_ms,
+            "memcpy_peer_what": ("cudaMemcpyPeerAsync" if world > 1 else "cudaMemcpyAsync (same GPU)") + f" of {copy_bytes} contiguous bytes, timed in this run",
+            "frac_of_memcpy_peer": gbs / copy_gbs, "frac_of_nvlink_900": (gbs / 900.0) if world > 1 else None}
+
+
+def measure_migration_sweep(rank: int, world: int, local: int, dev: torch.device) -> tuple[dict, dict]:
+    sweep = {"unit": "GB/s per receiving GPU, payload bytes one direction", "points": []}
+    headline = None
+    for pool_name in ("llava7b", "qwen2vl7b"):
+        for n_move in (16, 256, 4096):
+            point = measure_migration(rank, world, local, dev, pool_name, n_move, reps=3 if n_move >= 4096 and pool_name == "llava7b" else 5)
+            sweep["points"].append(point)
+            if pool_name == "llava7b" and n_move == 256:
+                headline = point
+    return headline, sweep
+
+
+def reference_gpu_baseline(dev: torch.device, steps: int, warmup: int) -> dict:
+    """Comparator only (baseline leg, next to cpu_baseline): the REFERENCE's own layer — its python files and its own csrc
+    (set_kv_cache kernel + vendored FlashAttention-2 mha_varlen_fwd) compiled unmodified into oracle/_ref — on this GPU on the
+    bench workload.  Nothing of hydrainfer_b200 is on that path."""
+    try:
+        from oracle import reference_tree
+        if not (reference_tree.available("flash_attn") and reference_tree.available("kv_cache_kernels")):
+            return {"unavailable": "oracle/_ref was not built with the reference's flash_attn (python oracle/build_ref.py --fa2)"}
+        from hydrainfer_b200.workloads import make_batch
+        ca, mem = reference_tree.import_reference_package(native="ref")
+        batch = make_batch([(1, CTX)] * BATCH, HQ, HKV, D, BS, dtype=DTYPE, device=dev, gen_device=dev, seed=0)
+        builder = ca.AttentionParametersBuilder(num_qo_heads=HQ, num_kv_heads=HKV, head_dim=D, block_size=BS, device=dev)
+        for req in batch.requests():
+            builder.add_request(*req)
+        builder.add_kv_cache(mem.KVCache(batch.key_cache, batch.value_cache))
+        params = builder.build_attention_parameters()[0]
+        layer = ca.CausalGroupedQueryPageAttention(ca.CausalGroupedQueryPageAttentionConfig(n_qo_heads=HQ, n_kv_heads=HKV, head_dim=D))
+        for _ in range(warmup):
+            layer(batch.query, batch.key, batch.value, params)
+        torch.cuda.synchronize(dev)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        if is_receiver:
-            bm.migrate_blocks(src_bt, dst_bt, src_handle, dst_pool, pool_blocks)
+        for _ in range(steps):
+            layer(batch.query, batch.key, batch.value, params)
         e.record()
         torch.cuda.synchronize(dev)
-        if i >= 2:
-            times.append(s.elapsed_time(e))
-    ok = True
-    if is_receiver and world == 1:
-        ok = bool(torch.equal(dst_pool[:, :, dst_bt[:4]], pool[:, :, src_bt[:4]]))
-    t = torch.tensor([statistics.median(times) if is_receiver else 0.0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    pairs = max(1, world // 2)
-    payload = n_move * bytes_per_block
-    del pool
-    return {"gbs_per_pair": payload / (ms * 1e-3) / 1e9, "gbs_aggregate": pairs * payload / (ms * 1e-3) / 1e9, "ms": ms, "pattern": pattern,
-            "blocks_per_request": n_move, "bytes_per_request": payload, "bit_exact_spot_check": ok,
-            "nvlink_peer_copy_reference_gbs": 770.0 if world > 1 else None}
+        ms = s.elapsed_time(e) / steps
+        return {"value": BATCH / ms * 1e3, "unit": "tokens/s", "ms_per_step": ms, "kind": "reference (oracle/_ref: the reference's python layer + its own kv_cache_kernels.cu and FlashAttention-2 csrc, nvcc 12.9 sm_100, unmodified)",
+                "hbm_gbs": BATCH * ALGO_BYTES_PER_TOKEN / ms / 1e6, "steps": steps}
+    except Exception as ex:  # comparator only: never fails the bench
+        return {"unavailable": repr(ex)[:300]}
 
 
 def main() -> None:
@@ -443,6 +737,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-extras", action="store_true", help="skip the prefill / cfg4 / migration-sweep extras (the headline metric only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to stdout when

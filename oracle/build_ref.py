@@ -96,10 +96,18 @@ def _compile(name: str, sources: list[Path], includes: list[Path], dest: Path, e
     nvcc = _nvcc()
     flags = [*COMMON, *extra_flags, f"-DPY_MODULE_NAME={name}", f"-DTORCH_EXTENSION_NAME={name}", *inc, *[f"-I{p}" for p in includes]]
 
+    host_flags = ["-O2", "-std=c++17", "-fPIC", "-w", "-DTORCH_API_INCLUDE_EXTENSION_H", f"-DPY_MODULE_NAME={name}", f"-DTORCH_EXTENSION_NAME={name}",
+                  *inc, *[f"-I{p}" for p in includes]]
+    cxx = os.environ.get("CXX") or shutil.which("g++")
+
     def one(src: Path) -> str:
         obj = obj_dir / (src.stem + ".o")
-        # .cpp files of the reference include torch/CUDA headers only; -x cu lets one driver handle both kinds
-        cmd = [nvcc, *flags, "-x", "cu", "-c", str(src), "-o", str(obj)]
+        if src.suffix == ".cpp" and cxx is not None:
+            # host-only translation units (pybind glue, block_migration.cpp: CUDA runtime API calls, no device code): g++ is
+            # several times faster than nvcc's front end on the torch headers
+            cmd = [cxx, *host_flags, "-c", str(src), "-o", str(obj)]
+        else:
+            cmd = [nvcc, *flags, "-x", "cu", "-c", str(src), "-o", str(obj)]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError(f"reference source {src} did not compile:\n{res.stderr[-4000:]}")
@@ -146,10 +154,13 @@ def build(fa2: bool = False, verbose: bool = True) -> dict[str, Path]:
     copy_python_tree()
     built = {}
     csrc = REF / "csrc"
-    for name, (dest, sources, includes) in MODULES.items():
-        built[name] = _compile(name, [csrc / s for s in sources], [csrc / i for i in includes], PKG / dest)
-        if verbose:
-            print(f"oracle/_ref: {built[name].relative_to(ROOT)}", file=sys.stderr)
+    with ThreadPoolExecutor(max_workers=len(MODULES)) as pool:  # the modules are independent: compile them side by side
+        futures = {name: pool.submit(_compile, name, [csrc / s for s in sources], [csrc / i for i in includes], PKG / dest)
+                   for name, (dest, sources, includes) in MODULES.items()}
+        for name, fut in futures.items():
+            built[name] = fut.result()
+            if verbose:
+                print(f"oracle/_ref: {built[name].relative_to(ROOT)}", file=sys.stderr)
     if fa2:
         built["flash_attn"] = build_fa2()
         if verbose:
