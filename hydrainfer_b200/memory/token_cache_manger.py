@@ -12,9 +12,11 @@ for its NCCL path (:68-72); the packed NCCL path here does not need them.
 """
 from __future__ import annotations
 
+from array import array
 from dataclasses import dataclass
 from typing import Optional
 
+import numpy as np
 import torch
 
 from .._C.data_transfer.block_migration import get_ipc_mem_handle
@@ -108,6 +110,9 @@ class TokenCacheBlockManager:
         self.total_block_matched = 0.0
 
     def get_num_avaiable_blocks(self) -> int:
+        """Free blocks + unpinned (evictable) blocks.  Deviation from the reference: its SharedCache starts with every block
+        evictable, so a fresh reference pool reports 2 * n_blocks here (shared_cache.py:27-31 + :88); this one reports n_blocks,
+        the number that can really be allocated."""
         return self.block_allocator.get_num_avaiable_blocks() + self.shared_cache.get_num_avaiable_blocks()
 
     def _allocate_new_blocks(self, n_blocks: int) -> list[int]:
@@ -126,10 +131,45 @@ class TokenCacheBlockManager:
                                  rank=self.rank, n_blocks_of_cache_manager=self.n_blocks)
 
     def v2p(self, virtual_cache: VirtualTokenCache, virtual_cache_ids: list[int]) -> list[int]:
-        """Virtual token index -> physical slot: block_table[v // bs] * bs + v % bs (:126-133)."""
+        """Virtual token index -> physical slot: block_table[v // bs] * bs + v % bs (:126-133).  One id (a decode row) is
+        two integer operations; long lists (a prefill chunk) go through numpy instead of a per-token Python loop."""
         bs = self.block_size
         table = virtual_cache.block_table
+        n = len(virtual_cache_ids)
+        if n == 1:
+            v = virtual_cache_ids[0]
+            return [table[v // bs] * bs + v % bs]
+        if n >= 64:
+            ids = np.asarray(virtual_cache_ids, dtype=np.int64)
+            return (np.asarray(table, dtype=np.int64)[ids // bs] * bs + ids % bs).tolist()
         return [table[v // bs] * bs + v % bs for v in virtual_cache_ids]
+
+    def v2p_range(self, virtual_cache: VirtualTokenCache, begin: int, end: int) -> array:
+        """Physical slots of the CONTIGUOUS virtual ids [begin, end) as an int32 `array` - what every step actually asks for
+        (the new tokens of a request are its last q positions, engine/parameters_builder.py:63-69).  Built block by block (one
+        `range` per page touched), it goes into AttentionParametersBuilder.add_request unchanged: no per-token Python and no
+        intermediate list (extension of the reference class)."""
+        bs = self.block_size
+        table = virtual_cache.block_table
+        out = array("i")
+        v = begin
+        while v < end:
+            block, off = divmod(v, bs)
+            run = min(end - v, bs - off)
+            base = table[block] * bs + off
+            out.extend(range(base, base + run))
+            v += run
+        return out
+
+    def set_blocks(self, virtual_cache: VirtualTokenCache, virtual_block_ids: list[int], hashes: list[int]) -> None:
+        """Prefix-cache insertion (:135-138; the reference's executor calls it for every request whose Fill carries hashes,
+        engine/executor.py:127).  Prefix matching is out of scope: accepted and ignored, so every later lookup stays
+        a miss and the engine runs unchanged with prefix caching switched on."""
+        assert len(virtual_block_ids) == len(hashes)
+
+    def set(self, virtual_cache: VirtualTokenCache, virtual_cache_ids: list[int], hashes: list[int]) -> None:
+        """Token-granular variant of set_blocks (:140-148): accepted and ignored, see set_blocks."""
+        assert len(virtual_cache_ids) == len(hashes)
 
     def realloc(self, virtual_cache: VirtualTokenCache, n_tokens: int) -> None:
         """Grow by whole blocks or shrink and release the tail blocks (:150-159)."""

@@ -51,3 +51,73 @@ def test_argument_validation_needs_no_gpu():
     assert _lib.lib.hi_varlen_attention(None, None) == -1
     assert b"null args" in _lib.lib.hi_last_error()
     assert _lib.lib.hi_attention_workspace_bytes(64, 32, 128, 2048) > 0
+
+
+# ---- the compiled Python boundary: the reference's five pybind modules ------------------------------------------
+REFERENCE_MODULES = {
+    # module -> (package directory, functions the reference imports from it)
+    "kv_cache_kernels": ("_C/kernel", ["set_kv_cache"]),                          # hydrainfer/memory/kv_cache.py:9
+    "cache_kernels": ("_C/kernel", ["set_image_cache"]),                          # hydrainfer/memory/token_cache.py:9
+    "flash_attn": ("_C/kernel", ["mha_varlen_fwd"]),                              # hydrainfer/layer/causal_attention.py:14
+    "position_embedding": ("_C/kernel", ["apply_rotary_pos_emb"]),                # hydrainfer/layer/rotary_embedding.py:7
+    "block_migration": ("_C/data_transfer", ["get_ipc_mem_handle", "register_ipc_mem_handle", "migrate_blocks"]),  # communication.py:10-11
+}
+
+
+def test_compiled_modules_export_the_reference_init_symbols():
+    """Each module is a real extension with the `PyInit_<name>` entry point the reference's CMake target produces
+    (csrc/CMakeLists.txt:4-11, PYBIND11_MODULE(PY_MODULE_NAME, m)), not a Python shim."""
+    import importlib
+    import importlib.machinery
+
+    from hydrainfer_b200 import build
+    for name, path in build.binding_paths().items():
+        assert path.exists(), path
+        assert path.name.endswith(tuple(importlib.machinery.EXTENSION_SUFFIXES)), path.name
+        lib = ctypes.CDLL(str(path))
+        assert hasattr(lib, f"PyInit_{name}"), f"{path.name} does not export PyInit_{name}"
+    for name, (sub, functions) in REFERENCE_MODULES.items():
+        mod = importlib.import_module(f"hydrainfer_b200.{sub.replace('/', '.')}.{name}")
+        assert isinstance(mod.__loader__, importlib.machinery.ExtensionFileLoader), f"{name} is not a compiled extension"
+        for fn in functions:
+            assert callable(getattr(mod, fn)), f"{name}.{fn}"
+
+
+def test_mha_varlen_fwd_keeps_the_reference_positional_signature():
+    """16 positional arguments (hydrainfer/_C/kernel/flash_attn/__init__.pyi:22-40); a call with 15 is a TypeError, CPU tensors
+    a RuntimeError (no CPU fallback), alibi / softcap / windows a RuntimeError like TORCH_CHECK."""
+    import pytest
+    import torch
+
+    from hydrainfer_b200._C.kernel.flash_attn import mha_varlen_fwd
+    q = torch.zeros(2, 4, 128, dtype=torch.float16)
+    kc = torch.zeros(3, 16, 4, 128, dtype=torch.float16)
+    cu = torch.tensor([0, 2], dtype=torch.int32)
+    bt = torch.tensor([0], dtype=torch.int32)
+    cub = torch.tensor([0, 1], dtype=torch.int32)
+    with pytest.raises(TypeError):
+        mha_varlen_fwd(q, q, kc, kc, cu, cu, bt, cub, None, 2, 2, 0.1, 0, -1, 0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        mha_varlen_fwd(q, q, kc, kc, cu, cu, bt, cub, None, 2, 2, 0.1, 0, -1, 0, 0)
+    with pytest.raises(RuntimeError, match="softcap"):
+        mha_varlen_fwd(q, q, kc, kc, cu, cu, bt, cub, None, 2, 2, 0.1, 30.0, -1, 0, 0)
+    with pytest.raises(RuntimeError, match="cu_block_lens"):
+        mha_varlen_fwd(q, q, kc, kc, cu, cu, bt, None, None, 2, 2, 0.1, 0, -1, 0, 0)
+
+
+def test_dropin_install_aliases_the_reference_names():
+    """hydrainfer_b200.dropin.install() in a fresh interpreter: the five `hydrainfer._C...` names resolve to our extensions."""
+    import subprocess
+    import sys
+    root = Path(__file__).resolve().parents[1]
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from hydrainfer_b200 import dropin\n"
+        "mods = dropin.install()\n"
+        "assert len(mods) == 5\n"
+        "import importlib\n"
+        "for name, mod in mods.items():\n"
+        "    assert sys.modules[name] is mod and 'hydrainfer_b200/_C' in mod.__file__, (name, mod)\n"
+        "print('ALIASED')\n" % str(root))
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "ALIASED" in res.stdout, res.stderr[-3000:]

@@ -193,3 +193,30 @@ def test_block_table_image_cache_follows_the_list():
     assert p.block_tables.tolist() == [4, 6, 8, 4, 6, 8, 1] and p.cu_blocks_lens.tolist() == [0, 3, 7]
     # tuples / other sequences are accepted too (converted every time)
     assert _built_tables([(2, 20, (3, 4), (1, 2))])[0] == [1, 2]
+
+
+def test_v2p_fast_paths_and_prefix_cache_stubs():
+    """v2p keeps the reference's arithmetic (token_cache_manger.py:126-133) on every internal path; v2p_range is the same map
+    over a contiguous id range; set_blocks / set (called by the reference's executor when prefix caching is on) are accepted."""
+    from hydrainfer_b200.memory.token_cache import VirtualTokenCache
+
+    class _Geometry:
+        block_size = 16
+
+    vc = VirtualTokenCache(vid=1, n_blocks_of_cache_manager=10, n_cache_tokens=100, block_table=[7, 2, 9, 4, 0, 1, 3], memory_handle=None, rank=0)
+    ids = list(range(5, 100))
+    want = [vc.block_table[v // 16] * 16 + v % 16 for v in ids]
+    v2p, v2p_range = TokenCacheBlockManager.v2p, TokenCacheBlockManager.v2p_range
+    assert v2p(_Geometry, vc, ids) == want                      # numpy path (>= 64 ids)
+    assert v2p(_Geometry, vc, ids[:10]) == want[:10]            # short list
+    assert v2p(_Geometry, vc, [33]) == [9 * 16 + 1]             # decode row
+    assert list(v2p_range(_Geometry, vc, 5, 100)) == want and v2p_range(_Geometry, vc, 5, 100).typecode == "i"
+    assert list(v2p_range(_Geometry, vc, 99, 100)) == want[-1:] and len(v2p_range(_Geometry, vc, 7, 7)) == 0
+    TokenCacheBlockManager.set_blocks(_Geometry, vc, [0, 1], [123, 456])
+    TokenCacheBlockManager.set(_Geometry, vc, [0, 1, 2], [1, 2, 3])
+    with pytest.raises(AssertionError):
+        TokenCacheBlockManager.set_blocks(_Geometry, vc, [0, 1], [123])
+    # the int32 array goes into the builder unchanged
+    b = AttentionParametersBuilder(4, 4, 64, 16, torch.device("cpu"))
+    b.add_request(95, 100, v2p_range(_Geometry, vc, 5, 100), vc.block_table)
+    assert list(b.new_cache_slots) == want
