@@ -76,6 +76,7 @@ struct P2Args {
   unsigned int* work_counter;  // zeroed before the launch; NULL = static (boustrophedon) assignment
   int n_items;       // work items of the launch = CTA-sized units: (sequence, KV head, pair of tiles, split)
   int max_pairs;     // without a host plan: pair slots per sequence, ceil(max_q_len / (2 tq))
+  int use_tma_store;  // epilogue of whole direct tiles through shared memory + cp.async.bulk.tensor (needs tm_o and head_dim 128)
   int debug;  // timing experiments only (HI_PAIR_DEBUG): bit 0 = softmax warps skip their math, bit 1 = no MMA is issued,
               // bit 2 = K/V tiles are not loaded (barriers only)
   // ---- un-paged varlen mode (template parameter VL; hi_varlen_attention) --------------------------------------------------
@@ -95,7 +96,8 @@ struct P2Smem {
   static constexpr int kQ = 0;                          // two tiles
   static constexpr int kK = 2 * kP2QTile;
   static constexpr int kV = kK + NK * kP2Tile;
-  static constexpr int kBars = kV + NV * kP2Tile;
+  static constexpr int kOst = kV + NV * kP2Tile;        // output staging for the TMA-store epilogue: one 64-dim half (128 rows x 128 B) per tile
+  static constexpr int kBars = kOst + 2 * kP2QHalf;
   static constexpr int bQFull = 0;                      // [2]
   static constexpr int bKFull = 2;                      // [NK]
   static constexpr int bKEmpty = bKFull + NK;
@@ -225,11 +227,50 @@ __device__ __forceinline__ unsigned long long trace_globaltimer() {
 }
 #endif
 
+// Epilogue of a whole, direct tile of a head_dim-128 launch: O / l as 16-bit rows through shared memory and one TMA store per
+// 64-dim half.  Thread r owns tile row r (TMEM lane); `stage` is the tile's 16 KiB staging buffer (128 rows x 128 B, 1024-byte
+// aligned), written in the 128B-swizzled layout of the tensor map - the layout the Q tile was loaded in.  Out of line on
+// purpose: its register needs (the row as 64 packed words) stay out of the allocation of the softmax step loop.
+template <typename T>
+__device__ __noinline__ void p2_store_tile_tma(const CUtensorMap* tm_o, uint32_t tmem_o, float inv_l, bool warp_active, uint32_t stage, int r,
+                                               uint32_t bar_id, uint32_t o_empty_bar, int head0, int token0) {
+  uint32_t pk[64];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t v[32];
+    if (warp_active) {
+      ptx::tmem_ld_x32(tmem_o + c * 32, v);
+      ptx::tmem_wait_ld();
+    }
+#pragma unroll
+    for (int e = 0; e < 32; e += 2) pk[c * 16 + (e >> 1)] = pack2<T>(__uint_as_float(v[e]) * inv_l, __uint_as_float(v[e + 1]) * inv_l);
+  }
+  ptx::tc_fence_before_sync();
+  ptx::mbar_arrive(o_empty_bar);  // O_t has left TMEM: the next item's first P.V may overwrite it
+  const uint32_t row_addr = stage + static_cast<uint32_t>(r) * 128u;
+  const bool issuer = r == 0;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if (issuer) ptx::bulk_wait_group_read<0>();  // the store that last used this buffer has read it
+    ptx::named_bar_sync(bar_id, kP2TileM);
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      ptx::st_shared_v4(row_addr + static_cast<uint32_t>((c ^ (r & 7)) << 4), pk[h * 32 + c * 4], pk[h * 32 + c * 4 + 1], pk[h * 32 + c * 4 + 2],
+                        pk[h * 32 + c * 4 + 3]);
+    ptx::fence_proxy_async_smem();
+    ptx::named_bar_sync(bar_id, kP2TileM);
+    if (issuer) {
+      ptx::tma_store_3d(tm_o, stage, h * 64, head0, token0);
+      ptx::bulk_commit_group();
+    }
+  }
+}
+
 // PF = how many of every 4 (pairs of) exponentials run on the FMA pipes (exp2_poly2) instead of MUFU.EX2.
 template <typename T, int NK, int NV, int PF, bool VL = false>
 __global__ void __launch_bounds__(kP2Threads, 1)
 paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                       const __grid_constant__ CUtensorMap tm_v, const P2Args a) {
+                       const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o, const P2Args a) {
   using L = P2Smem<NK, NV>;
   static_assert(NK == 4 && NV == 4, "ring stages are addressed as step & 3");
   constexpr bool kBf16 = !std::is_same<T, __half>::value;
@@ -272,6 +313,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       ptx::prefetch_tensormap(&tm_q);
       ptx::prefetch_tensormap(&tm_k);
       ptx::prefetch_tensormap(&tm_v);
+      ptx::prefetch_tensormap(&tm_o);
     }
     __syncwarp();
     ptx::tmem_alloc(smem_base + L::kTmemPtr, kP2TmemCols);
@@ -691,6 +733,17 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         a.part_ml[pidx * 2 + 0] = m_used;
         a.part_ml[pidx * 2 + 1] = l;
       }
+      // Whole tiles of a head_dim-128 launch whose rows go straight to `out` leave through shared memory and ONE TMA store
+      // per 64-dim half: the thread (= row) writes its 128 B of the half into the tile's staging buffer in the 128B-swizzled
+      // layout of the tensor map (the layout Q was loaded in), a bulk tensor store moves the {64 dims, group heads, tq tokens}
+      // box.  A per-row 16-byte store instruction touches 32 different 256-byte rows per warp; this path writes whole lines.
+      // Tiles cut by the end of the sequence (their box would cover the next sequence's tokens), split-KV partials and
+      // other head dims keep the per-row stores below.
+      const bool tma_out = a.use_tma_store && direct && d_out == kP2D && first + a.tq <= it.q_len;  // uniform over the warpgroup
+      if (tma_out) {
+        p2_store_tile_tma<T>(&tm_o, tmem_o, inv_l, warp_active, smem_base + L::kOst + t * kP2QHalf, r, 1 + t, bar(L::bOEmpty + t), it.kvh * a.group,
+                             it.q_start + first);
+      } else {
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
@@ -722,11 +775,13 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
           }
         }
       }
+      }
       trace(6, n_it, 0);
       gs += n_mine;
       ++n_act;
       if (n_mine >= 2) ++n_pv2;
     }
+    if (r == 0) ptx::bulk_wait_group<0>();  // the staging buffers must outlive the last TMA store's reads; writes done before exit
   }
 
   // ---- teardown ----------------------------------------------------------------------------------------------------
@@ -821,7 +876,7 @@ bool attn_pair_supported(const HiAttnArgs& args) {
 
 template <typename T, int PF, bool VL = false>
 static int launch_pair_t(int device, const P2Args& a, const CUtensorMap& mq, const CUtensorMap& mk,
-                         const CUtensorMap& mv, cudaStream_t stream) {
+                         const CUtensorMap& mv, const CUtensorMap& mo, cudaStream_t stream) {
   constexpr int NK = 4, NV = 4;  // 4 + 4 steps of 64 keys (16 KiB each) + 64 KiB of Q = 192 KiB
   using L = P2Smem<NK, NV>;
   static PerDeviceFlags configured;
@@ -833,7 +888,7 @@ static int launch_pair_t(int device, const P2Args& a, const CUtensorMap& mq, con
   if (const char* env = tuning_env("HI_PAIR_CTAS")) ctas = atoi(env) > 0 ? atoi(env) : ctas;  // tuning / test override
   const dim3 grid(ctas, 1, 1);
   timing_mark_start(stream);
-  paged_attn_pair_kernel<T, NK, NV, PF, VL><<<grid, kP2Threads, L::kDynamicBytes, stream>>>(mq, mk, mv, a);
+  paged_attn_pair_kernel<T, NK, NV, PF, VL><<<grid, kP2Threads, L::kDynamicBytes, stream>>>(mq, mk, mv, mo, a);
   timing_mark_stop(stream);
   note_launch();
   HI_CUDA(cudaGetLastError());
@@ -944,8 +999,10 @@ int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
     HI_CUDA(cudaGetLastError());
   }
 
-  CUtensorMap mq, mk, mv;
+  CUtensorMap mq, mk, mv, mo;
   int rc = make_map(&mq, args.dtype, args.q, args.n_tokens, args.n_qo_heads, args.q_row_stride, a.group, a.tq);
+  if (rc != HI_OK) return rc;
+  rc = make_map(&mo, args.dtype, args.out, args.n_tokens, args.n_qo_heads, args.out_row_stride, a.group, a.tq);
   if (rc != HI_OK) return rc;
   const int64_t n_slots = args.n_blocks * args.block_size;
   rc = pool_map(&mk, args.dtype, args.key_cache, n_slots, args.n_kv_heads, args.block_size);
@@ -953,17 +1010,19 @@ int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
   rc = pool_map(&mv, args.dtype, args.value_cache, n_slots, args.n_kv_heads, args.block_size);
   if (rc != HI_OK) return rc;
 
+  a.use_tma_store = 1;
+  if (const char* env = tuning_env("HI_PAIR_TMA_STORE")) a.use_tma_store = atoi(env) != 0;  // A/B switch
   if (const char* env = tuning_env("HI_PAIR_DEBUG")) a.debug = atoi(env);
   int poly = 0;  // exponentials per 4 moved from MUFU to the FMA pipes (measured: no gain while the softmax warps have idle issue slots)
   if (const char* env = tuning_env("HI_PAIR_POLY")) poly = atoi(env);  // tuning override
   if (args.dtype == HI_BF16) {
-    rc = poly <= 0 ? launch_pair_t<__nv_bfloat16, 0>(args.device, a, mq, mk, mv, stream)
-       : poly == 1 ? launch_pair_t<__nv_bfloat16, 1>(args.device, a, mq, mk, mv, stream)
-                   : launch_pair_t<__nv_bfloat16, 2>(args.device, a, mq, mk, mv, stream);
+    rc = poly <= 0 ? launch_pair_t<__nv_bfloat16, 0>(args.device, a, mq, mk, mv, mo, stream)
+       : poly == 1 ? launch_pair_t<__nv_bfloat16, 1>(args.device, a, mq, mk, mv, mo, stream)
+                   : launch_pair_t<__nv_bfloat16, 2>(args.device, a, mq, mk, mv, mo, stream);
   } else {
-    rc = poly <= 0 ? launch_pair_t<__half, 0>(args.device, a, mq, mk, mv, stream)
-       : poly == 1 ? launch_pair_t<__half, 1>(args.device, a, mq, mk, mv, stream)
-                   : launch_pair_t<__half, 2>(args.device, a, mq, mk, mv, stream);
+    rc = poly <= 0 ? launch_pair_t<__half, 0>(args.device, a, mq, mk, mv, mo, stream)
+       : poly == 1 ? launch_pair_t<__half, 1>(args.device, a, mq, mk, mv, mo, stream)
+                   : launch_pair_t<__half, 2>(args.device, a, mq, mk, mv, mo, stream);
   }
   if (rc != HI_OK || a.n_splits == 1) return rc;
 
@@ -1027,16 +1086,20 @@ int launch_varlen_pair(const HiVarlenArgs& v, cudaStream_t stream) {
     a.work_counter = reinterpret_cast<unsigned int*>(static_cast<char*>(v.workspace) + ((v.workspace_bytes - 256) & ~int64_t(255)));
     HI_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned int), stream));
   }
-  CUtensorMap mq, mk, mv;
+  CUtensorMap mq, mk, mv, mo;
   int rc = make_map_d(&mq, v.dtype, v.q, v.n_q_tokens, v.n_qo_heads, v.head_dim, v.q_row_stride, a.group, a.tq);
   if (rc != HI_OK) return rc;
+  rc = make_map_d(&mo, v.dtype, v.out, v.n_q_tokens, v.n_qo_heads, v.head_dim, v.out_row_stride, a.group, a.tq);
+  if (rc != HI_OK) return rc;
+  a.use_tma_store = v.head_dim == kP2D ? 1 : 0;
+  if (const char* env = tuning_env("HI_PAIR_TMA_STORE")) a.use_tma_store = a.use_tma_store && atoi(env) != 0;
   rc = make_map_d(&mk, v.dtype, v.k, v.n_k_tokens, v.n_kv_heads, v.head_dim, v.k_row_stride, 1, kP2TileN);
   if (rc != HI_OK) return rc;
   rc = make_map_d(&mv, v.dtype, v.v, v.n_k_tokens, v.n_kv_heads, v.head_dim, v.v_row_stride, 1, kP2TileN);
   if (rc != HI_OK) return rc;
   if (const char* env = tuning_env("HI_PAIR_DEBUG")) a.debug = atoi(env);
-  return v.dtype == HI_BF16 ? launch_pair_t<__nv_bfloat16, 0, true>(v.device, a, mq, mk, mv, stream)
-                            : launch_pair_t<__half, 0, true>(v.device, a, mq, mk, mv, stream);
+  return v.dtype == HI_BF16 ? launch_pair_t<__nv_bfloat16, 0, true>(v.device, a, mq, mk, mv, mo, stream)
+                            : launch_pair_t<__half, 0, true>(v.device, a, mq, mk, mv, mo, stream);
 }
 
 }  // namespace hi

@@ -104,6 +104,28 @@ __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const void* tmap,
       : "memory");
 }
 
+// 3-D tiled store shared -> global (bulk async-group completion; the issuing thread commits and waits).
+__device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+      ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// Every bulk group of this thread except the newest N has finished READING its shared-memory source (the buffer may be reused).
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// ... has completed (the global writes are done).
+template <int N>
+__device__ __forceinline__ void bulk_wait_group() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+
 // ---- TMEM allocation --------------------------------------------------------------------------------------------
 // Executed by one full warp. Writes the TMEM base address (lane 0, first column) to *smem_dst.
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t n_cols) {

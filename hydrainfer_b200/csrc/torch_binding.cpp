@@ -361,6 +361,13 @@ Tensor append_and_attend(const Tensor& query, const Tensor& key, const Tensor& v
 
 int last_launch_count() { return hi_last_launch_count(); }
 
+// The split-KV scratch of (device, torch's current stream of that device), at least `min_bytes` long: tests poison it, a CUDA-graph
+// runner can size it for its largest captured batch before capturing.
+Tensor workspace(int64_t device, int64_t min_bytes) {
+  const int dev = static_cast<int>(device);
+  return workspace_for(dev, current_stream(dev), min_bytes > 4096 ? min_bytes : hi_attention_workspace_bytes(0, 0, 128, 0));
+}
+
 // ---- block_migration -----------------------------------------------------------------------------------------------------------
 // Differences from the reference module, all inside its contract: the peer pool is mapped once per process and cached (the
 // reference re-opens the handle on every call, block_migration.cpp:213-215); all (layer, K/V, block) runs of a request move in
@@ -526,6 +533,7 @@ PYBIND11_MODULE(flash_attn, m) {
         py::arg("max_seqlen_k"), py::arg("softmax_scale"), py::arg("path") = 0, py::arg("work_items") = py::none(), py::arg("work_tile_tokens") = 0,
         py::arg("qk_work_hint") = 0);
   m.def("last_launch_count", &last_launch_count);
+  m.def("workspace", &workspace, py::arg("device"), py::arg("min_bytes") = 0);
 }
 
 PYBIND11_MODULE(block_migration, m) {
