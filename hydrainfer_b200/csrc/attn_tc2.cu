@@ -227,52 +227,18 @@ __device__ __forceinline__ unsigned long long trace_globaltimer() {
 }
 #endif
 
-// Epilogue of a whole, direct tile of a head_dim-128 launch: O / l as 16-bit rows through shared memory and one TMA store per
-// 64-dim half.  Thread r owns tile row r (TMEM lane); `stage` is the tile's 16 KiB staging buffer (128 rows x 128 B, 1024-byte
-// aligned), written in the 128B-swizzled layout of the tensor map - the layout the Q tile was loaded in.  Out of line on
-// purpose: its register needs (the row as 64 packed words) stay out of the allocation of the softmax step loop.
-template <typename T>
-__device__ __noinline__ void p2_store_tile_tma(const CUtensorMap* tm_o, uint32_t tmem_o, float inv_l, bool warp_active, uint32_t stage, int r,
-                                               uint32_t bar_id, uint32_t o_empty_bar, int head0, int token0) {
-  uint32_t pk[64];
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    uint32_t v[32];
-    if (warp_active) {
-      ptx::tmem_ld_x32(tmem_o + c * 32, v);
-      ptx::tmem_wait_ld();
-    }
-#pragma unroll
-    for (int e = 0; e < 32; e += 2) pk[c * 16 + (e >> 1)] = pack2<T>(__uint_as_float(v[e]) * inv_l, __uint_as_float(v[e + 1]) * inv_l);
-  }
-  ptx::tc_fence_before_sync();
-  ptx::mbar_arrive(o_empty_bar);  // O_t has left TMEM: the next item's first P.V may overwrite it
-  const uint32_t row_addr = stage + static_cast<uint32_t>(r) * 128u;
-  const bool issuer = r == 0;
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    if (issuer) ptx::bulk_wait_group_read<0>();  // the store that last used this buffer has read it
-    ptx::named_bar_sync(bar_id, kP2TileM);
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-      ptx::st_shared_v4(row_addr + static_cast<uint32_t>((c ^ (r & 7)) << 4), pk[h * 32 + c * 4], pk[h * 32 + c * 4 + 1], pk[h * 32 + c * 4 + 2],
-                        pk[h * 32 + c * 4 + 3]);
-    ptx::fence_proxy_async_smem();
-    ptx::named_bar_sync(bar_id, kP2TileM);
-    if (issuer) {
-      ptx::tma_store_3d(tm_o, stage, h * 64, head0, token0);
-      ptx::bulk_commit_group();
-    }
-  }
-}
-
 // PF = how many of every 4 (pairs of) exponentials run on the FMA pipes (exp2_poly2) instead of MUFU.EX2.
 template <typename T, int NK, int NV, int PF, bool VL = false>
 __global__ void __launch_bounds__(kP2Threads, 1)
 paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                        const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o, const P2Args a) {
   using L = P2Smem<NK, NV>;
-  static_assert(NK == 4 && NV == 4, "ring stages are addressed as step & 3");
+  static_assert(NK >= 3 && NV >= 3 && NK + NV == 8, "the K and V rings share 128 KiB; each needs 2 steps of lookahead at least");
+  // ring stage / phase of running step g (division by a compile-time constant)
+  auto k_stage = [](uint32_t g) -> uint32_t { return g % NK; };
+  auto k_phase = [](uint32_t g) -> uint32_t { return (g / NK) & 1u; };
+  auto v_stage = [](uint32_t g) -> uint32_t { return g % NV; };
+  auto v_phase = [](uint32_t g) -> uint32_t { return (g / NV) & 1u; };
   constexpr bool kBf16 = !std::is_same<T, __half>::value;
 
   extern __shared__ uint8_t smem_raw[];
@@ -339,7 +305,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     return k;
   };
 
-  // Running counters (identical in every role, never reset): g = K/V steps so far (ring stage g & 3, phase g >> 2);
+  // Running counters (identical in every role, never reset): g = K/V steps so far (ring stage g % N, phase (g / N) & 1);
   // per tile, steps so far (S/P buffer & 1, phase >> 1), items in which the tile was active (Q/O barriers) and items
   // with at least two steps (P.V(n-2) barrier).
   if (warp >= 8) {
@@ -416,10 +382,11 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
           const int blk_lane = blk_next;
           blk_next = pages_of(j + 1, n_valid_next);
           const uint32_t tx = static_cast<uint32_t>(n_valid) * n_halves * page_half_bytes;
-          const int st = g & 3;
+          const int st = static_cast<int>(is_k ? k_stage(g) : v_stage(g));
+          const uint32_t ph = is_k ? k_phase(g) : v_phase(g);
           const int kv0 = (it.j_begin + j) * kP2TileN;
           const bool tail = !is_k && (kv0 + kP2TileN > it.kv_len);  // at most one such step per item
-          ptx::mbar_wait(bar(b_empty + st), ((g >> 2) & 1u) ^ 1u);
+          ptx::mbar_wait(bar(b_empty + st), ph ^ 1u);
           trace(3, n_it, j);
           const uint32_t full_bar = tail ? bar(L::bVTail) : bar(b_full + st);
           uint32_t dst = ring + st * kP2Tile;
@@ -531,10 +498,11 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         for (int jj = 0; jj < 2; ++jj) {
           if (jj < n_all) {
             const uint32_t gj = g + jj;
-            ptx::mbar_wait(bar(L::bKFull + (gj & 3)), (gj >> 2) & 1u);
+            const int ks = static_cast<int>(k_stage(gj));
+            ptx::mbar_wait(bar(L::bKFull + ks), k_phase(gj));
             ptx::tc_fence_after_sync();
             if (ptx::elect_one()) {
-              if (jj < n_t) issue_qk(gj & 3, (gs + jj) & 1, jj == n_t - 1); else ptx::mbar_arrive(bar(L::bKEmpty + (gj & 3)));
+              if (jj < n_t) issue_qk(ks, (gs + jj) & 1, jj == n_t - 1); else ptx::mbar_arrive(bar(L::bKEmpty + ks));
             }
             __syncwarp();
           }
@@ -542,7 +510,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         // step j: P_t.V(j), then Q_t.K(j+2) into the S buffer P_t(j) just vacated (in order behind P_t.V(j))
         for (int j = 0; j < n_all; ++j) {
           const uint32_t gj = g + j;
-          const int s = gj & 3, s2 = (gj + 2) & 3, buf = (gs + j) & 1;
+          const int s = static_cast<int>(v_stage(gj)), s2 = static_cast<int>(k_stage(gj + 2)), buf = (gs + j) & 1;
           const bool has_pv = j < n_t;
           const bool more = j + 2 < n_all;
           if (j == max(n_all - 2, 0)) {  // warp 8 published the next index when it finished this item's K loads, steps ago
@@ -551,8 +519,8 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
             if (more_items) pair_nxt = p2_item_head(a, k, nxt);
           }
           if (j == n_all - 1 && more_items) p2_item_body<VL>(a, pair_nxt, nxt);
-          ptx::mbar_wait(bar(L::bVFull + s), (gj >> 2) & 1u);
-          if (more) ptx::mbar_wait(bar(L::bKFull + s2), ((gj + 2) >> 2) & 1u);
+          ptx::mbar_wait(bar(L::bVFull + s), v_phase(gj));
+          if (more) ptx::mbar_wait(bar(L::bKFull + s2), k_phase(gj + 2));
           if (has_pv) {
             if (j == 0) ptx::mbar_wait(bar(L::bOEmpty + t), (n_act & 1u) ^ 1u);  // the previous item's O_t has been read out
             ptx::mbar_wait(bar(L::bPFull + 2 * t + buf), ((gs + j) >> 1) & 1u);
@@ -735,46 +703,56 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       }
       // Whole tiles of a head_dim-128 launch whose rows go straight to `out` leave through shared memory and ONE TMA store
       // per 64-dim half: the thread (= row) writes its 128 B of the half into the tile's staging buffer in the 128B-swizzled
-      // layout of the tensor map (the layout Q was loaded in), a bulk tensor store moves the {64 dims, group heads, tq tokens}
-      // box.  A per-row 16-byte store instruction touches 32 different 256-byte rows per warp; this path writes whole lines.
-      // Tiles cut by the end of the sequence (their box would cover the next sequence's tokens), split-KV partials and
-      // other head dims keep the per-row stores below.
+      // layout of the tensor map (the layout Q was loaded in) and a bulk tensor store moves the {64 dims, group heads, tq
+      // tokens} box.  (A per-row 16-byte store instruction touches 32 different 256-byte rows per warp.)  Tiles cut by the end
+      // of the sequence (their box would cover the next sequence's tokens) and other head dims store per row; split-KV
+      // partials leave as fp32.  All three share the TMEM loads and the packing: one register footprint for the epilogue.
       const bool tma_out = a.use_tma_store && direct && d_out == kP2D && first + a.tq <= it.q_len;  // uniform over the warpgroup
-      if (tma_out) {
-        p2_store_tile_tma<T>(&tm_o, tmem_o, inv_l, warp_active, smem_base + L::kOst + t * kP2QHalf, r, 1 + t, bar(L::bOEmpty + t), it.kvh * a.group,
-                             it.q_start + first);
-      } else {
+      const uint32_t stage = smem_base + L::kOst + t * kP2QHalf;
+      const uint32_t row_addr = stage + static_cast<uint32_t>(r) * 128u;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        if (warp_active && c * 32 < d_out) {
-          ptx::tmem_ld_x32(tmem_o + c * 32, v);
-          ptx::tmem_wait_ld();
-        }
-        if (c == 3) {  // O_t has left TMEM: the next item's first P.V may overwrite it
-          ptx::tc_fence_before_sync();
-          ptx::mbar_arrive(bar(L::bOEmpty + t));
-        }
-        if (warp_active && row_valid) {
-          if (!direct) {
-            float4* dst = reinterpret_cast<float4*>(a.part_o + pidx * kP2D + c * 32);
+      for (int h = 0; h < 2; ++h) {
+        uint32_t pk[32];  // 64 dims of the row as 16-bit pairs
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          if (warp_active && (h * 2 + c) * 32 < d_out) {
+            ptx::tmem_ld_x32(tmem_o + (h * 2 + c) * 32, v);
+            ptx::tmem_wait_ld();
+          }
+          if (!direct && warp_active && row_valid) {
+            float4* dst = reinterpret_cast<float4*>(a.part_o + pidx * kP2D + (h * 2 + c) * 32);
 #pragma unroll
             for (int e = 0; e < 32; e += 4)
               dst[e >> 2] = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
-          } else {
+          }
 #pragma unroll
-            for (int e = 0; e < 32; e += 8) {
-              if (VL && c * 32 + e >= d_out) break;
-              uint4 w;
-              w.x = pack2<T>(__uint_as_float(v[e + 0]) * inv_l, __uint_as_float(v[e + 1]) * inv_l);
-              w.y = pack2<T>(__uint_as_float(v[e + 2]) * inv_l, __uint_as_float(v[e + 3]) * inv_l);
-              w.z = pack2<T>(__uint_as_float(v[e + 4]) * inv_l, __uint_as_float(v[e + 5]) * inv_l);
-              w.w = pack2<T>(__uint_as_float(v[e + 6]) * inv_l, __uint_as_float(v[e + 7]) * inv_l);
-              *reinterpret_cast<uint4*>(orow + c * 32 + e) = w;
-            }
+          for (int e = 0; e < 32; e += 2) pk[c * 16 + (e >> 1)] = pack2<T>(__uint_as_float(v[e]) * inv_l, __uint_as_float(v[e + 1]) * inv_l);
+        }
+        if (h == 1) {  // O_t has left TMEM: the next item's first P.V may overwrite it
+          ptx::tc_fence_before_sync();
+          ptx::mbar_arrive(bar(L::bOEmpty + t));
+        }
+        if (tma_out) {
+          // (the TMEM loads and the packing of half 1 ran while the TMA engine was still reading half 0 out of the buffer)
+          if (r == 0) ptx::bulk_wait_group_read<0>();  // the store that last used this buffer has read it
+          ptx::named_bar_sync(1 + t, kP2TileM);
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            ptx::st_shared_v4(row_addr + static_cast<uint32_t>((c ^ (r & 7)) << 4), pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
+          ptx::fence_proxy_async_smem();
+          ptx::named_bar_sync(1 + t, kP2TileM);
+          if (r == 0) {
+            ptx::tma_store_3d(&tm_o, stage, h * 64, it.kvh * a.group, it.q_start + first);
+            ptx::bulk_commit_group();
+          }
+        } else if (direct && warp_active && row_valid) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            if (VL && h * 64 + c * 8 >= d_out) break;
+            *reinterpret_cast<uint4*>(orow + h * 64 + c * 8) = make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
           }
         }
-      }
       }
       trace(6, n_it, 0);
       gs += n_mine;
@@ -874,10 +852,10 @@ bool attn_pair_supported(const HiAttnArgs& args) {
          args.n_blocks > 0;
 }
 
-template <typename T, int PF, bool VL = false>
-static int launch_pair_t(int device, const P2Args& a, const CUtensorMap& mq, const CUtensorMap& mk,
-                         const CUtensorMap& mv, const CUtensorMap& mo, cudaStream_t stream) {
-  constexpr int NK = 4, NV = 4;  // 4 + 4 steps of 64 keys (16 KiB each) + 64 KiB of Q = 192 KiB
+template <typename T, int PF, bool VL, int NK, int NV>
+static int launch_pair_ring(int device, const P2Args& a, const CUtensorMap& mq, const CUtensorMap& mk,
+                            const CUtensorMap& mv, const CUtensorMap& mo, cudaStream_t stream) {
+  // NK + NV = 8 steps of 64 keys (16 KiB each) + 64 KiB of Q + 32 KiB of output staging = 224 KiB
   using L = P2Smem<NK, NV>;
   static PerDeviceFlags configured;
   HI_CUDA(configure_dynamic_smem(configured, paged_attn_pair_kernel<T, NK, NV, PF, VL>, L::kDynamicBytes));
@@ -893,6 +871,15 @@ static int launch_pair_t(int device, const P2Args& a, const CUtensorMap& mq, con
   note_launch();
   HI_CUDA(cudaGetLastError());
   return HI_OK;
+}
+
+// Split of the 8 ring stages between K and V: 4 + 4.  (Q.K^T runs two steps ahead of P.V, so 5 + 3 would give both rings the same
+// lookahead; measured on B200 it loses 2-6 % on every prefill shape - the V ring then stalls P.V behind the softmax of the
+// lagging tile - so only 4 + 4 is instantiated.  The kernel itself is generic in NK / NV.)
+template <typename T, int PF, bool VL = false>
+static int launch_pair_t(int device, const P2Args& a, const CUtensorMap& mq, const CUtensorMap& mk,
+                         const CUtensorMap& mv, const CUtensorMap& mo, cudaStream_t stream) {
+  return launch_pair_ring<T, PF, VL, 4, 4>(device, a, mq, mk, mv, mo, stream);
 }
 
 int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {

@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+for c in pre1k cfg3p; do
+  HI_B200_LIB=hydrainfer_b200/lib/libhi_b200_trace.so timeout 300 python tools/pair_trace.py $c --items 3 --raw > gpurun_out/trace_$c.txt 2>&1
+  grep -v "^ *[0-9]* \(K-tma\|V-tma\|mma\|smx\)" gpurun_out/trace_$c.txt | head -40
+done
