@@ -294,7 +294,7 @@ paged_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       const float mxs = mx * a.scale_log2;
       if (j == 0) {
         m_used = (mxs == -INFINITY) ? 0.f : mxs;
-      } else if (__any_sync(0xffffffffu, mxs > m_used + kRescaleThreshold)) {
+      } else if (__any_sync(0xffffffffu, r < rows_real && mxs > m_used + kRescaleThreshold)) {  // padding rows (stale Q) do not vote
         // Lazy rescale: the whole warp pays the TMEM round trip only when some row's max grew by > 2^8.
         const float m_new = fmaxf(m_used, mxs);
         const float alpha = fast_exp2(m_used - m_new);

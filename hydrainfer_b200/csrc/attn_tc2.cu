@@ -635,7 +635,9 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
           const float mxs = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * a.scale_log2;
           if (j == 0) {
             m_used = (mxs == -INFINITY) ? 0.f : mxs;
-          } else if (__any_sync(0xffffffffu, mxs > m_used + kP2Rescale)) {
+          } else if (__any_sync(0xffffffffu, r < rows_real && mxs > m_used + kP2Rescale)) {
+            // (padding rows hold scores of stale Q rows: they must not vote, or the warp's rounding would depend on which
+            // item used this buffer before - results would stay within tolerance but not be reproducible run to run)
             // Lazy rescale: the warp pays the TMEM round trip only when some row's max grew by more than 2^8.  O_t must be
             // quiescent: P_t.V(j-1) complete (implied by S_t(j+1), issued behind it; the last step has its own commit) and
             // P_t.V(j) not issued before this thread's P arrival below.

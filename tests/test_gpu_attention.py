@@ -418,3 +418,16 @@ def test_unsupported_arguments_raise():
     with pytest.raises(RuntimeError, match="tcgen05"):
         mha_varlen_fwd(torch.empty_like(q64), q64, b64.key_cache, b64.value_cache, i32([0, 4]), i32([0, 20]), i32(b64.block_tables), i32([0, 2]),
                        None, 4, 20, 0.1, 0, -1, 0, 0, TC)
+
+
+@pytest.mark.parametrize("path", [TC, PAIR])
+def test_split_prefill_is_reproducible_run_to_run(path):
+    """Same inputs, same launch -> same bits, whichever work item used a CTA's buffers before.  (Padding rows of a tile hold
+    scores of stale Q rows; when they took part in the warp's lazy-rescale vote, the rounding of the warp's real rows depended on
+    the item order of the dynamic scheduler: within tolerance, but different from run to run once a launch had many splits.)"""
+    batch = make_batch([(300, 4000), (64, 64)], 28, 4, 128, 16, dtype=torch.bfloat16, seed=32).to(DEV)
+    q3 = batch.query.view(batch.n_tokens, 28, 128)
+    outs = [run_attention(q3, batch.key_cache, batch.value_cache, batch.q_cu_seq_lens, batch.kv_cu_seq_lens, batch.block_tables,
+                          batch.cu_blocks_lens, batch.q_max, batch.kv_max, 128, path) for _ in range(5)]
+    for i, o in enumerate(outs[1:], 1):
+        assert torch.equal(outs[0], o), f"path {path}: run {i} differs from run 0 in {int((outs[0] != o).sum())} elements"

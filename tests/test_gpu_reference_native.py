@@ -96,14 +96,7 @@ def test_set_image_cache_matches_reference_cuda(geom, dtype):
 
 
 # ---- apply_rotary_pos_emb ----------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("interleaved", [False, True])
-@pytest.mark.parametrize("geom", [(64, 32, 32, 128, 128), (37, 28, 4, 128, 128), (9, 8, 2, 64, 32)])
-def test_rotary_matches_reference_cuda_16bit(geom, interleaved, dtype):
-    """The reference kernel reads the cos/sin table in the element type and rounds every product and the sum to it
-    (rope.cu:9-29 with c10::Half / c10::BFloat16 operators): bit-exact."""
-    ref = _need("position_embedding")
-    from hydrainfer_b200._C.kernel.position_embedding import apply_rotary_pos_emb
+def _rope_inputs(geom, dtype):
     t, hq, hkv, d, rd = geom
     g = torch.Generator().manual_seed(t * 7 + rd)
     q = torch.randn(t, hq, d, generator=g).to(dtype).to(DEV)
@@ -112,11 +105,38 @@ def test_rotary_matches_reference_cuda_16bit(geom, interleaved, dtype):
     inv = 1.0 / torch.pow(torch.tensor(10000.0), torch.arange(0, rd, 2, dtype=torch.float) / rd)
     freqs = torch.einsum("i,j->ij", torch.arange(4096, dtype=torch.float), inv)
     cos_sin = torch.cat([freqs.cos()[:, None, :], freqs.sin()[:, None, :]], dim=1).to(dtype).to(DEV)  # rotary_embedding.py:113-116
+    return q, k, pos, cos_sin
+
+
+@pytest.mark.parametrize("interleaved", [False, True])
+@pytest.mark.parametrize("geom", [(64, 32, 32, 128, 128), (37, 28, 4, 128, 128), (9, 8, 2, 64, 32)])
+def test_rotary_matches_reference_cuda_fp16(geom, interleaved):
+    """The reference kernel computes `x*c - y*s` in native `half` (dispatch.h:21-24, rope.cu:27-28), which nvcc contracts into a
+    half FMA: ONE rounding where the reference's torch handler (rotary_embedding.py:47-99; the definition the oracle, the golden
+    fixtures and hi_rope_append follow bit for bit) has two.  So the two reference paths themselves differ by an ulp; against the
+    compiled kernel the bar is one fp16 ulp, with most elements identical."""
+    ref = _need("position_embedding")
+    from hydrainfer_b200._C.kernel.position_embedding import apply_rotary_pos_emb
+    q, k, pos, cos_sin = _rope_inputs(geom, torch.float16)
+    rd = geom[4]
     q_ref, k_ref = q.clone(), k.clone()
     ref.apply_rotary_pos_emb(q_ref, k_ref, pos, cos_sin, rd, interleaved)
     apply_rotary_pos_emb(q, k, pos, cos_sin, rd, interleaved)
     torch.cuda.synchronize()
-    assert torch.equal(q, q_ref) and torch.equal(k, k_ref)
+    for ours, theirs in ((q, q_ref), (k, k_ref)):
+        ulp = torch.maximum(theirs.float().abs(), torch.tensor(2.0 ** -14, device=DEV)).log2().floor().exp2() * 2.0 ** -10
+        assert bool(((ours.float() - theirs.float()).abs() <= ulp).all()), "more than one fp16 ulp from the reference's compiled kernel"
+        assert (ours == theirs).float().mean().item() > 0.8
+        assert torch.equal(ours[..., rd:], theirs[..., rd:])  # the pass-through dims are copies
+
+
+def test_reference_cuda_rotary_has_no_bf16():
+    """dispatch.h:12-29 knows Float and Half only: the reference's compiled rotary kernel rejects bf16 (its handler chain then has
+    no fused path for bf16 models); hi_rope_append covers bf16, pinned by the torch-handler fixtures of tests/test_rope.py."""
+    ref = _need("position_embedding")
+    q, k, pos, cos_sin = _rope_inputs((9, 8, 2, 64, 32), torch.bfloat16)
+    with pytest.raises(RuntimeError, match="dispatch"):
+        ref.apply_rotary_pos_emb(q, k, pos, cos_sin, 32, False)
 
 
 def test_rotary_matches_reference_cuda_fp32():

@@ -191,6 +191,9 @@ def main():
         ("cfg4_2k", [(1, 2048)] * 256, 64, 8, [SIMT, TC, DEC]),
         ("cfg4_4k", [(1, 4096)] * 256, 64, 8, [SIMT, TC, DEC]),
         ("cfg4_shard8", [(1, 4096)] * 32, 64, 8, [SIMT, TC, DEC]),
+        ("cfg4_shard8_2k", [(1, 2048)] * 32, 64, 8, [DEC]),
+        ("cfg4_shard4_2k", [(1, 2048)] * 64, 64, 8, [DEC]),
+        ("cfg4_shard2_2k", [(1, 2048)] * 128, 64, 8, [DEC]),
     ]
     lines = []
     for name, seq_lens, hq, hkv, paths in cases:
