@@ -21,6 +21,8 @@ clocks) and, as extras on the same line, the other halves of BASELINE.json's met
                    NVLink pairs at N > 1, next to a cudaMemcpyPeerAsync of the same bytes timed in the same run; every moved block
                    is verified against checksums of the source blocks
   "migrate"        the 256-block LLaVA point of that sweep (kept as its own key: SCALE_r01 carried it)
+  "migrate_under_decode"  the receiver decodes (the bench workload) WHILE it pulls 2 GiB requests on a side stream, per CTA cap of
+                   the migration kernel: decode tokens/s alone / under the pull, pull GB/s alone / under decode
 `--impl reference` times the CPU restatement of the reference's torch path (oracle/, kind "port") on the box's host cores instead.
 """
 from __future__ import annotations
@@ -350,6 +352,7 @@ def run_ours(args) -> None:
     prefill = measure_prefill(dev) if world == 1 and not args.no_extras else None
     cfg4 = measure_cfg4(rank, world, dev) if not args.no_extras else None
     migrate, migrate_sweep = measure_migration_sweep(rank, world, local, dev) if not args.no_extras else (None, None)
+    migrate_under_decode = measure_migration_under_decode(rank, world, local, dev) if not args.no_extras else None
     extras_s = time.time() - extras_t0
 
     # ---- aggregate over ranks: MAX time, SUM tokens ---------------------------------------------------------------------------
@@ -390,7 +393,7 @@ def run_ours(args) -> None:
                     "result_equals_resident_path": e2e_checked},
             "gpu_launches": launches,
             "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"), "reasons": clocks.get("reasons", []), "samples": clocks.get("samples", 0)},
-            "migrate": migrate, "migrate_sweep": migrate_sweep, "prefill": prefill, "cfg4": cfg4,
+            "migrate": migrate, "migrate_sweep": migrate_sweep, "migrate_under_decode": migrate_under_decode, "prefill": prefill, "cfg4": cfg4,
             "reference_gpu_baseline": ref_gpu, "extras_seconds": extras_s,
         }
         emit_result(line)
@@ -696,6 +699,85 @@ def measure_migration_sweep(rank: int, world: int, local: int, dev: torch.device
             if pool_name == "llava7b" and n_move == 256:
                 headline = point
     return headline, sweep
+
+
+def measure_migration_under_decode(rank: int, world: int, local: int, dev: torch.device) -> dict:
+    """What the disaggregated protocol actually does (hydrainfer/cluster/epdnode.py:362-447): the decode node pulls a request's
+    pages on its migrate stream WHILE it runs decode steps.  Pairs 2i -> 2i+1; the receiver runs the bench workload's decode layer
+    call back to back on the compute stream and, beside it, pulls 256 LLaVA-7B blocks (2 GiB) over and over on a side stream.
+    Reported per CTA cap of the migration kernel: decode tokens/s of the receiver (alone and under the pull) and the pull's GB/s
+    (alone and under decode).  N = 1: the same on one GPU (pool -> pool), where the two streams share HBM instead of NVLink."""
+    import torch.distributed as dist
+    from hydrainfer_b200._C.data_transfer import block_migration as bm
+    geom = MIGRATION_POOLS["llava7b"]
+    n_move, pool_blocks = 256, 288
+    shape = (geom["n_layers"], geom["n_tokens"], pool_blocks, geom["block_size"], geom["n_heads"], geom["head_size"])
+    payload = n_move * geom["n_layers"] * geom["n_tokens"] * geom["block_size"] * geom["n_heads"] * geom["head_size"] * 2
+    pool = torch.empty(shape, dtype=DTYPE, device=dev).normal_()
+    g = torch.Generator().manual_seed(300)
+    src_bt = torch.randperm(pool_blocks, generator=g)[:n_move].tolist()
+    dst_bt = torch.randperm(pool_blocks, generator=g)[:n_move].tolist()
+    handle = bm.get_ipc_mem_handle(pool)
+    is_receiver = True
+    if world > 1:
+        handles = [None] * world
+        dist.all_gather_object(handles, handle)
+        is_receiver = rank % 2 == 1
+        src_handle, dst_pool = (handles[rank - 1] if is_receiver else handle), pool
+    else:
+        src_handle, dst_pool = handle, torch.empty_like(pool)
+    batch, step = _layer_case([(1, CTX)] * BATCH, HQ, HKV, dev, seed=2000 + rank)
+    compute, side = torch.cuda.current_stream(dev), torch.cuda.Stream(dev)
+    n_steps, n_pulls = 40, 3
+
+    def run(decode: bool, pull: bool) -> tuple[float, float]:
+        """-> (ms per decode step, ms per pull), each timed on its own stream while the other (if any) runs beside it."""
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if is_receiver:
+            if pull:
+                side.wait_stream(compute)
+                with torch.cuda.stream(side):
+                    p0.record(side)
+                    for _ in range(n_pulls):
+                        bm.migrate_blocks(src_bt, dst_bt, src_handle, dst_pool, pool_blocks)
+                    p1.record(side)
+            if decode:
+                d0.record(compute)
+                for _ in range(n_steps):
+                    step()
+                d1.record(compute)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        if not is_receiver:
+            return 0.0, 0.0
+        return (d0.elapsed_time(d1) / n_steps if decode else 0.0), (p0.elapsed_time(p1) / n_pulls if pull else 0.0)
+
+    out = {"pattern": (f"{world // 2} pair(s) 2i->2i+1 over NVLink, receiver decodes while it pulls" if world > 1 else "one GPU: pool->pool pull beside the decode step (shared HBM)"),
+           "decode_workload": WORKLOAD, "pull": f"{n_move} LLaVA-7B blocks ({payload} bytes) x {n_pulls} back to back on a side stream", "caps": {}}
+    for _ in range(2):
+        run(True, True)  # warm-up (IPC mapping, workspaces)
+    alone_decode_ms, _ = run(True, False)
+    for cap in (0, 296, 148, 64):
+        bm.set_max_ctas(cap)
+        _, alone_pull_ms = run(False, True)
+        both_decode_ms, both_pull_ms = run(True, True)
+        vals = torch.tensor([alone_decode_ms, alone_pull_ms, both_decode_ms, both_pull_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        a_d, a_p, b_d, b_p = (float(x) for x in vals.tolist())
+        out["caps"]["default (8 CTAs/SM)" if cap == 0 else str(cap)] = {
+            "decode_tokens_per_s_alone": BATCH / a_d * 1e3, "decode_tokens_per_s_under_pull": BATCH / b_d * 1e3, "decode_slowdown": b_d / a_d,
+            "pull_gbs_alone": payload / a_p / 1e6, "pull_gbs_under_decode": payload / b_p / 1e6,
+            "note": "the pull outlasts or ends inside the 40 timed decode steps depending on its rate; both figures are per-stream event times"}
+    bm.set_max_ctas(0)
+    del pool, dst_pool, batch, step
+    torch.cuda.empty_cache()
+    return out
 
 
 def reference_gpu_baseline(dev: torch.device, steps: int, warmup: int) -> dict:

@@ -85,6 +85,9 @@ SIGNATURES = {
     "hi_attention_tile_tokens": (c_int32, [c_int32, c_int32]),
     "hi_migrate_blocks": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, HiPoolGeom, HiPoolGeom, c_int, c_void_p]),
     "hi_migrate_blocks_layers": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, HiPoolGeom, HiPoolGeom, c_int64, c_int64, c_int, c_void_p]),
+    "hi_migrate_blocks_host_tables": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, HiPoolGeom, HiPoolGeom, c_int64, c_int64, c_int, c_void_p]),
+    "hi_migrate_inline_table_blocks": (c_int, []),
+    "hi_migrate_set_max_ctas": (c_int, [c_int]),
     "hi_ipc_get_handle": (c_int, [c_void_p, POINTER(c_uint8), POINTER(c_int64), c_int]),
     "hi_ipc_open_handle": (c_int, [POINTER(c_uint8), c_int64, c_int, POINTER(c_void_p)]),
     "hi_ipc_close_all": (c_int, []),

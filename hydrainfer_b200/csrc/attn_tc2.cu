@@ -97,7 +97,11 @@ struct P2Smem {
   static constexpr int kK = 2 * kP2QTile;
   static constexpr int kV = kK + NK * kP2Tile;
   static constexpr int kOst = kV + NV * kP2Tile;        // output staging for the TMA-store epilogue: one 64-dim half (128 rows x 128 B) per tile
+#ifdef HI_P2_NO_STAGING  // dev variant: the round-1 shared-memory footprint (192 KiB), per-row stores only
+  static constexpr int kBars = kOst;
+#else
   static constexpr int kBars = kOst + 2 * kP2QHalf;
+#endif
   static constexpr int bQFull = 0;                      // [2]
   static constexpr int bKFull = 2;                      // [NK]
   static constexpr int bKEmpty = bKFull + NK;
@@ -1000,6 +1004,9 @@ int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
   if (rc != HI_OK) return rc;
 
   a.use_tma_store = 1;
+#ifdef HI_P2_NO_STAGING
+  a.use_tma_store = 0;
+#endif
   if (const char* env = tuning_env("HI_PAIR_TMA_STORE")) a.use_tma_store = atoi(env) != 0;  // A/B switch
   if (const char* env = tuning_env("HI_PAIR_DEBUG")) a.debug = atoi(env);
   int poly = 0;  // exponentials per 4 moved from MUFU to the FMA pipes (measured: no gain while the softmax warps have idle issue slots)
@@ -1081,6 +1088,9 @@ int launch_varlen_pair(const HiVarlenArgs& v, cudaStream_t stream) {
   rc = make_map_d(&mo, v.dtype, v.out, v.n_q_tokens, v.n_qo_heads, v.head_dim, v.out_row_stride, a.group, a.tq);
   if (rc != HI_OK) return rc;
   a.use_tma_store = v.head_dim == kP2D ? 1 : 0;
+#ifdef HI_P2_NO_STAGING
+  a.use_tma_store = 0;
+#endif
   if (const char* env = tuning_env("HI_PAIR_TMA_STORE")) a.use_tma_store = a.use_tma_store && atoi(env) != 0;
   rc = make_map_d(&mk, v.dtype, v.k, v.n_k_tokens, v.n_kv_heads, v.head_dim, v.k_row_stride, 1, kP2TileN);
   if (rc != HI_OK) return rc;

@@ -35,15 +35,16 @@ constexpr int64_t kPieceBytes = kMigrateThreads * kVecPerThread * 16;  // 16 KiB
 // Persistent CTAs walk 16-KiB pieces of the (plane, block) runs.  A run is contiguous in both pools
 // (INDEX_6D of block_migration.cpp:26-27 with the three innermost indices 0), so every access is a
 // fully coalesced 128-bit vector; each thread keeps kVecPerThread loads in flight to cover NVLink latency.
-__global__ void __launch_bounds__(kMigrateThreads) migrate_gather_kernel(const MigrateArgs a) {
+template <typename Tables>
+__device__ __forceinline__ void migrate_gather_body(const MigrateArgs& a, const Tables& tables) {
   for (int64_t piece = blockIdx.x; piece < a.total_pieces; piece += gridDim.x) {
     const int64_t run = piece / a.pieces_per_run;
     const int64_t off = (piece - run * a.pieces_per_run) * kPieceBytes;
     const int64_t plane_rel = run / a.n;
     const int64_t i = run - plane_rel * a.n;
     const int64_t plane = a.plane_begin + plane_rel;
-    const int64_t sb = __ldg(a.src_blocks + i);
-    const int64_t db = __ldg(a.dst_blocks + i);
+    const int64_t sb = tables.src(i);
+    const int64_t db = tables.dst(i);
     const char* __restrict__ src = a.src_pool + plane * a.src_plane_bytes + sb * a.run_bytes + off;
     char* __restrict__ dst = a.dst_pool + plane * a.dst_plane_bytes + db * a.run_bytes + off;
     const int64_t left = a.run_bytes - off;
@@ -62,6 +63,33 @@ __global__ void __launch_bounds__(kMigrateThreads) migrate_gather_kernel(const M
   }
 }
 
+struct DeviceTables {
+  const int32_t* s;
+  const int32_t* d;
+  __device__ __forceinline__ int64_t src(int64_t i) const { return __ldg(s + i); }
+  __device__ __forceinline__ int64_t dst(int64_t i) const { return __ldg(d + i); }
+};
+__global__ void __launch_bounds__(kMigrateThreads) migrate_gather_kernel(const MigrateArgs a) {
+  migrate_gather_body(a, DeviceTables{a.src_blocks, a.dst_blocks});
+}
+
+// Small requests carry their block tables IN the kernel parameters: no staging buffer, no host-to-device copy in front of the
+// launch (a 16-block request is a few tens of microseconds of transfer, comparable with an extra stream operation).
+constexpr int kInlineBlocks = 384;  // 2 x 384 x 4 B = 3 KiB of the 4 KiB parameter space
+struct MigrateInlineArgs {
+  MigrateArgs base;
+  int32_t src[kInlineBlocks];
+  int32_t dst[kInlineBlocks];
+};
+struct InlineTables {
+  const MigrateInlineArgs* p;
+  __device__ __forceinline__ int64_t src(int64_t i) const { return p->src[i]; }
+  __device__ __forceinline__ int64_t dst(int64_t i) const { return p->dst[i]; }
+};
+__global__ void __launch_bounds__(kMigrateThreads) migrate_gather_inline_kernel(const __grid_constant__ MigrateInlineArgs a) {
+  migrate_gather_body(a.base, InlineTables{&a});
+}
+
 // ---- IPC mapping cache -------------------------------------------------------------------------------------------
 struct IpcEntry {
   uint8_t handle[64];
@@ -78,17 +106,12 @@ extern "C" int hi_migrate_blocks(const int32_t* src_blocks, const int32_t* dst_b
   return hi_migrate_blocks_layers(src_blocks, dst_blocks, n, src_pool, dst_pool, src, dst, 0, src.n_layers, device, stream);
 }
 
-extern "C" int hi_migrate_blocks_layers(const int32_t* src_blocks, const int32_t* dst_blocks, int64_t n, const void* src_pool,
-                                        void* dst_pool, HiPoolGeom src, HiPoolGeom dst, int64_t layer_begin, int64_t layer_end,
-                                        int device, void* stream) {
-  using namespace hi;
-  reset_launch_count();
-  HI_CHECK_ARG(n >= 0, "migrate_blocks: negative block count");
-  HI_CHECK_ARG(layer_begin >= 0 && layer_begin <= layer_end && layer_end <= src.n_layers,
-               "migrate_blocks: layer range [%lld, %lld) outside the pool's %lld layers", (long long)layer_begin,
-               (long long)layer_end, (long long)src.n_layers);
-  if (n == 0 || layer_begin == layer_end) return HI_OK;
-  HI_CHECK_ARG(src_blocks && dst_blocks && src_pool && dst_pool, "migrate_blocks: null pointer");
+namespace hi {
+static std::atomic<int> g_migrate_max_ctas{0};  // 0 = no cap (process-wide tuning knob)
+// Shared by the device-table and the inline-table entry points: checks + geometry -> MigrateArgs and the grid size.
+static int prepare_migration(MigrateArgs& a, int64_t& grid, int64_t n, const void* src_pool, void* dst_pool, const HiPoolGeom& src,
+                             const HiPoolGeom& dst, int64_t layer_begin, int64_t layer_end, int device) {
+  HI_CHECK_ARG(src_pool && dst_pool, "migrate_blocks: null pointer");
   HI_CHECK_ARG(src.n_layers == dst.n_layers && src.n_tokens == dst.n_tokens && src.run_bytes == dst.run_bytes,
                "migrate_blocks: pools differ in more than n_blocks (layers %lld/%lld, tokens %lld/%lld, run bytes %lld/%lld)",
                (long long)src.n_layers, (long long)dst.n_layers, (long long)src.n_tokens, (long long)dst.n_tokens,
@@ -96,11 +119,6 @@ extern "C" int hi_migrate_blocks_layers(const int32_t* src_blocks, const int32_t
   HI_CHECK_ARG(src.run_bytes > 0 && src.run_bytes % 16 == 0, "migrate_blocks: run of %lld bytes is not a multiple of 16",
                (long long)src.run_bytes);
   HI_CHECK_ARG(aligned_to(src_pool, 16) && aligned_to(dst_pool, 16), "migrate_blocks: pools must be 16-byte aligned");
-  HI_DEVICE_GUARD(device);
-
-  MigrateArgs a{};
-  a.src_blocks = src_blocks;
-  a.dst_blocks = dst_blocks;
   a.src_pool = static_cast<const char*>(src_pool);
   a.dst_pool = static_cast<char*>(dst_pool);
   a.n = n;
@@ -111,17 +129,73 @@ extern "C" int hi_migrate_blocks_layers(const int32_t* src_blocks, const int32_t
   a.dst_plane_bytes = dst.n_blocks * dst.run_bytes;
   a.pieces_per_run = (a.run_bytes + kPieceBytes - 1) / kPieceBytes;
   a.total_pieces = a.planes * n * a.pieces_per_run;
-
   const int sm_count = sm_count_of(device);
   HI_CHECK_ARG(sm_count > 0, "migrate_blocks: cannot read the SM count of device %d", device);
-  // 8 resident CTAs of 256 threads per SM = 128 KiB of loads in flight per SM.
-  int64_t grid = static_cast<int64_t>(sm_count) * 8;
+  // 8 resident CTAs of 256 threads per SM = 128 KiB of loads in flight per SM; hi_migrate_set_max_ctas() lowers the grid so a pull
+  // leaves SM slots (and HBM write bandwidth) to the decode step running beside it on the receiving GPU.
+  grid = static_cast<int64_t>(sm_count) * 8;
+  const int cap = g_migrate_max_ctas.load(std::memory_order_relaxed);
+  if (cap > 0 && grid > cap) grid = cap;
   if (grid > a.total_pieces) grid = a.total_pieces;
+  return HI_OK;
+}
+}  // namespace hi
+
+extern "C" int hi_migrate_set_max_ctas(int max_ctas) {
+  hi::g_migrate_max_ctas.store(max_ctas > 0 ? max_ctas : 0, std::memory_order_relaxed);
+  return HI_OK;
+}
+
+extern "C" int hi_migrate_blocks_layers(const int32_t* src_blocks, const int32_t* dst_blocks, int64_t n, const void* src_pool,
+                                        void* dst_pool, HiPoolGeom src, HiPoolGeom dst, int64_t layer_begin, int64_t layer_end,
+                                        int device, void* stream) {
+  using namespace hi;
+  reset_launch_count();
+  HI_CHECK_ARG(n >= 0, "migrate_blocks: negative block count");
+  HI_CHECK_ARG(layer_begin >= 0 && layer_begin <= layer_end && layer_end <= src.n_layers,
+               "migrate_blocks: layer range [%lld, %lld) outside the pool's %lld layers", (long long)layer_begin,
+               (long long)layer_end, (long long)src.n_layers);
+  if (n == 0 || layer_begin == layer_end) return HI_OK;
+  HI_CHECK_ARG(src_blocks && dst_blocks, "migrate_blocks: null pointer");
+  MigrateArgs a{};
+  int64_t grid = 0;
+  const int rc = prepare_migration(a, grid, n, src_pool, dst_pool, src, dst, layer_begin, layer_end, device);
+  if (rc != HI_OK) return rc;
+  a.src_blocks = src_blocks;
+  a.dst_blocks = dst_blocks;
+  HI_DEVICE_GUARD(device);
   migrate_gather_kernel<<<static_cast<unsigned>(grid), kMigrateThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
   note_launch();
   HI_CUDA(cudaGetLastError());
   return HI_OK;
 }
+
+extern "C" int hi_migrate_blocks_host_tables(const int32_t* src_blocks_host, const int32_t* dst_blocks_host, int64_t n, const void* src_pool,
+                                             void* dst_pool, HiPoolGeom src, HiPoolGeom dst, int64_t layer_begin, int64_t layer_end,
+                                             int device, void* stream) {
+  using namespace hi;
+  reset_launch_count();
+  HI_CHECK_ARG(n >= 0 && n <= kInlineBlocks, "migrate_blocks: %lld blocks exceed the %d an inline table holds (use hi_migrate_blocks_layers)",
+               (long long)n, kInlineBlocks);
+  HI_CHECK_ARG(layer_begin >= 0 && layer_begin <= layer_end && layer_end <= src.n_layers,
+               "migrate_blocks: layer range [%lld, %lld) outside the pool's %lld layers", (long long)layer_begin,
+               (long long)layer_end, (long long)src.n_layers);
+  if (n == 0 || layer_begin == layer_end) return HI_OK;
+  HI_CHECK_ARG(src_blocks_host && dst_blocks_host, "migrate_blocks: null pointer");
+  MigrateInlineArgs a{};
+  int64_t grid = 0;
+  const int rc = prepare_migration(a.base, grid, n, src_pool, dst_pool, src, dst, layer_begin, layer_end, device);
+  if (rc != HI_OK) return rc;
+  std::memcpy(a.src, src_blocks_host, static_cast<size_t>(n) * sizeof(int32_t));
+  std::memcpy(a.dst, dst_blocks_host, static_cast<size_t>(n) * sizeof(int32_t));
+  HI_DEVICE_GUARD(device);
+  migrate_gather_inline_kernel<<<static_cast<unsigned>(grid), kMigrateThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  note_launch();
+  HI_CUDA(cudaGetLastError());
+  return HI_OK;
+}
+
+extern "C" int hi_migrate_inline_table_blocks(void) { return hi::kInlineBlocks; }
 
 extern "C" int hi_ipc_get_handle(const void* ptr, uint8_t handle_out[64], int64_t* offset_out, int device) {
   using namespace hi;

@@ -442,6 +442,18 @@ void launch_migration(int dev, const std::vector<int64_t>& src_bt, const std::ve
                       int64_t src_n_blocks, int64_t dst_n_blocks, int64_t layer_begin, int64_t layer_end) {
   const int64_t n = static_cast<int64_t>(src_bt.size());
   const int64_t run_bytes = local_pool.size(3) * local_pool.size(4) * local_pool.size(5) * local_pool.element_size();
+  static const int64_t inline_blocks = hi_migrate_inline_table_blocks();
+  if (n <= inline_blocks) {  // the tables ride in the kernel parameters: one launch, nothing in front of it
+    int32_t tables[2][512];
+    for (int64_t i = 0; i < n; ++i) {
+      tables[0][i] = static_cast<int32_t>(src_bt[i]);
+      tables[1][i] = static_cast<int32_t>(dst_bt[i]);
+    }
+    const HiPoolGeom src{local_pool.size(0), local_pool.size(1), src_n_blocks, run_bytes};
+    const HiPoolGeom dst{local_pool.size(0), local_pool.size(1), dst_n_blocks, run_bytes};
+    check(hi_migrate_blocks_host_tables(tables[0], tables[1], n, src_ptr, dst_ptr, src, dst, layer_begin, layer_end, dev, current_stream(dev)));
+    return;
+  }
   // both tables in one pinned staging tensor and one asynchronous H2D copy; torch's caching allocators keep the pinned block
   // and the device block alive until the copy / the kernel have run on this stream
   Tensor host = at::empty({2, n}, at::TensorOptions().dtype(at::kInt).pinned_memory(true));
@@ -545,4 +557,5 @@ PYBIND11_MODULE(block_migration, m) {
   m.def("push_blocks", &push_blocks, py::arg("src_block_table"), py::arg("dst_block_table"), py::arg("src_cache"), py::arg("dst_cache"),
         py::arg("dst_cache_n_blocks"), py::arg("layer_begin") = 0, py::arg("layer_end") = -1);
   m.def("copy_blocks", &copy_blocks);
+  m.def("set_max_ctas", [](int64_t n) { check(hi_migrate_set_max_ctas(static_cast<int>(n))); }, py::arg("max_ctas"));
 }

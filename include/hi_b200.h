@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HI_B200_ABI_VERSION 4
+#define HI_B200_ABI_VERSION 5
 
 typedef enum HiStatus {
   HI_OK = 0,
@@ -93,10 +93,11 @@ int hi_get_image_cache(const int32_t* slot_ids /*[dev] [n_tokens]*/, const void*
  *   key_cache / value_cache[slot_ids[t]] (geometry as hi_set_kv_cache) and k itself is rewritten only if
  *   write_back_k; without slot_ids k is rotated in place (plain apply_rotary_pos_emb).
  *
- * Rounding is the reference's: every product and the final sum round separately, to the element type when the
- * table has the element type (rope.cu computes in c10::Half/BFloat16; torch's 16-bit ops in
- * TorchRotaryEmbeddingHandler, hydrainfer/layer/rotary_embedding.py:44-83, do the same), to fp32 when the table is
- * fp32 (torch promotes).  Results are bit-identical to that path.
+ * Rounding is that of the reference's torch handler (TorchRotaryEmbeddingHandler, hydrainfer/layer/rotary_embedding.py:44-83):
+ * every product and the final sum round separately, to the element type when the table has the element type, to fp32 when
+ * the table is fp32 (torch promotes).  Results are bit-identical to that path.  (The reference's compiled kernel computes
+ * `x*c - y*s` in native half, which nvcc contracts into one FMA - one rounding fewer - and has no bf16 instance,
+ * csrc/kernel/dispatch.h:12-29; tests/test_gpu_reference_native.py bounds the difference.)
  * ------------------------------------------------------------------------------------------- */
 typedef struct HiRopeArgs {
   void* q;                   /* [dev] [n_tokens, n_qo_heads, head_dim], head stride == head_dim; rotated in place */
@@ -261,6 +262,20 @@ int hi_migrate_blocks_layers(const int32_t* src_blocks /*[dev] [n]*/, const int3
                              int64_t n, const void* src_pool /*[dev]*/, void* dst_pool /*[dev]*/,
                              HiPoolGeom src, HiPoolGeom dst, int64_t layer_begin, int64_t layer_end,
                              int device, void* stream);
+
+/* The same copy with the block tables in HOST memory (what migrate_blocks of block_migration.cpp:194-199 receives: two
+ * std::vector<int64_t>): requests of up to hi_migrate_inline_table_blocks() blocks carry their tables inside the kernel
+ * parameters, so the launch needs no staging buffer and no host-to-device copy in front of it.  Larger requests: upload the
+ * tables and call hi_migrate_blocks_layers. */
+int hi_migrate_blocks_host_tables(const int32_t* src_blocks_host /*[n]*/, const int32_t* dst_blocks_host /*[n]*/, int64_t n,
+                                  const void* src_pool /*[dev]*/, void* dst_pool /*[dev]*/, HiPoolGeom src, HiPoolGeom dst,
+                                  int64_t layer_begin, int64_t layer_end, int device, void* stream);
+int hi_migrate_inline_table_blocks(void);
+
+/* Caps the grid of the migration kernels (process-wide; 0 = default, 8 CTAs per SM).  A receiver that decodes while it pulls
+ * pages (hydrainfer/cluster/epdnode.py:362-447 issues the pull on a side stream during the step) trades transfer rate for
+ * decode throughput with it; bench.py's `migrate_under_decode` extra measures both sides. */
+int hi_migrate_set_max_ctas(int max_ctas);
 
 /* get_ipc_mem_handle (block_migration.cpp:55-59).  handle_out receives the 64 bytes of
  * cudaIpcMemHandle_t of the ALLOCATION containing ptr; *offset_out the byte offset of ptr inside it

@@ -30,7 +30,7 @@ def test_binding_table_matches_header():
 
 
 def test_abi_version_and_error_string():
-    assert _lib.lib.hi_abi_version() == 4
+    assert _lib.lib.hi_abi_version() == 5
     assert isinstance(_lib.lib.hi_last_error(), bytes)
 
 
