@@ -123,6 +123,8 @@ extern "C" int hi_paged_attention(const HiAttnArgs* p, void* stream_) {
     const int group = a.n_qo_heads / a.n_kv_heads;
     if (a.max_q_len > 1) {
       path = attn_pair_supported(a) ? HI_ATTN_TCGEN05_PAIR : attn_tc_supported(a) ? HI_ATTN_TCGEN05 : HI_ATTN_SIMT;
+    } else if (a.head_dim != 64 && a.head_dim != 128 && a.head_dim != 256 && attn_pair_supported(a)) {
+      path = HI_ATTN_TCGEN05_PAIR;  // head dims only the tile kernel covers (96, ...): it takes decode rows as one-token tiles
     } else if (group >= 4 && attn_decode_tc_supported(a)) {
       path = HI_ATTN_TCGEN05_DECODE;
     } else if (group >= 4 && attn_tc_supported(a)) {

@@ -476,8 +476,8 @@ struct MapKeyHash {
 static std::mutex g_map_mu;
 static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_pool_maps;
 
-int pool_map(CUtensorMap* out, int dtype, const void* base, int64_t n_slots, int heads, int block_size) {
-  const MapKey key{base, n_slots, heads, dtype, block_size};
+int pool_map_d(CUtensorMap* out, int dtype, const void* base, int64_t n_slots, int heads, int head_dim, int block_size) {
+  const MapKey key{base, n_slots, heads, dtype | (head_dim << 8), block_size};
   std::lock_guard<std::mutex> lock(g_map_mu);
   auto it = g_pool_maps.find(key);
   if (it != g_pool_maps.end()) {
@@ -485,12 +485,16 @@ int pool_map(CUtensorMap* out, int dtype, const void* base, int64_t n_slots, int
     return HI_OK;
   }
   CUtensorMap m;
-  const int rc = make_map(&m, dtype, base, n_slots, heads, static_cast<int64_t>(heads) * kHeadDim, 1, block_size);
+  const int rc = make_map_d(&m, dtype, base, n_slots, heads, head_dim, static_cast<int64_t>(heads) * head_dim, 1, block_size);
   if (rc != HI_OK) return rc;
   if (g_pool_maps.size() > 4096) g_pool_maps.clear();
   g_pool_maps.emplace(key, m);
   *out = m;
   return HI_OK;
+}
+
+int pool_map(CUtensorMap* out, int dtype, const void* base, int64_t n_slots, int heads, int block_size) {
+  return pool_map_d(out, dtype, base, n_slots, heads, kHeadDim, block_size);
 }
 
 bool attn_tc_supported(const HiAttnArgs& args) {

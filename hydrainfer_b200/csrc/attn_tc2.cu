@@ -232,12 +232,19 @@ __device__ __forceinline__ unsigned long long trace_globaltimer() {
 #endif
 
 // PF = how many of every 4 (pairs of) exponentials run on the FMA pipes (exp2_poly2) instead of MUFU.EX2.
-template <typename T, int NK, int NV, int PF, bool VL = false>
+// MODE 0: paged K/V, head_dim 128 (everything about the head dim is a compile-time constant).
+// MODE 1: un-paged varlen K/V (hi_varlen_attention), head_dim any multiple of 8 up to 128 (VL).
+// MODE 2: paged K/V, head_dim a multiple of 16 below 128 (64, 96: the reference's FA2 covers 64 / 96 / 128 / 256,
+//         csrc/kernel/flash_attn/src/static_switch.h:70-85): the tensor maps carry the real head_dim, TMA zero-fills the dims
+//         beyond it, Q.K^T walks head_dim / 16 k-steps and P.V produces head_dim columns, exactly as MODE 1 does.
+template <typename T, int NK, int NV, int PF, int MODE = 0>
 __global__ void __launch_bounds__(kP2Threads, 1)
 paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                        const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o, const P2Args a) {
   using L = P2Smem<NK, NV>;
   static_assert(NK >= 3 && NV >= 3 && NK + NV == 8, "the K and V rings share 128 KiB; each needs 2 steps of lookahead at least");
+  constexpr bool VL = MODE == 1;   // un-paged keys, optional causal mask
+  constexpr bool VD = MODE != 0;   // head_dim is a run-time value
   // ring stage / phase of running step g (division by a compile-time constant)
   auto k_stage = [](uint32_t g) -> uint32_t { return g % NK; };
   auto k_phase = [](uint32_t g) -> uint32_t { return (g / NK) & 1u; };
@@ -321,7 +328,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       const bool is_k = warp == 8;
       const CUtensorMap* tm = is_k ? &tm_k : &tm_v;
       const uint32_t page_half_bytes = static_cast<uint32_t>(a.block_size) * 128u;
-      const uint32_t n_halves = VL ? static_cast<uint32_t>(a.n_halves) : 2u;
+      const uint32_t n_halves = VD ? static_cast<uint32_t>(a.n_halves) : 2u;
       const int b_full = is_k ? L::bKFull : L::bVFull;
       const int b_empty = is_k ? L::bKEmpty : L::bVEmpty;
       const uint32_t ring = smem_base + (is_k ? L::kK : L::kV);
@@ -432,8 +439,8 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       // ---- MMA warp of tile t: the warp stays converged (every lane polls the barriers), one elected lane issues ------------
       const int t = warp - 9;
       constexpr uint32_t idesc_qk = ptx::make_idesc_f16(kBf16, false, false, kP2TileM, kP2TileN);
-      const uint32_t idesc_pv = VL ? a.idesc_pv : ptx::make_idesc_f16(kBf16, false, true, kP2TileM, kP2D);
-      const int n_kk = VL ? a.n_kk : 8;
+      const uint32_t idesc_pv = VD ? a.idesc_pv : ptx::make_idesc_f16(kBf16, false, true, kP2TileM, kP2D);
+      const int n_kk = VD ? a.n_kk : 8;
       // Descriptors of the operand bases, built once; stages and k-steps only add to the 14-bit start-address field.
       const uint64_t desc_q = ptx::make_smem_desc_sw128(smem_base + L::kQ + t * kP2QTile, 16, 1024);
       const uint64_t desc_k = ptx::make_smem_desc_sw128(smem_base + L::kK, 16, 1024);
@@ -447,7 +454,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         if (!no_mma) {
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {  // 2 halves x 4 k-steps of 16 dims; K-major operands, 8-row groups 1024 B apart
-            if (VL && kk >= n_kk) break;
+            if (VD && kk >= n_kk) break;
             ptx::mma_f16_ss(tmem_s, desc_q + static_cast<uint64_t>(((kk >> 2) * kP2QHalf + (kk & 3) * 32) >> 4),
                             dk + static_cast<uint64_t>(((kk >> 2) * kP2Half + (kk & 3) * 32) >> 4), idesc_qk, kk > 0);
           }
@@ -699,7 +706,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       trace(5, n_it, 0);
       const float inv_l = 1.f / l;
       const int head = it.kvh * a.group + g;
-      const int d_out = VL ? a.head_dim : kP2D;
+      const int d_out = VD ? a.head_dim : kP2D;
       T* orow = static_cast<T*>(a.out) + static_cast<int64_t>(it.q_start + i) * a.out_row_stride + head * d_out;
       const int64_t pidx = (static_cast<int64_t>(it.q_start + i) * a.n_qo_heads + head) * a.n_splits + it.sp;
       const bool direct = t ? it.direct[1] : it.direct[0];
@@ -755,7 +762,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         } else if (direct && warp_active && row_valid) {
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
-            if (VL && h * 64 + c * 8 >= d_out) break;
+            if (VD && h * 64 + c * 8 >= d_out) break;
             *reinterpret_cast<uint4*>(orow + h * 64 + c * 8) = make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
           }
         }
@@ -851,20 +858,21 @@ __global__ void __launch_bounds__(kPlanThreads) p2_plan_kernel(const int32_t* __
 
 bool attn_pair_supported(const HiAttnArgs& args) {
   const int group = args.n_kv_heads > 0 ? args.n_qo_heads / args.n_kv_heads : 0;
-  return (args.dtype == HI_F16 || args.dtype == HI_BF16) && args.head_dim == kP2D && group >= 1 && group <= kP2TileM &&
+  const bool dim_ok = args.head_dim == kP2D || (args.head_dim >= 16 && args.head_dim < kP2D && (args.head_dim % 16) == 0);
+  return (args.dtype == HI_F16 || args.dtype == HI_BF16) && dim_ok && group >= 1 && group <= kP2TileM &&
          args.block_size >= 8 && args.block_size <= kP2TileN && (kP2TileN % args.block_size) == 0 &&
          (args.q_row_stride % 8) == 0 && (args.out_row_stride % 8) == 0 && aligned_to(args.q, 16) &&
          aligned_to(args.out, 16) && aligned_to(args.key_cache, 16) && aligned_to(args.value_cache, 16) &&
          args.n_blocks > 0;
 }
 
-template <typename T, int PF, bool VL, int NK, int NV>
+template <typename T, int PF, int MODE, int NK, int NV>
 static int launch_pair_ring(int device, const P2Args& a, const CUtensorMap& mq, const CUtensorMap& mk,
                             const CUtensorMap& mv, const CUtensorMap& mo, cudaStream_t stream) {
   // NK + NV = 8 steps of 64 keys (16 KiB each) + 64 KiB of Q + 32 KiB of output staging = 224 KiB
   using L = P2Smem<NK, NV>;
   static PerDeviceFlags configured;
-  HI_CUDA(configure_dynamic_smem(configured, paged_attn_pair_kernel<T, NK, NV, PF, VL>, L::kDynamicBytes));
+  HI_CUDA(configure_dynamic_smem(configured, paged_attn_pair_kernel<T, NK, NV, PF, MODE>, L::kDynamicBytes));
   // persistent: one CTA per SM walks the items with a stride of the grid size
   const int n_sms = sm_count_of(device);
   HI_CHECK_ARG(n_sms > 0, "paged_attention: cannot read the SM count of device %d", device);
@@ -872,7 +880,7 @@ static int launch_pair_ring(int device, const P2Args& a, const CUtensorMap& mq, 
   if (const char* env = tuning_env("HI_PAIR_CTAS")) ctas = atoi(env) > 0 ? atoi(env) : ctas;  // tuning / test override
   const dim3 grid(ctas, 1, 1);
   timing_mark_start(stream);
-  paged_attn_pair_kernel<T, NK, NV, PF, VL><<<grid, kP2Threads, L::kDynamicBytes, stream>>>(mq, mk, mv, mo, a);
+  paged_attn_pair_kernel<T, NK, NV, PF, MODE><<<grid, kP2Threads, L::kDynamicBytes, stream>>>(mq, mk, mv, mo, a);
   timing_mark_stop(stream);
   note_launch();
   HI_CUDA(cudaGetLastError());
@@ -882,15 +890,15 @@ static int launch_pair_ring(int device, const P2Args& a, const CUtensorMap& mq, 
 // Split of the 8 ring stages between K and V: 4 + 4.  (Q.K^T runs two steps ahead of P.V, so 5 + 3 would give both rings the same
 // lookahead; measured on B200 it loses 2-6 % on every prefill shape - the V ring then stalls P.V behind the softmax of the
 // lagging tile - so only 4 + 4 is instantiated.  The kernel itself is generic in NK / NV.)
-template <typename T, int PF, bool VL = false>
+template <typename T, int PF, int MODE = 0>
 static int launch_pair_t(int device, const P2Args& a, const CUtensorMap& mq, const CUtensorMap& mk,
                          const CUtensorMap& mv, const CUtensorMap& mo, cudaStream_t stream) {
-  return launch_pair_ring<T, PF, VL, 4, 4>(device, a, mq, mk, mv, mo, stream);
+  return launch_pair_ring<T, PF, MODE, 4, 4>(device, a, mq, mk, mv, mo, stream);
 }
 
 int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
   if (!attn_pair_supported(args)) {
-    set_error("paged_attention: the tcgen05 pair-tile path needs fp16/bf16, head_dim 128, block_size in {8,16,32,64} and 16-byte aligned rows");
+    set_error("paged_attention: the tcgen05 pair-tile path needs fp16/bf16, head_dim 128 or a multiple of 16 below it, block_size in {8,16,32,64} and 16-byte aligned rows");
     return HI_ERR_UNSUPPORTED;
   }
   P2Args a{};
@@ -953,6 +961,8 @@ int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
   }
   if (const char* env = tuning_env("HI_TC_SPLITS")) n_splits = atoi(env);  // tuning / test override
   if (n_splits < 1) n_splits = 1;
+  const bool var_dim = args.head_dim != kP2D;
+  if (var_dim) n_splits = 1;  // the fp32 partials and their merge are laid out for head_dim 128; other head dims run unsplit
   n_splits = cap_splits(n_splits, args.n_tokens, args.n_qo_heads, kP2D);
   if (n_splits > 1) {
     const int64_t need = partial_bytes_per_split(args.n_tokens, args.n_qo_heads, kP2D) * n_splits + plan_tail + kWorkspaceTailBytes;
@@ -993,22 +1003,37 @@ int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
   }
 
   CUtensorMap mq, mk, mv, mo;
-  int rc = make_map(&mq, args.dtype, args.q, args.n_tokens, args.n_qo_heads, args.q_row_stride, a.group, a.tq);
+  int rc = make_map_d(&mq, args.dtype, args.q, args.n_tokens, args.n_qo_heads, args.head_dim, args.q_row_stride, a.group, a.tq);
   if (rc != HI_OK) return rc;
-  rc = make_map(&mo, args.dtype, args.out, args.n_tokens, args.n_qo_heads, args.out_row_stride, a.group, a.tq);
+  rc = make_map_d(&mo, args.dtype, args.out, args.n_tokens, args.n_qo_heads, args.head_dim, args.out_row_stride, a.group, a.tq);
   if (rc != HI_OK) return rc;
   const int64_t n_slots = args.n_blocks * args.block_size;
-  rc = pool_map(&mk, args.dtype, args.key_cache, n_slots, args.n_kv_heads, args.block_size);
+  rc = pool_map_d(&mk, args.dtype, args.key_cache, n_slots, args.n_kv_heads, args.head_dim, args.block_size);
   if (rc != HI_OK) return rc;
-  rc = pool_map(&mv, args.dtype, args.value_cache, n_slots, args.n_kv_heads, args.block_size);
+  rc = pool_map_d(&mv, args.dtype, args.value_cache, n_slots, args.n_kv_heads, args.head_dim, args.block_size);
   if (rc != HI_OK) return rc;
+  if (const char* env = tuning_env("HI_PAIR_DEBUG")) a.debug = atoi(env);
+  if (var_dim) {
+    // MODE 2: the tensor maps carry the real head_dim (TMA zero-fills up to the 64-dim box), the MMAs walk head_dim / 16 k-steps
+    a.head_dim = args.head_dim;
+    a.causal = 1;
+    a.n_halves = args.head_dim > 64 ? 2 : 1;
+    a.n_kk = args.head_dim / 16;
+    a.idesc_pv = ptx::make_idesc_f16(args.dtype == HI_BF16, false, true, kP2TileM, args.head_dim);
+    a.use_tma_store = 0;
+    // (With half the head dim the products need half the tensor-pipe cycles while the softmax still needs one exponential per
+    // score, so the softmax warps bound the kernel: 8k prefill at head_dim 64 runs 0.331 ms against 0.393 ms at 128.  Moving
+    // 1/4 or 1/2 of the exponentials from MUFU.EX2 to an FMA-pipe polynomial was measured on B200 and does not help - 0.331 /
+    // 0.331 / 0.366 ms: the warps are short of issue slots, not of MUFU throughput.)
+    return args.dtype == HI_BF16 ? launch_pair_t<__nv_bfloat16, 0, 2>(args.device, a, mq, mk, mv, mo, stream)
+                                 : launch_pair_t<__half, 0, 2>(args.device, a, mq, mk, mv, mo, stream);
+  }
 
   a.use_tma_store = 1;
 #ifdef HI_P2_NO_STAGING
   a.use_tma_store = 0;
 #endif
   if (const char* env = tuning_env("HI_PAIR_TMA_STORE")) a.use_tma_store = atoi(env) != 0;  // A/B switch
-  if (const char* env = tuning_env("HI_PAIR_DEBUG")) a.debug = atoi(env);
   int poly = 0;  // exponentials per 4 moved from MUFU to the FMA pipes (measured: no gain while the softmax warps have idle issue slots)
   if (const char* env = tuning_env("HI_PAIR_POLY")) poly = atoi(env);  // tuning override
   if (args.dtype == HI_BF16) {
@@ -1097,8 +1122,8 @@ int launch_varlen_pair(const HiVarlenArgs& v, cudaStream_t stream) {
   rc = make_map_d(&mv, v.dtype, v.v, v.n_k_tokens, v.n_kv_heads, v.head_dim, v.v_row_stride, 1, kP2TileN);
   if (rc != HI_OK) return rc;
   if (const char* env = tuning_env("HI_PAIR_DEBUG")) a.debug = atoi(env);
-  return v.dtype == HI_BF16 ? launch_pair_t<__nv_bfloat16, 0, true>(v.device, a, mq, mk, mv, mo, stream)
-                            : launch_pair_t<__half, 0, true>(v.device, a, mq, mk, mv, mo, stream);
+  return v.dtype == HI_BF16 ? launch_pair_t<__nv_bfloat16, 0, 1>(v.device, a, mq, mk, mv, mo, stream)
+                            : launch_pair_t<__half, 0, 1>(v.device, a, mq, mk, mv, mo, stream);
 }
 
 }  // namespace hi

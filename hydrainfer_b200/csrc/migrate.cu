@@ -108,6 +108,28 @@ extern "C" int hi_migrate_blocks(const int32_t* src_blocks, const int32_t* dst_b
 
 namespace hi {
 static std::atomic<int> g_migrate_max_ctas{0};  // 0 = no cap (process-wide tuning knob)
+
+// Device that owns the allocation behind `ptr` (peer-mapped and IPC-mapped pools report the exporting GPU); `fallback` when the
+// runtime cannot tell.  The last few answers are cached: pools live for the life of the process.
+static int pointer_device(const void* ptr, int fallback) {
+  struct Entry {
+    const void* ptr;
+    int device;
+  };
+  static std::mutex mu;
+  static Entry cache[8] = {};
+  static int next = 0;
+  std::lock_guard<std::mutex> lock(mu);
+  for (const Entry& e : cache)
+    if (e.ptr == ptr && ptr != nullptr) return e.device;
+  cudaPointerAttributes attr;
+  int dev = fallback;
+  if (cudaPointerGetAttributes(&attr, ptr) == cudaSuccess && attr.type == cudaMemoryTypeDevice) dev = attr.device;
+  else (void)cudaGetLastError();
+  cache[next] = Entry{ptr, dev};
+  next = (next + 1) % 8;
+  return dev;
+}
 // Shared by the device-table and the inline-table entry points: checks + geometry -> MigrateArgs and the grid size.
 static int prepare_migration(MigrateArgs& a, int64_t& grid, int64_t n, const void* src_pool, void* dst_pool, const HiPoolGeom& src,
                              const HiPoolGeom& dst, int64_t layer_begin, int64_t layer_end, int device) {
@@ -131,11 +153,19 @@ static int prepare_migration(MigrateArgs& a, int64_t& grid, int64_t n, const voi
   a.total_pieces = a.planes * n * a.pieces_per_run;
   const int sm_count = sm_count_of(device);
   HI_CHECK_ARG(sm_count > 0, "migrate_blocks: cannot read the SM count of device %d", device);
-  // 8 resident CTAs of 256 threads per SM = 128 KiB of loads in flight per SM; hi_migrate_set_max_ctas() lowers the grid so a pull
-  // leaves SM slots (and HBM write bandwidth) to the decode step running beside it on the receiving GPU.
+  // 8 resident CTAs of 256 threads per SM = 128 KiB of loads in flight per SM: what a pool -> pool copy inside one GPU's HBM wants
+  // (2.9 TB/s), and what a small request wants (all its pieces in flight in one round trip).  A LARGE transfer over NVLink needs
+  // far less - 800 GB/s x 3 us = 2.4 MB in flight, 16 KiB per SM - and 8 CTAs per SM take every thread slot of the receiving
+  // GPU away from the decode step running beside the pull (bench.py migrate_under_decode on 2 B200: decode 1.57x slower at
+  // 8 CTAs/SM, 1.41x at 2, 1.31x at 1, the pull alone 777 / 775 / 762 GB/s): 2 CTAs per SM there.
+  // hi_migrate_set_max_ctas() overrides the choice.
   grid = static_cast<int64_t>(sm_count) * 8;
   const int cap = g_migrate_max_ctas.load(std::memory_order_relaxed);
-  if (cap > 0 && grid > cap) grid = cap;
+  if (cap > 0) {
+    if (grid > cap) grid = cap;
+  } else if (a.total_pieces > grid * 4 && (pointer_device(src_pool, device) != device || pointer_device(dst_pool, device) != device)) {
+    grid = static_cast<int64_t>(sm_count) * 2;
+  }
   if (grid > a.total_pieces) grid = a.total_pieces;
   return HI_OK;
 }

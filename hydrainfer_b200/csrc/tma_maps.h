@@ -20,4 +20,7 @@ int make_map_d(CUtensorMap* map, int dtype, const void* base, int64_t rows, int6
 // Cached map of a paged pool [n_slots, heads, 128]; box = one page of one head and one 64-dim half.
 int pool_map(CUtensorMap* out, int dtype, const void* base, int64_t n_slots, int heads, int block_size);
 
+// Same for pools whose heads are `head_dim` (a multiple of 8, <= 128) elements wide.
+int pool_map_d(CUtensorMap* out, int dtype, const void* base, int64_t n_slots, int heads, int head_dim, int block_size);
+
 }  // namespace hi

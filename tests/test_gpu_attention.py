@@ -34,6 +34,10 @@ def tc_supported(head_dim, dtype, block_size):
     return head_dim == 128 and dtype in (torch.float16, torch.bfloat16) and block_size in (8, 16, 32, 64, 128)
 
 
+def pair_supported(head_dim, dtype, block_size):
+    return head_dim % 16 == 0 and 16 <= head_dim <= 128 and dtype in (torch.float16, torch.bfloat16) and block_size in (8, 16, 32, 64)
+
+
 def run_attention(query3d, key_cache, value_cache, q_cu, kv_cu, block_tables, cu_blocks, q_max, kv_max, head_dim, path):
     """mha_varlen_fwd exactly as FlashAttentionCausalGroupedQueryPageAttentionHandler calls it (causal_attention.py:274-291)."""
     from hydrainfer_b200._C.kernel.flash_attn import mha_varlen_fwd
@@ -79,6 +83,8 @@ def paths_for(head_dim, dtype, block_size=16, group=1):
     if os.environ.get("HI_TEST_SKIP_TC") == "1":  # dev switch: validate the split-KV kernel alone
         return [SIMT]
     if not tc_supported(head_dim, dtype, block_size):
+        if pair_supported(head_dim, dtype, block_size):  # head_dim 64 / 96: the pair-tile kernel's variable-head-dim mode
+            return ([SIMT] if head_dim == 64 else []) + [PAIR, 0]
         return [SIMT, 0]
     return [SIMT, TC, DEC, PAIR, 0] if group <= 16 else [SIMT, TC, PAIR, 0]
 
@@ -407,10 +413,10 @@ def test_unsupported_arguments_raise():
     with pytest.raises(RuntimeError, match="dtype"):
         mha_varlen_fwd(*bad)
     # head_dim the kernels do not cover -> RuntimeError from the C ABI status, not a crash
-    b96 = make_batch([(1, 20)], 4, 2, 96, 16, dtype=torch.bfloat16, device=DEV, seed=1)
-    q96 = b96.query.view(1, 4, 96)
+    b72 = make_batch([(1, 20)], 4, 2, 72, 16, dtype=torch.bfloat16, device=DEV, seed=1)
+    q72 = b72.query.view(1, 4, 72)
     with pytest.raises(RuntimeError, match="head_dim"):
-        mha_varlen_fwd(torch.empty_like(q96), q96, b96.key_cache, b96.value_cache, i32([0, 1]), i32([0, 20]), i32(b96.block_tables), i32([0, 2]),
+        mha_varlen_fwd(torch.empty_like(q72), q72, b72.key_cache, b72.value_cache, i32([0, 1]), i32([0, 20]), i32(b72.block_tables), i32([0, 2]),
                        None, 1, 20, 0.1, 0, -1, 0, 0)
     # forcing the tile kernel on a shape it does not support is an error, not a silent fallback
     b64 = make_batch([(4, 20)], 4, 2, 64, 16, dtype=torch.bfloat16, device=DEV, seed=1)
@@ -431,3 +437,19 @@ def test_split_prefill_is_reproducible_run_to_run(path):
                           batch.cu_blocks_lens, batch.q_max, batch.kv_max, 128, path) for _ in range(5)]
     for i, o in enumerate(outs[1:], 1):
         assert torch.equal(outs[0], o), f"path {path}: run {i} differs from run 0 in {int((outs[0] != o).sum())} elements"
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("head_dim", [64, 96, 32])
+def test_tcgen05_prefill_for_head_dims_below_128(head_dim, dtype):
+    """The pair-tile kernel's variable-head-dim mode on PAGED caches: the reference's fused backend covers head_dim 64 / 96 / 128 /
+    256 (csrc/kernel/flash_attn/src/static_switch.h:70-85, flash_api.cpp:126-136).  Prefill, chunked prefill and decode rows in
+    one batch, MHA and GQA, forced PAIR path and AUTO (which must pick it for batches with prefill rows)."""
+    seq_lens = [(1, 300), (130, 130), (75, 900), (1, 17), (300, 300), (40, 1300), (1, 1)]
+    for heads in ((8, 8), (12, 4), (14, 2)):
+        batch = make_batch(seq_lens, heads[0], heads[1], head_dim, 16, dtype=dtype, seed=61)
+        check_batch(batch, [PAIR, 0], f"head_dim {head_dim} heads {heads}")
+    # decode-only batch of a head dim the CUDA-core kernels do not cover: AUTO has to route it to the tile kernel
+    if head_dim == 96:
+        batch = make_batch([(1, 700), (1, 64), (1, 2000)], 8, 2, head_dim, 16, dtype=dtype, seed=62)
+        check_batch(batch, [0], "decode-only head_dim 96")

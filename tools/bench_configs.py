@@ -8,6 +8,7 @@ from __future__ import annotations
 import argparse
 import json
 import math
+import os
 import sys
 import time
 from pathlib import Path
@@ -84,7 +85,7 @@ USE_GRAPH = False
 
 
 def run_case(name, seq_lens, hq, hkv, paths, out_lines, flashinfer_cmp=False, dtype=torch.bfloat16):
-    d, bs = 128, 16
+    d, bs = int(os.environ.get("HEAD_DIM", "128")), 16  # HEAD_DIM=64: the variable-head-dim mode of the pair kernel
     batch = make_batch(seq_lens, hq, hkv, d, bs, dtype=dtype, device=DEV, gen_device=DEV, seed=0)
     t = batch.n_tokens
     q3 = batch.query.view(t, hq, d)
