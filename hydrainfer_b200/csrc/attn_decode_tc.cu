@@ -146,6 +146,10 @@ paged_decode_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // The prologue above (barriers, TMEM, tensor maps; metadata from a copy) ran beside the tail of the append kernel; q and the
+  // appended K / V rows are touched only from here on.
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 4) {
     // ================================================ TMA producer ================================================
@@ -367,7 +371,7 @@ static int launch_decode_t(const HiAttnArgs& args, const DecArgs& a, const CUten
   HI_CUDA(configure_dynamic_smem(configured, paged_decode_tc_kernel<T, 1, GP>, L::kDynamicBytes));
   const dim3 grid(args.n_tokens, args.n_kv_heads, a.n_splits);
   timing_mark_start(stream);
-  paged_decode_tc_kernel<T, 1, GP><<<grid, kDecThreads, L::kDynamicBytes, stream>>>(mq, mk, mv, a);
+  HI_CUDA(launch_pdl(paged_decode_tc_kernel<T, 1, GP>, grid, dim3(kDecThreads), L::kDynamicBytes, stream, mq, mk, mv, a));
   timing_mark_stop(stream);
   note_launch();
   HI_CUDA(cudaGetLastError());

@@ -186,6 +186,8 @@ __global__ void __launch_bounds__(kSimtThreads) paged_attn_simt_kernel(const Sim
   const int tile_end = min(tiles_total, tile_begin + a.chunk_tiles);
   const int n_iters = (tile_end - tile_begin + kHalfWarps - 1) / kHalfWarps;
   const int32_t* __restrict__ bt = a.block_tables + __ldg(a.cu_blocks + b);
+  pdl_wait();               // q and the appended K / V rows come from kernels in front of this one (the metadata above from a copy)
+  pdl_launch_dependents();  // the split merge / the next layer's append may start launching
 
   const int lane = threadIdx.x & 31;
   const int l16 = lane & 15;
@@ -381,6 +383,8 @@ __global__ void __launch_bounds__(kSimtThreads) paged_attn_stream_kernel(const S
   const int tile_end = min(tiles_total, tile_begin + a.chunk_tiles);
   const int n_iters = (tile_end - tile_begin + kHalfWarps - 1) / kHalfWarps;
   const int32_t* __restrict__ bt = a.block_tables + __ldg(a.cu_blocks + b);
+  pdl_wait();               // q and the appended K / V rows come from kernels in front of this one (the metadata above from a copy)
+  pdl_launch_dependents();  // the split merge / the next layer's append may start launching
 
   const int l16 = threadIdx.x & 15;
   const int hw = threadIdx.x >> 4;
@@ -511,6 +515,8 @@ __global__ void __launch_bounds__(kMergeThreads) merge_partials_kernel(const Sim
   const int q_start = __ldg(a.q_cu + b);
   const int q_len = __ldg(a.q_cu + b + 1) - q_start;
   const int kv_len = __ldg(a.kv_cu + b + 1) - __ldg(a.kv_cu + b);
+  pdl_wait();  // the partials come from the attention kernel in front of this one
+  pdl_launch_dependents();
   if (a.direct_tile_tokens > 0) {
     // the producer wrote this row's tile directly when the tile's last row fits in one chunk
     const int i_last = min(q_len, ((t - q_start) / a.direct_tile_tokens + 1) * a.direct_tile_tokens) - 1;
@@ -573,9 +579,9 @@ int64_t simt_workspace_bytes(int head_dim) {
 // Split-merge launch shared with the tile kernel's split-KV mode (a.n_tokens rows, a.n_chunks partials per row and head).
 int launch_merge_partials(const SimtArgs& a, int dtype, int head_dim, cudaStream_t stream) {
   if (head_dim == 128 && dtype == HI_BF16) {
-    merge_partials_kernel<__nv_bfloat16, 128><<<merge_grid<__nv_bfloat16, 128>(a), kMergeThreads, 0, stream>>>(a);
+    HI_CUDA(launch_pdl(merge_partials_kernel<__nv_bfloat16, 128>, merge_grid<__nv_bfloat16, 128>(a), dim3(kMergeThreads), 0, stream, a));
   } else if (head_dim == 128 && dtype == HI_F16) {
-    merge_partials_kernel<__half, 128><<<merge_grid<__half, 128>(a), kMergeThreads, 0, stream>>>(a);
+    HI_CUDA(launch_pdl(merge_partials_kernel<__half, 128>, merge_grid<__half, 128>(a), dim3(kMergeThreads), 0, stream, a));
   } else {
     set_error("merge_partials: unsupported head_dim %d / dtype %d", head_dim, dtype);
     return HI_ERR_UNSUPPORTED;
@@ -594,16 +600,16 @@ static int launch_simt_g(const SimtArgs& a, cudaStream_t stream) {
     static PerDeviceFlags configured;
     HI_CUDA(configure_dynamic_smem(configured, paged_attn_stream_kernel<T, D, G>, smem));
     timing_mark_start(stream);
-    paged_attn_stream_kernel<T, D, G><<<grid, kSimtThreads, smem, stream>>>(a);
+    HI_CUDA(launch_pdl(paged_attn_stream_kernel<T, D, G>, grid, dim3(kSimtThreads), smem, stream, a));
   } else {
     timing_mark_start(stream);
-    paged_attn_simt_kernel<T, D, G><<<grid, kSimtThreads, 0, stream>>>(a);
+    HI_CUDA(launch_pdl(paged_attn_simt_kernel<T, D, G>, grid, dim3(kSimtThreads), 0, stream, a));
   }
   timing_mark_stop(stream);
   note_launch();
   HI_CUDA(cudaGetLastError());
   if (a.n_chunks > 1) {
-    merge_partials_kernel<T, D><<<merge_grid<T, D>(a), kMergeThreads, 0, stream>>>(a);
+    HI_CUDA(launch_pdl(merge_partials_kernel<T, D>, merge_grid<T, D>(a), dim3(kMergeThreads), 0, stream, a));
     note_launch();
     HI_CUDA(cudaGetLastError());
   }

@@ -299,6 +299,10 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // The setup above ran beside the tail of the kernel in front (append / device plan); nothing a kernel produced - q, the
+  // appended K / V rows, the device-built plan, the work counter - has been touched yet.
+  pdl_wait();
+  pdl_launch_dependents();
   volatile int* item_ring = reinterpret_cast<volatile int*>(smem_gen + L::kItemRing);
   // Next work item of a consumer role (see p2_claim_item): entry n of the ring sequence.  `warp_role` consumers stay
   // converged and release the slot from one lane; softmax threads release it individually.
@@ -799,6 +803,8 @@ __global__ void __launch_bounds__(kPlanThreads) p2_plan_kernel(const int32_t* __
                                                               unsigned int* __restrict__ work_counter) {
   __shared__ int hist[kPlanBuckets];
   __shared__ int total;
+  pdl_wait();  // (a previous attention call on this stream may still be walking the list this kernel rewrites)
+  pdl_launch_dependents();
   const int width = max_kv_len / kPlanBuckets + 1;  // keys per bucket
   for (int i = threadIdx.x; i < kPlanBuckets; i += kPlanThreads) hist[i] = 0;
   if (threadIdx.x == 0) {
@@ -880,7 +886,7 @@ static int launch_pair_ring(int device, const P2Args& a, const CUtensorMap& mq, 
   if (const char* env = tuning_env("HI_PAIR_CTAS")) ctas = atoi(env) > 0 ? atoi(env) : ctas;  // tuning / test override
   const dim3 grid(ctas, 1, 1);
   timing_mark_start(stream);
-  paged_attn_pair_kernel<T, NK, NV, PF, MODE><<<grid, kP2Threads, L::kDynamicBytes, stream>>>(mq, mk, mv, mo, a);
+  HI_CUDA(launch_pdl(paged_attn_pair_kernel<T, NK, NV, PF, MODE>, grid, dim3(kP2Threads), L::kDynamicBytes, stream, mq, mk, mv, mo, a));
   timing_mark_stop(stream);
   note_launch();
   HI_CUDA(cudaGetLastError());
@@ -996,8 +1002,8 @@ int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
     }
   }
   if (dev_plan != nullptr) {
-    p2_plan_kernel<<<1, kPlanThreads, 0, stream>>>(args.q_cu_seq_lens, args.kv_cu_seq_lens, args.n_seqs, 2 * a.tq, args.max_kv_len,
-                                                   static_cast<int>(n_list), dev_plan, a.work_counter);
+    HI_CUDA(launch_pdl(p2_plan_kernel, dim3(1), dim3(kPlanThreads), 0, stream, args.q_cu_seq_lens, args.kv_cu_seq_lens, args.n_seqs, 2 * a.tq,
+                       args.max_kv_len, static_cast<int>(n_list), dev_plan, a.work_counter));
     note_launch();
     HI_CUDA(cudaGetLastError());
   }

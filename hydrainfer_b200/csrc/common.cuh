@@ -124,6 +124,42 @@ inline int cap_splits(int n_splits, int64_t n_tokens, int n_qo_heads, int head_d
   return n_splits > most ? static_cast<int>(most) : n_splits;
 }
 
+// ---- programmatic dependent launch ------------------------------------------------------------------------------------------
+// The kernels of one layer call (append -> attention -> split merge) are short, and for small decode batches the gap between two
+// dependent launches (grid launch + CTA scheduling + the prologue: barrier init, TMEM allocation, tensor-map prefetch) is a
+// visible share of the call.  Every kernel of the path is therefore launched with programmatic stream serialization: it may
+// start while its predecessor is still running, executes pdl_wait() before it touches anything a predecessor kernel produced
+// (griddepcontrol.wait returns once the prerequisite grids have completed and their writes are visible), and calls
+// pdl_launch_dependents() early so that ITS successor can do the same.  A predecessor that is not one of ours (it never triggers)
+// simply completes first: the ordinary stream order.  HI_PDL=0 switches the launch attribute off (A/B, debugging).
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* env = tuning_env("HI_PDL");
+    return !(env != nullptr && env[0] == '0');
+  }();
+  return on;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // SM count of `device`, cached per device (0 on error).
 inline int sm_count_of(int device) {
   static std::atomic<int> cache[kMaxDevices];

@@ -93,6 +93,8 @@ __device__ __forceinline__ void store8(T* p, const Pack8<T>& v) {
 // token's task list); small batches get several CTAs per token so a decode step still fills the machine.
 template <typename T, typename C>
 __global__ void __launch_bounds__(256) rope_append_vec_kernel(const RopeArgs a) {
+  pdl_wait();
+  pdl_launch_dependents();
   constexpr bool kRoundToT = sizeof(T) == 2 && sizeof(C) == 2;
   const int64_t token = blockIdx.x;
   const int n = a.rotary_dim >> 1;
@@ -171,6 +173,8 @@ __global__ void __launch_bounds__(256) rope_append_vec_kernel(const RopeArgs a) 
 // Any-shape kernel (odd rotary_dim / 16, unaligned rows): one pair or one copied element per task.
 template <typename T, typename C>
 __global__ void __launch_bounds__(256) rope_append_scalar_kernel(const RopeArgs a) {
+  pdl_wait();
+  pdl_launch_dependents();
   constexpr bool kRoundToT = sizeof(T) == 2 && sizeof(C) == 2;
   const int64_t token = blockIdx.x;
   const int n = a.rotary_dim >> 1;
@@ -237,9 +241,9 @@ static int launch_rope_t(const RopeArgs& a, int64_t n_tokens, bool vec, cudaStre
   if (slices < 1) slices = 1;
   const dim3 grid(static_cast<unsigned>(n_tokens), static_cast<unsigned>(slices));
   if (vec) {
-    rope_append_vec_kernel<T, C><<<grid, threads, 0, stream>>>(a);
+    HI_CUDA(launch_pdl(rope_append_vec_kernel<T, C>, grid, threads, 0, stream, a));
   } else {
-    rope_append_scalar_kernel<T, C><<<grid, threads, 0, stream>>>(a);
+    HI_CUDA(launch_pdl(rope_append_scalar_kernel<T, C>, grid, threads, 0, stream, a));
   }
   note_launch();
   HI_CUDA(cudaGetLastError());

@@ -20,6 +20,8 @@ struct ScatterArgs {
 
 template <typename Vec>
 __global__ void __launch_bounds__(256) scatter_rows_kernel(ScatterArgs a) {
+  pdl_wait();                // k / v (and the slot ids) may come from the kernel in front of this one
+  pdl_launch_dependents();   // the attention kernel behind may start its prologue while the rows are copied
   const int64_t token = blockIdx.x;
   const int which = blockIdx.y;
   const int64_t slot = a.slot_ids[token];
@@ -62,13 +64,13 @@ static int launch_scatter(const ScatterArgs& a, int n_tensors, int64_t n_tokens,
     return t < 32 ? 32 : t;
   };
   if (bits % 16 == 0) {
-    scatter_rows_kernel<uint4><<<grid, threads_for(16), 0, stream>>>(a);
+    HI_CUDA(launch_pdl(scatter_rows_kernel<uint4>, grid, dim3(threads_for(16)), 0, stream, a));
   } else if (bits % 8 == 0) {
-    scatter_rows_kernel<uint2><<<grid, threads_for(8), 0, stream>>>(a);
+    HI_CUDA(launch_pdl(scatter_rows_kernel<uint2>, grid, dim3(threads_for(8)), 0, stream, a));
   } else if (bits % 4 == 0) {
-    scatter_rows_kernel<uint32_t><<<grid, threads_for(4), 0, stream>>>(a);
+    HI_CUDA(launch_pdl(scatter_rows_kernel<uint32_t>, grid, dim3(threads_for(4)), 0, stream, a));
   } else {
-    scatter_rows_kernel<uint16_t><<<grid, threads_for(2), 0, stream>>>(a);
+    HI_CUDA(launch_pdl(scatter_rows_kernel<uint16_t>, grid, dim3(threads_for(2)), 0, stream, a));
   }
   note_launch();
   HI_CUDA(cudaGetLastError());

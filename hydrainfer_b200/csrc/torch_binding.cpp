@@ -350,13 +350,23 @@ Tensor append_and_attend(const Tensor& query, const Tensor& key, const Tensor& v
                          const Tensor& cu_seqlens_q, const Tensor& cu_seqlens_k, const Tensor& block_table, const Tensor& cu_block_lens, int64_t max_seqlen_q,
                          int64_t max_seqlen_k, double softmax_scale, int64_t path, const std::optional<Tensor>& work_items, int64_t work_tile_tokens,
                          int64_t qk_work_hint) {
-  set_kv_cache(new_cache_slots, key, value, key_cache, value_cache);
-  const int dev = require_cuda({&query, &key_cache, &cu_seqlens_q, &cu_seqlens_k, &block_table, &cu_block_lens});
-  if (query.dim() != 3) fail("append_and_attend: query must be [n_tokens, n_heads, head_dim]");
-  Tensor out = at::empty({query.size(0), query.size(1), query.size(2)}, query.options());
-  paged_fwd(dev, out, query, key_cache, value_cache, cu_seqlens_q, cu_seqlens_k, block_table, cu_block_lens, max_seqlen_q, max_seqlen_k, softmax_scale, path,
+  // query / key / value may also be the layer's 2-D [T, H * d] tensors (row strides free): the head geometry comes from the caches
+  if (key_cache.dim() != 4) fail("append_and_attend: caches must be [n_blocks, block_size, n_kv_heads, head_dim]");
+  const int64_t hkv = key_cache.size(2), d = key_cache.size(3);
+  const bool flat = query.dim() == 2;
+  if (flat && (d == 0 || query.size(1) % d != 0 || key.dim() != 2 || value.dim() != 2 || key.size(1) != hkv * d || value.size(1) != hkv * d))
+    fail("append_and_attend: 2-D query / key / value must be [n_tokens, n_heads * head_dim] matching the caches");
+  if (!flat && query.dim() != 3) fail("append_and_attend: query must be [n_tokens, n_heads, head_dim] or [n_tokens, n_heads * head_dim]");
+  const int64_t n_tokens = query.size(0), hq = flat ? query.size(1) / d : query.size(1);
+  const Tensor q3 = flat ? query.view({n_tokens, hq, d}) : query;
+  const Tensor k3 = flat ? key.view({n_tokens, hkv, d}) : key;
+  const Tensor v3 = flat ? value.view({n_tokens, hkv, d}) : value;
+  set_kv_cache(new_cache_slots, k3, v3, key_cache, value_cache);
+  const int dev = require_cuda({&q3, &key_cache, &cu_seqlens_q, &cu_seqlens_k, &block_table, &cu_block_lens});
+  Tensor out = at::empty({n_tokens, hq, q3.size(2)}, query.options());
+  paged_fwd(dev, out, q3, key_cache, value_cache, cu_seqlens_q, cu_seqlens_k, block_table, cu_block_lens, max_seqlen_q, max_seqlen_k, softmax_scale, path,
             work_items, work_tile_tokens, qk_work_hint);
-  return out;
+  return flat ? out.view({n_tokens, hq * d}) : out;
 }
 
 int last_launch_count() { return hi_last_launch_count(); }

@@ -292,18 +292,18 @@ class CausalGroupedQueryPageAttention(nn.Module):
         self.handler = self.handlers[0]
 
     def forward(self, query: Tensor, key: Tensor, value: Tensor, attention_params: AttentionParameters) -> CausalGroupedQueryPageAttentionOutput:
+        handler = self.handler
+        if type(handler) is B200CausalGroupedQueryPageAttentionHandler and handler.next_handler is None and query.is_cuda:
+            # view + append + attend in ONE call into the compiled module (the steps of :396-405 back to back on the current stream)
+            p = attention_params
+            kv = p.kv_cache
+            o = append_and_attend(
+                query, key, value, p.new_cache_slots, kv.key_cache, kv.value_cache, p.q_cu_seq_lens, p.kv_cu_seq_lens, p.block_tables, p.cu_blocks_lens,
+                p.q_max_seq_len, p.kv_max_seq_len, self.softmax_scale, handler.path, p.work_items, p.work_tile_tokens, p.qk_work)
+            return CausalGroupedQueryPageAttentionOutput(o=o if o.dim() == 2 else o.view(o.shape[0], -1))  # 3-D in -> 3-D out of the extension
         n_tokens = query.shape[0]
         query = query.view(n_tokens, self.n_qo_heads, self.head_dim)
         key = key.view(n_tokens, self.n_kv_heads, self.head_dim)
         value = value.view(n_tokens, self.n_kv_heads, self.head_dim)
-        handler = self.handler
-        if type(handler) is B200CausalGroupedQueryPageAttentionHandler and handler.next_handler is None and query.is_cuda:
-            # append + attend in ONE call into the compiled module (the two steps of :402-405 back to back on the current stream)
-            p = attention_params
-            key_cache, value_cache = p.kv_cache.get_kv_cache()
-            o = append_and_attend(query, key, value, p.new_cache_slots, key_cache, value_cache, p.q_cu_seq_lens, p.kv_cu_seq_lens,
-                                  p.block_tables, p.cu_blocks_lens, p.q_max_seq_len, p.kv_max_seq_len, self.softmax_scale, handler.path,
-                                  p.work_items, p.work_tile_tokens, p.qk_work)
-            return CausalGroupedQueryPageAttentionOutput(o=o.view(n_tokens, self.n_qo_heads * self.head_dim))
         attention_params.kv_cache.set_kv_cache(attention_params.new_cache_slots, key, value)
         return handler(query, attention_params)

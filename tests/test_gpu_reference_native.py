@@ -235,6 +235,7 @@ def test_migrate_blocks_matches_reference_cuda_across_processes(tmp_path):
         for name, shape, nb_src, nb_dst, n_move in MIGRATION_GEOMETRIES:
             L, T, bs, H, d = shape
             g = torch.Generator().manual_seed(n_move)
+            torch.cuda.empty_cache()  # a fresh cudaMalloc per pool: offset 0 inside its allocation, as the reference assumes
             src = torch.randn(L, T, nb_src, bs, H, d, generator=g).to(torch.bfloat16).to(DEV)
             src_bt = torch.randperm(nb_src, generator=g)[:n_move].tolist()
             dst_bt = torch.randperm(nb_dst, generator=g)[:n_move].tolist()
@@ -269,13 +270,14 @@ def test_oracle_migrate_blocks_agrees_with_reference_cuda(tmp_path):
     import torch.multiprocessing as mp
     _need("block_migration")
     from hydrainfer_b200._C.data_transfer import block_migration as bm
-    shape, nb_src, nb_dst = (3, 2, 8, 2, 64), 700, 650   # > 20 MiB: its own allocation, offset 0
+    shape, nb_src, nb_dst = (3, 2, 8, 2, 64), 2100, 1950   # 25 MiB straight from cudaMalloc (empty_cache below): its own allocation, offset 0
     L, T, bs, H, d = shape
     g = torch.Generator().manual_seed(23)
     src = torch.randn(L, T, nb_src, bs, H, d, generator=g).to(torch.float16)
     dst0 = torch.randn(L, T, nb_dst, bs, H, d, generator=g).to(torch.float16)
     src_bt = torch.randperm(nb_src, generator=g)[:129].tolist()
     dst_bt = torch.randperm(nb_dst, generator=g)[:129].tolist()
+    torch.cuda.empty_cache()  # the pool must not be carved out of a cached segment: the reference assumes offset 0 inside the allocation
     src_d = src.to(DEV)
     handle = bm.get_ipc_mem_handle(src_d)
     assert len(handle) == 64
