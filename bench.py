@@ -10,7 +10,7 @@ paged decode attention over the 2048 cached tokens of every sequence.  Synthetic
 Multi-GPU: sequences are independent, every rank runs its own batch of 64 on its own pool (weak scaling, no data-path
 collective); value = tokens of all ranks / max-over-ranks device time.
 
-Prints ONE JSON line (rank 0): metric decode-attn tokens/s (+ roofline on the split-KV kernel, cpu_baseline, e2e,
+Prints ONE JSON line (rank 0): metric decode-attn tokens/s (+ roofline on the decode attention kernel, cpu_baseline, e2e,
 clocks) and, as extras on the same line, the other halves of BASELINE.json's metric and configs:
   "prefill"        N = 1: BASELINE config 3 (Qwen2-VL-7B 28q/4kv) — pre1k, pre8k, cfg3p (chunked prefill), cfg3mix (48 decode rows +
                    4 chunked prefills) through the layer API; ms, TFLOP/s from 4*Hq*d*sum[q(L-q)+q(q+1)/2], fraction of the measured
@@ -239,7 +239,7 @@ def run_ours(args) -> None:
     t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record(stream)
     for i in range(args.steps):
-        # the append launch happens first; arm the pair so the attention call records around its split-KV kernel
+        # the append launch happens first; arm the pair so the attention call records around its decode kernel
         _lib.lib.hi_set_kernel_timing_events(evs[2 * i], evs[2 * i + 1])
         step()
         launches += 1 + last_launch_count()  # set_kv_cache (1 launch) + attention kernels of the last call
@@ -289,8 +289,9 @@ def run_ours(args) -> None:
             q.copy_(q_host, non_blocking=True)
             k.copy_(k_host, non_blocking=True)
             v.copy_(v_host, non_blocking=True)
+            p = build_params()                  # metadata: one pinned buffer, uploaded on the copy stream with q / k / v
             in_ready[b].record(copy_in)
-        p = build_params()                      # metadata: one pinned buffer, uploaded on the compute stream
+        p.q_cu_seq_lens.record_stream(stream)   # the six metadata arrays are views of one buffer allocated on the copy stream
         stream.wait_event(in_ready[b])
         o = layer(q, k, v, p).o
         computed[b].record(stream)
@@ -371,7 +372,7 @@ def run_ours(args) -> None:
         tp = ROOT / "profiles" / "traffic.json"
         if tp.exists():
             try:
-                traffic = json.loads(tp.read_text()).get("paged_attn_stream_kernel_dram_bytes_per_launch")
+                traffic = json.loads(tp.read_text()).get("bench_decode_kernel_dram_bytes_per_launch")
             except Exception:
                 traffic = None
         # the reference's CPU path on this box's host cores: rank 0, N = 1 only (at N > 1 the other ranks' processes share the cores)
@@ -382,7 +383,7 @@ def run_ours(args) -> None:
             "ms_per_step": ms_total_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "tokens_per_step_per_gpu": BATCH, "l2": "inputs_larger_than_l2 (2.1 GB of KV per step vs 126 MB L2)",
-                       "parallelism": f"sequences sharded, {world} independent rank(s), no collective", "kernel": "scatter_rows_kernel + paged_attn_stream_kernel<bf16,128,1> (cp.async split-KV) + merge_partials_kernel"},
+                       "parallelism": f"sequences sharded, {world} independent rank(s), no collective", "kernel": "scatter_rows_kernel + paged_decode_tc_kernel<bf16,1,8> (TMA-fed KV stream, tokens on the tcgen05 M side; one CTA per (row, KV head), unsplit at this size)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0, "kernel_ms": kernel_ms_max,
                          "algorithmic_bytes_per_launch": BATCH * ALGO_BYTES_PER_TOKEN},

@@ -49,6 +49,20 @@ bool attn_pair_supported(const HiAttnArgs& args);
 int launch_varlen_pair(const HiVarlenArgs& args, cudaStream_t stream);
 int64_t simt_workspace_bytes(int head_dim);
 
+// MHA / group-2 decode: the TMA-fed swapped-operand kernel also streams KV a little faster than the cp.async kernel once the launch
+// is several waves of uniform rows - graph-timed on B200, 32q/32kv heads at ctx 2048: batch 64 0.3003 vs 0.3083 ms (7.15 TB/s =
+// 109 % of the measured copy bandwidth), batch 128 0.595 vs 0.601, batch 64 at ctx 4096 0.593 vs 0.602, 32q/16kv batch 64 0.160 vs
+// 0.167 - and loses where its one-CTA-per-(row, head) grid is a partial wave or the rows are ragged (batch 16 at ctx 2048 0.092 vs
+// 0.085, batch 16 at ctx 8192 0.356 vs 0.308, 64 ragged rows 0.310 vs 0.304, ctx 512 0.086 vs 0.085): those stay on the cp.async kernel.
+static bool decode_tc_wins_ungrouped(const HiAttnArgs& a) {
+  const int64_t ctas = static_cast<int64_t>(a.n_tokens) * a.n_kv_heads;  // one CTA per (row, KV head), 3 resident per SM
+  if (ctas < 4 * 3 * 148) return false;
+  if (a.max_kv_len < 1024 || a.max_kv_len > 6144) return false;
+  if (a.kv_blocks_hint <= 0 || a.n_seqs <= 0) return false;  // no length information: cannot tell uniform from ragged
+  const double mean_len = static_cast<double>(a.kv_blocks_hint) * a.block_size / a.n_seqs;
+  return a.max_kv_len <= 1.15 * mean_len;
+}
+
 }  // namespace hi
 
 extern "C" const char* hi_last_error(void) { return hi::g_error; }
@@ -126,6 +140,8 @@ extern "C" int hi_paged_attention(const HiAttnArgs* p, void* stream_) {
     } else if (a.head_dim != 64 && a.head_dim != 128 && a.head_dim != 256 && attn_pair_supported(a)) {
       path = HI_ATTN_TCGEN05_PAIR;  // head dims only the tile kernel covers (96, ...): it takes decode rows as one-token tiles
     } else if (group >= 4 && attn_decode_tc_supported(a)) {
+      path = HI_ATTN_TCGEN05_DECODE;
+    } else if (decode_tc_wins_ungrouped(a) && attn_decode_tc_supported(a)) {
       path = HI_ATTN_TCGEN05_DECODE;
     } else if (group >= 4 && attn_tc_supported(a)) {
       path = HI_ATTN_TCGEN05;

@@ -169,7 +169,7 @@ def main():
     cfg3_dec = [(1, int(L)) for L in torch.randint(256, 8193, (48,), generator=g).tolist()]
     cfg3_pre = [(512, 512), (512, 2048), (512, 4096), (512, 8192)]
     cases = [
-        ("cfg2", [(1, 2048)] * 64, 32, 32, [SIMT, TC]),
+        ("cfg2", [(1, 2048)] * 64, 32, 32, [SIMT, TC, DEC, AUTO]),
         ("cfg2_b8", [(1, 2048)] * 8, 32, 32, [SIMT, TC]),
         ("cfg2_b1", [(1, 2048)] * 1, 32, 32, [SIMT]),
         ("cfg2_b4", [(1, 2048)] * 4, 32, 32, [SIMT]),
