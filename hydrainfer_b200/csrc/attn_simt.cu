@@ -582,6 +582,10 @@ int launch_merge_partials(const SimtArgs& a, int dtype, int head_dim, cudaStream
     HI_CUDA(launch_pdl(merge_partials_kernel<__nv_bfloat16, 128>, merge_grid<__nv_bfloat16, 128>(a), dim3(kMergeThreads), 0, stream, a));
   } else if (head_dim == 128 && dtype == HI_F16) {
     HI_CUDA(launch_pdl(merge_partials_kernel<__half, 128>, merge_grid<__half, 128>(a), dim3(kMergeThreads), 0, stream, a));
+  } else if (head_dim == 256 && dtype == HI_BF16) {
+    HI_CUDA(launch_pdl(merge_partials_kernel<__nv_bfloat16, 256>, merge_grid<__nv_bfloat16, 256>(a), dim3(kMergeThreads), 0, stream, a));
+  } else if (head_dim == 256 && dtype == HI_F16) {
+    HI_CUDA(launch_pdl(merge_partials_kernel<__half, 256>, merge_grid<__half, 256>(a), dim3(kMergeThreads), 0, stream, a));
   } else {
     set_error("merge_partials: unsupported head_dim %d / dtype %d", head_dim, dtype);
     return HI_ERR_UNSUPPORTED;

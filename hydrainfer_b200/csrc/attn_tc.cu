@@ -69,12 +69,14 @@ struct TcArgs {
   float* part_ml;       // [n_tokens * Hq * n_splits][2]
 };
 
-template <int NST>
+// D = head_dim (128 or 256): a 128-row Q tile and a 128-key K or V tile are D / 64 halves of 16 KiB each.
+template <int NST, int D = kHeadDim>
 struct TcSmem {
+  static constexpr int kTile = (D / 64) * kHalfBytes;   // 32 KiB at head_dim 128, 64 KiB at 256
   static constexpr int kQ = 0;
-  static constexpr int kK = kTileBytes;
-  static constexpr int kV = kTileBytes + NST * kTileBytes;
-  static constexpr int kBars = kTileBytes + 2 * NST * kTileBytes;
+  static constexpr int kK = kTile;
+  static constexpr int kV = kTile + NST * kTile;
+  static constexpr int kBars = kTile + 2 * NST * kTile;
   // barrier slots (8 bytes each)
   static constexpr int bQFull = 0;
   static constexpr int bKFull = 1;
@@ -90,12 +92,17 @@ struct TcSmem {
   static constexpr int kDynamicBytes = kTotal + 1024;  // slack to align the base to 1024 B (128B swizzle atoms)
 };
 
-template <typename T, int NST>
-__global__ void __launch_bounds__(kTcThreads, NST == 1 ? 2 : 1)
+// D = 256 (round 2): the reference's fused backend covers head_dim 256 (static_switch.h:70-85).  One 128-row tile per CTA with
+// S (128 TMEM columns) | O (256 columns); Q, one K and one V stage are 64 KiB each, so one CTA per SM and a single stage:
+// the serial chain Q.K^T -> softmax -> P.V of this kernel, at twice the tensor work per step.
+template <typename T, int NST, int D = kHeadDim>
+__global__ void __launch_bounds__(kTcThreads, (NST == 1 && D == kHeadDim) ? 2 : 1)
 paged_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                      const __grid_constant__ CUtensorMap tm_v, const TcArgs a) {
-  using L = TcSmem<NST>;
+  using L = TcSmem<NST, D>;
   constexpr bool kBf16 = sizeof(T) == 2 && !std::is_same<T, __half>::value;
+  constexpr int kHalves = D / 64;                         // 64-dim halves of a row
+  constexpr uint32_t kTmemAlloc = D == kHeadDim ? kTmemCols : 512u;  // S 128 + O D columns, rounded up to a power of two
 
   // ---- which tile --------------------------------------------------------------------------------------------------
   const int b = blockIdx.z;
@@ -149,7 +156,7 @@ paged_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       ptx::prefetch_tensormap(&tm_v);
     }
     __syncwarp();
-    ptx::tmem_alloc(smem_base + L::kTmemPtr, kTmemCols);
+    ptx::tmem_alloc(smem_base + L::kTmemPtr, kTmemAlloc);
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
@@ -160,10 +167,11 @@ paged_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     // ================================================ TMA producer ================================================
     if (lane == 0) {
       // Q tile: both 64-dim halves, rows ordered (token, head-in-group).
-      const uint32_t q_bytes = 2u * static_cast<uint32_t>(a.group * a.tq) * 128u;
+      const uint32_t q_bytes = static_cast<uint32_t>(kHalves) * static_cast<uint32_t>(a.group * a.tq) * 128u;
       ptx::mbar_arrive_expect_tx(bar(L::bQFull), q_bytes);
-      ptx::tma_load_3d(smem_base + L::kQ, &tm_q, bar(L::bQFull), 0, kvh * a.group, q_start + i0);
-      ptx::tma_load_3d(smem_base + L::kQ + kHalfBytes, &tm_q, bar(L::bQFull), 64, kvh * a.group, q_start + i0);
+#pragma unroll
+      for (int h = 0; h < kHalves; ++h)
+        ptx::tma_load_3d(smem_base + L::kQ + h * kHalfBytes, &tm_q, bar(L::bQFull), 64 * h, kvh * a.group, q_start + i0);
     }
     const uint32_t page_half_bytes = static_cast<uint32_t>(a.block_size) * 128u;
     for (int j = 0; j < n_kv_tiles; ++j) {
@@ -174,7 +182,7 @@ paged_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       // lane p stages page p of the tile
       int blk = 0;
       if (lane < n_valid) blk = __ldg(a.block_tables + blk0 + page0 + lane);
-      const uint32_t tx = static_cast<uint32_t>(n_valid) * 2u * page_half_bytes;
+      const uint32_t tx = static_cast<uint32_t>(n_valid) * static_cast<uint32_t>(kHalves) * page_half_bytes;
       // K
       if (lane == 0) {
         ptx::mbar_wait(bar(L::bKEmpty + st), ph ^ 1u);
@@ -182,9 +190,9 @@ paged_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       }
       __syncwarp();
       if (lane < n_valid) {
-        const uint32_t dst = smem_base + L::kK + st * kTileBytes + lane * page_half_bytes;
-        ptx::tma_load_3d(dst, &tm_k, bar(L::bKFull + st), 0, kvh, blk * a.block_size);
-        ptx::tma_load_3d(dst + kHalfBytes, &tm_k, bar(L::bKFull + st), 64, kvh, blk * a.block_size);
+        const uint32_t dst = smem_base + L::kK + st * L::kTile + lane * page_half_bytes;
+#pragma unroll
+        for (int h = 0; h < kHalves; ++h) ptx::tma_load_3d(dst + h * kHalfBytes, &tm_k, bar(L::bKFull + st), 64 * h, kvh, blk * a.block_size);
       }
       // V
       if (lane == 0) {
@@ -193,16 +201,16 @@ paged_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       }
       __syncwarp();
       if (lane < n_valid) {
-        const uint32_t dst = smem_base + L::kV + st * kTileBytes + lane * page_half_bytes;
-        ptx::tma_load_3d(dst, &tm_v, bar(L::bVFull + st), 0, kvh, blk * a.block_size);
-        ptx::tma_load_3d(dst + kHalfBytes, &tm_v, bar(L::bVFull + st), 64, kvh, blk * a.block_size);
+        const uint32_t dst = smem_base + L::kV + st * L::kTile + lane * page_half_bytes;
+#pragma unroll
+        for (int h = 0; h < kHalves; ++h) ptx::tma_load_3d(dst + h * kHalfBytes, &tm_v, bar(L::bVFull + st), 64 * h, kvh, blk * a.block_size);
       }
     }
   } else if (warp == 5) {
     // ================================================ MMA issuer ==================================================
     if (lane == 0) {
       constexpr uint32_t idesc_qk = ptx::make_idesc_f16(kBf16, false, false, kTileM, kTileN);
-      constexpr uint32_t idesc_pv = ptx::make_idesc_f16(kBf16, false, true, kTileM, kHeadDim);
+      constexpr uint32_t idesc_pv = ptx::make_idesc_f16(kBf16, false, true, kTileM, D);
       const uint32_t tmem_s = tmem_base + kColS;
       const uint32_t tmem_o = tmem_base + kColO;
       ptx::mbar_wait(bar(L::bQFull), 0);
@@ -213,9 +221,9 @@ paged_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         ptx::mbar_wait(bar(L::bKFull + st), ph);
         ptx::tc_fence_after_sync();
         const uint32_t q_addr = smem_base + L::kQ;
-        const uint32_t k_addr = smem_base + L::kK + st * kTileBytes;
+        const uint32_t k_addr = smem_base + L::kK + st * L::kTile;
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
+        for (int kk = 0; kk < D / 16; ++kk) {  // D / 64 halves x 4 k-steps of 16 dims
           const uint32_t off = (kk >> 2) * kHalfBytes + (kk & 3) * 32;
           ptx::mma_f16_ss(tmem_s, ptx::make_smem_desc_sw128(q_addr + off, 16, 1024),
                           ptx::make_smem_desc_sw128(k_addr + off, 16, 1024), idesc_qk, kk > 0);
@@ -226,9 +234,9 @@ paged_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         ptx::mbar_wait(bar(L::bPFull), static_cast<uint32_t>(j) & 1u);
         ptx::mbar_wait(bar(L::bVFull + st), ph);
         ptx::tc_fence_after_sync();
-        const uint32_t v_addr = smem_base + L::kV + st * kTileBytes;
+        const uint32_t v_addr = smem_base + L::kV + st * L::kTile;
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
+        for (int kk = 0; kk < 8; ++kk) {  // (N = D: the MN-major descriptor walks the D / 64 halves at its leading-dim offset)
           ptx::mma_f16_ts(tmem_o, tmem_s + kk * 8, ptx::make_smem_desc_sw128(v_addr + kk * 2048, kHalfBytes, 1024),
                           idesc_pv, (j > 0) || (kk > 0));
         }
@@ -301,7 +309,7 @@ paged_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         l *= alpha;
         m_used = m_new;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < D / 32; ++c) {
           ptx::tmem_ld_x32(tmem_o + c * 32, va);
           ptx::tmem_wait_ld();
 #pragma unroll
@@ -348,13 +356,12 @@ paged_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const int st = j % NST;
         ptx::mbar_wait(bar(L::bVFull + st), static_cast<uint32_t>(j / NST) & 1u);
         if (kv0 + r >= kv_len) {
-          uint4* row0 = reinterpret_cast<uint4*>(smem_gen + L::kV + st * kTileBytes + r * 128);
-          uint4* row1 = reinterpret_cast<uint4*>(smem_gen + L::kV + st * kTileBytes + kHalfBytes + r * 128);
           const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            row0[e] = z;
-            row1[e] = z;
+          for (int h = 0; h < kHalves; ++h) {
+            uint4* row = reinterpret_cast<uint4*>(smem_gen + L::kV + st * L::kTile + h * kHalfBytes + r * 128);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) row[e] = z;
           }
         }
         ptx::fence_proxy_async_smem();
@@ -369,20 +376,20 @@ paged_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     ptx::tc_fence_after_sync();
     const float inv_l = 1.f / l;
     T* orow = static_cast<T*>(a.out) + static_cast<int64_t>(q_start + i) * a.out_row_stride +
-              (kvh * a.group + g) * kHeadDim;
+              (kvh * a.group + g) * D;
     const int64_t pidx = (static_cast<int64_t>(q_start + i) * a.n_qo_heads + (kvh * a.group + g)) * a.n_splits + sp;
     if (a.n_splits > 1 && row_valid) {
       a.part_ml[pidx * 2 + 0] = m_used;
       a.part_ml[pidx * 2 + 1] = l;
     }
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < D / 32; ++c) {
       uint32_t v[32];
       ptx::tmem_ld_x32(tmem_o + c * 32, v);
       ptx::tmem_wait_ld();
       if (a.n_splits > 1) {
         if (row_valid) {
-          float4* dst = reinterpret_cast<float4*>(a.part_o + pidx * kHeadDim + c * 32);
+          float4* dst = reinterpret_cast<float4*>(a.part_o + pidx * D + c * 32);
 #pragma unroll
           for (int e = 0; e < 32; e += 4)
             dst[e >> 2] = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
@@ -406,7 +413,7 @@ paged_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   __syncthreads();
   if (warp == 4) {
     ptx::tc_fence_after_sync();
-    ptx::tmem_dealloc(tmem_base, kTmemCols);
+    ptx::tmem_dealloc(tmem_base, kTmemAlloc);
   }
 }
 
@@ -499,23 +506,23 @@ int pool_map(CUtensorMap* out, int dtype, const void* base, int64_t n_slots, int
 
 bool attn_tc_supported(const HiAttnArgs& args) {
   const int group = args.n_kv_heads > 0 ? args.n_qo_heads / args.n_kv_heads : 0;
-  return (args.dtype == HI_F16 || args.dtype == HI_BF16) && args.head_dim == kHeadDim && group >= 1 && group <= kTileM &&
+  return (args.dtype == HI_F16 || args.dtype == HI_BF16) && (args.head_dim == kHeadDim || args.head_dim == 256) && group >= 1 && group <= kTileM &&
          args.block_size >= 8 && args.block_size <= kTileN && (kTileN % args.block_size) == 0 &&
          (args.q_row_stride % 8) == 0 && (args.out_row_stride % 8) == 0 && aligned_to(args.q, 16) &&
          aligned_to(args.out, 16) && aligned_to(args.key_cache, 16) && aligned_to(args.value_cache, 16) &&
          args.n_blocks > 0;
 }
 
-template <typename T, int NST>
+template <typename T, int NST, int D = kHeadDim>
 static int launch_tc_t(const HiAttnArgs& args, const TcArgs& a, const CUtensorMap& mq, const CUtensorMap& mk,
                        const CUtensorMap& mv, cudaStream_t stream) {
-  using L = TcSmem<NST>;
+  using L = TcSmem<NST, D>;
   static PerDeviceFlags configured;
-  HI_CUDA(configure_dynamic_smem(configured, paged_attn_tc_kernel<T, NST>, L::kDynamicBytes));
+  HI_CUDA(configure_dynamic_smem(configured, paged_attn_tc_kernel<T, NST, D>, L::kDynamicBytes));
   const int q_tiles = (args.max_q_len + a.tq - 1) / a.tq;
   const dim3 grid(q_tiles * a.n_splits, args.n_kv_heads, args.n_seqs);
   timing_mark_start(stream);
-  paged_attn_tc_kernel<T, NST><<<grid, kTcThreads, L::kDynamicBytes, stream>>>(mq, mk, mv, a);
+  paged_attn_tc_kernel<T, NST, D><<<grid, kTcThreads, L::kDynamicBytes, stream>>>(mq, mk, mv, a);
   timing_mark_stop(stream);
   note_launch();
   HI_CUDA(cudaGetLastError());
@@ -524,7 +531,7 @@ static int launch_tc_t(const HiAttnArgs& args, const TcArgs& a, const CUtensorMa
 
 int launch_attn_tc(const HiAttnArgs& args, cudaStream_t stream) {
   if (!attn_tc_supported(args)) {
-    set_error("paged_attention: the tcgen05 path needs fp16/bf16, head_dim 128, block_size in {8,16,32,64,128} and 16-byte aligned rows");
+    set_error("paged_attention: the tcgen05 path needs fp16/bf16, head_dim 128 or 256, block_size in {8,16,32,64,128} and 16-byte aligned rows");
     return HI_ERR_UNSUPPORTED;
   }
   TcArgs a{};
@@ -558,8 +565,8 @@ int launch_attn_tc(const HiAttnArgs& args, cudaStream_t stream) {
     if (n_splits > max_splits) n_splits = max_splits;
     if (const char* env = tuning_env("HI_TC_SPLITS")) n_splits = atoi(env);  // tuning override
     if (n_splits < 1) n_splits = 1;
-    n_splits = cap_splits(n_splits, args.n_tokens, args.n_qo_heads, kHeadDim);
-    const int64_t need = partial_bytes_per_split(args.n_tokens, args.n_qo_heads, kHeadDim) * n_splits;
+    n_splits = cap_splits(n_splits, args.n_tokens, args.n_qo_heads, args.head_dim);
+    const int64_t need = partial_bytes_per_split(args.n_tokens, args.n_qo_heads, args.head_dim) * n_splits;
     if (n_splits > 1 && (args.workspace == nullptr || need > args.workspace_bytes)) {
       set_error("paged_attention: workspace of %lld bytes is smaller than the %lld needed for %d KV splits (see hi_attention_workspace_bytes)",
                 (long long)args.workspace_bytes, (long long)need, n_splits);
@@ -571,18 +578,23 @@ int launch_attn_tc(const HiAttnArgs& args, cudaStream_t stream) {
   if (a.n_splits > 1) {
     const int64_t entries = static_cast<int64_t>(args.n_tokens) * args.n_qo_heads * a.n_splits;
     a.part_o = static_cast<float*>(args.workspace);
-    a.part_ml = a.part_o + entries * kHeadDim;
+    a.part_ml = a.part_o + entries * args.head_dim;
   }
 
   CUtensorMap mq, mk, mv;
-  int rc = make_map(&mq, args.dtype, args.q, args.n_tokens, args.n_qo_heads, args.q_row_stride, a.group, a.tq);
+  int rc = make_map_d(&mq, args.dtype, args.q, args.n_tokens, args.n_qo_heads, args.head_dim, args.q_row_stride, a.group, a.tq);
   if (rc != HI_OK) return rc;
   const int64_t n_slots = args.n_blocks * args.block_size;
-  rc = pool_map(&mk, args.dtype, args.key_cache, n_slots, args.n_kv_heads, args.block_size);
+  rc = pool_map_d(&mk, args.dtype, args.key_cache, n_slots, args.n_kv_heads, args.head_dim, args.block_size);
   if (rc != HI_OK) return rc;
-  rc = pool_map(&mv, args.dtype, args.value_cache, n_slots, args.n_kv_heads, args.block_size);
+  rc = pool_map_d(&mv, args.dtype, args.value_cache, n_slots, args.n_kv_heads, args.head_dim, args.block_size);
   if (rc != HI_OK) return rc;
 
+  if (args.head_dim == 256) {  // 64 KiB each for Q, the K stage and the V stage: one stage, one CTA per SM
+    rc = args.dtype == HI_BF16 ? launch_tc_t<__nv_bfloat16, 1, 256>(args, a, mq, mk, mv, stream)
+                               : launch_tc_t<__half, 1, 256>(args, a, mq, mk, mv, stream);
+    if (rc != HI_OK || a.n_splits == 1) return rc;
+  } else {
   // Ring depth 1 = two co-resident CTAs per SM whose QK / softmax / PV phases overlap each other; measured better than
   // one CTA per SM with a 2- or 3-deep ring for both prefill and decode tiles (profiles/r01_notes.md).
   int stages = 1;
@@ -597,6 +609,7 @@ int launch_attn_tc(const HiAttnArgs& args, cudaStream_t stream) {
                      : launch_tc_t<__half, 1>(args, a, mq, mk, mv, stream);
   }
   if (rc != HI_OK || a.n_splits == 1) return rc;
+  }
 
   SimtArgs m{};
   m.out = args.out;
@@ -610,7 +623,7 @@ int launch_attn_tc(const HiAttnArgs& args, cudaStream_t stream) {
   m.chunk_tiles = a.tiles_per_split * (kTileN / 16);
   m.part_o = a.part_o;
   m.part_ml = a.part_ml;
-  return launch_merge_partials(m, args.dtype, kHeadDim, stream);
+  return launch_merge_partials(m, args.dtype, args.head_dim, stream);
 }
 
 }  // namespace hi

@@ -82,6 +82,8 @@ def paths_for(head_dim, dtype, block_size=16, group=1):
     import os
     if os.environ.get("HI_TEST_SKIP_TC") == "1":  # dev switch: validate the split-KV kernel alone
         return [SIMT]
+    if head_dim == 256 and dtype in (torch.float16, torch.bfloat16) and block_size in (8, 16, 32, 64, 128):
+        return [SIMT, TC, 0]  # the tile kernel's head_dim-256 instance (one CTA per SM, S | O = 128 + 256 TMEM columns)
     if not tc_supported(head_dim, dtype, block_size):
         if pair_supported(head_dim, dtype, block_size):  # head_dim 64 / 96: the pair-tile kernel's variable-head-dim mode
             return ([SIMT] if head_dim == 64 else []) + [PAIR, 0]
@@ -453,3 +455,15 @@ def test_tcgen05_prefill_for_head_dims_below_128(head_dim, dtype):
     if head_dim == 96:
         batch = make_batch([(1, 700), (1, 64), (1, 2000)], 8, 2, head_dim, 16, dtype=dtype, seed=62)
         check_batch(batch, [0], "decode-only head_dim 96")
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_tcgen05_prefill_for_head_dim_256(dtype):
+    """head_dim 256 (the last of the reference's fused head dims, static_switch.h:70-85) on the tcgen05 tile kernel: prefill,
+    chunked prefill and decode rows, MHA / GQA / MQA, unsplit and split (few tiles -> split-KV + the 256-wide merge)."""
+    seq_lens = [(1, 300), (130, 130), (75, 900), (1, 17), (300, 300), (40, 1300), (1, 1)]
+    for heads in ((4, 4), (8, 2), (16, 1)):
+        batch = make_batch(seq_lens, heads[0], heads[1], 256, 16, dtype=dtype, seed=71)
+        check_batch(batch, [TC, 0], f"head_dim 256 heads {heads}")
+    batch = make_batch([(200, 3000)], 4, 2, 256, 16, dtype=dtype, seed=72)  # 2 tiles x 2 heads: split-KV
+    check_batch(batch, [TC], "head_dim 256 split")
