@@ -80,7 +80,12 @@ class B200MultiHeadAttentionHandler(nn.Module):
         v = self._rows(value, batch_size, seq_len)
         o = torch.empty((batch_size * seq_len, self.n_heads, self.head_dim), dtype=query.dtype, device=query.device)
         cu = _cu_seqlens_cache.get(batch_size, seq_len, query.device)
-        mha_varlen_fwd(o, q, k, v, cu, cu, None, None, None, seq_len, seq_len, 1.0 / math.sqrt(self.head_dim), 0, -1, -1, 0)
+        try:
+            mha_varlen_fwd(o, q, k, v, cu, cu, None, None, None, seq_len, seq_len, 1.0 / math.sqrt(self.head_dim), 0, -1, -1, 0)
+        except RuntimeError as e:  # a geometry the kernel does not cover goes down the chain when one is linked
+            if self.next_handler is not None and "hi_b200 error -2" in str(e):
+                return self.next_handler(query, key, value, params)
+            raise
         return MultiHeadAttentionOutput(o=o.view(batch_size, seq_len, hidden_size), attention_scores=None)
 
     def _rows(self, t: Tensor, batch_size: int, seq_len: int) -> Tensor:
@@ -120,8 +125,13 @@ class B200QwenMultiHeadAttentionHandler(nn.Module):
             cu_seqlens = cu_seqlens.to(torch.int32)
         attn_output = torch.empty((seq_length, self.n_heads, self.head_dim), dtype=q.dtype, device=q.device)
         bound = int(max_seqlen) if max_seqlen is not None else int(seq_length)
-        mha_varlen_fwd(attn_output, q, k, v, cu_seqlens, cu_seqlens, None, None, None, bound, bound,
-                       1.0 / math.sqrt(self.head_dim), 0, -1, -1, 0)
+        try:
+            mha_varlen_fwd(attn_output, q, k, v, cu_seqlens, cu_seqlens, None, None, None, bound, bound,
+                           1.0 / math.sqrt(self.head_dim), 0, -1, -1, 0)
+        except RuntimeError as e:
+            if self.next_handler is not None and "hi_b200 error -2" in str(e):
+                return self.next_handler(q, k, v, seq_length, cu_seqlens)
+            raise
         return attn_output.reshape(seq_length, -1)
 
 

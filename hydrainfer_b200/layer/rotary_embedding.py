@@ -42,7 +42,12 @@ class B200RotaryEmbeddingHandler(nn.Module):
             if self.next_handler is not None:
                 return self.next_handler(query, key, position_ids)
             raise RuntimeError("hydrainfer_b200: rotary embedding needs CUDA tensors; no CPU handler is linked")
-        apply_rotary_pos_emb(query, key, position_ids, self.cos_sin_cache, self.rotary_dim, self.interleaved)
+        try:
+            apply_rotary_pos_emb(query, key, position_ids, self.cos_sin_cache, self.rotary_dim, self.interleaved)
+        except RuntimeError as e:  # a dtype / layout the kernel does not cover goes down the chain when one is linked
+            if self.next_handler is not None and "hi_b200 error -2" in str(e):
+                return self.next_handler(query, key, position_ids)
+            raise
         return query, key
 
     def forward_and_cache(self, query: Tensor, key: Tensor, value: Tensor, position_ids: Tensor, slot_ids: Tensor,
