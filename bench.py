@@ -350,7 +350,14 @@ def run_ours(args) -> None:
     del batch, kv_cache, params, qkv_dev
     torch.cuda.empty_cache()
     extras_t0 = time.time()
-    prefill = measure_prefill(dev) if world == 1 and not args.no_extras else None
+    prefill = None
+    if world == 1 and not args.no_extras:
+        # the tensor-bound kernels are the clock-sensitive ones: sample the clocks of THIS leg too, so that a box that throttles under
+        # the tensor load (sw_power_cap / thermal) is visible next to the fractions it produced
+        pre_sampler = ClockSampler(local)
+        pre_sampler.start()
+        prefill = measure_prefill(dev)
+        prefill["clocks"] = pre_sampler.stop()
     cfg4 = measure_cfg4(rank, world, dev) if not args.no_extras else None
     migrate, migrate_sweep = measure_migration_sweep(rank, world, local, dev) if not args.no_extras else (None, None)
     migrate_under_decode = measure_migration_under_decode(rank, world, local, dev) if not args.no_extras else None
