@@ -95,9 +95,20 @@ struct IpcEntry {
   uint8_t handle[64];
   int device;
   void* base;
+  size_t size;  // bytes of the mapped allocation (0 if the driver would not tell)
 };
 static std::mutex g_ipc_mu;
 static std::vector<IpcEntry> g_ipc_entries;
+
+// A pool another process exported (cudaPointerGetAttributes reports the MAPPING device for such memory, not the exporting GPU).
+static bool pointer_is_ipc_mapped(const void* ptr) {
+  std::lock_guard<std::mutex> lock(g_ipc_mu);
+  for (const IpcEntry& e : g_ipc_entries) {
+    const char* b = static_cast<const char*>(e.base);
+    if (ptr >= b && (e.size == 0 ? ptr == b : ptr < b + e.size)) return true;
+  }
+  return false;
+}
 
 }  // namespace hi
 
@@ -108,6 +119,9 @@ extern "C" int hi_migrate_blocks(const int32_t* src_blocks, const int32_t* dst_b
 
 namespace hi {
 static std::atomic<int> g_migrate_max_ctas{0};  // 0 = no cap (process-wide tuning knob)
+
+struct IpcEntry;
+static bool pointer_is_ipc_mapped(const void* ptr);  // defined behind the IPC cache below
 
 // Device that owns the allocation behind `ptr` (peer-mapped and IPC-mapped pools report the exporting GPU); `fallback` when the
 // runtime cannot tell.  The last few answers are cached: pools live for the life of the process.
@@ -163,7 +177,8 @@ static int prepare_migration(MigrateArgs& a, int64_t& grid, int64_t n, const voi
   const int cap = g_migrate_max_ctas.load(std::memory_order_relaxed);
   if (cap > 0) {
     if (grid > cap) grid = cap;
-  } else if (a.total_pieces > grid * 4 && (pointer_device(src_pool, device) != device || pointer_device(dst_pool, device) != device)) {
+  } else if (a.total_pieces > grid * 4 && (pointer_is_ipc_mapped(src_pool) || pointer_is_ipc_mapped(dst_pool) ||
+                                            pointer_device(src_pool, device) != device || pointer_device(dst_pool, device) != device)) {
     grid = static_cast<int64_t>(sm_count) * 2;
   }
   if (grid > a.total_pieces) grid = a.total_pieces;
@@ -284,6 +299,19 @@ extern "C" int hi_ipc_open_handle(const uint8_t handle[64], int64_t offset, int 
   std::memcpy(e.handle, handle, 64);
   e.device = device;
   e.base = base;
+  e.size = 0;
+  {
+    typedef int (*GetRangeFn)(void**, size_t*, void*);  // cuMemGetAddressRange
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    void* rbase = nullptr;
+    size_t rsize = 0;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn != nullptr &&
+        qres == cudaDriverEntryPointSuccess && reinterpret_cast<GetRangeFn>(fn)(&rbase, &rsize, base) == 0)
+      e.size = rsize;
+    else
+      (void)cudaGetLastError();
+  }
   g_ipc_entries.push_back(e);
   *ptr_out = static_cast<char*>(base) + offset;
   return HI_OK;
