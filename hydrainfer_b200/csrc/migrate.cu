@@ -170,8 +170,9 @@ static int prepare_migration(MigrateArgs& a, int64_t& grid, int64_t n, const voi
   // 8 resident CTAs of 256 threads per SM = 128 KiB of loads in flight per SM: what a pool -> pool copy inside one GPU's HBM wants
   // (2.9 TB/s), and what a small request wants (all its pieces in flight in one round trip).  A LARGE transfer over NVLink needs
   // far less - 800 GB/s x 3 us = 2.4 MB in flight, 16 KiB per SM - and 8 CTAs per SM take every thread slot of the receiving
-  // GPU away from the decode step running beside the pull (bench.py migrate_under_decode on 2 B200: decode 1.57x slower at
-  // 8 CTAs/SM, 1.41x at 2, 1.31x at 1, the pull alone 777 / 775 / 762 GB/s): 2 CTAs per SM there.
+  // GPU away from the decode step running beside the pull.  bench.py migrate_under_decode on 2 B200 (pull alone / pull under
+  // decode / slowdown of the decode step): 8 CTAs per SM 778 / 769 GB/s / 1.61x, 2 per SM 773 / 463 / 1.52x, 1 per SM
+  // 761 / 555 / 1.33x, 64 CTAs 410 / 255 / 1.19x.  One CTA per SM keeps 98 % of the rate alone and is the best trade under load.
   // hi_migrate_set_max_ctas() overrides the choice.
   grid = static_cast<int64_t>(sm_count) * 8;
   const int cap = g_migrate_max_ctas.load(std::memory_order_relaxed);
@@ -179,7 +180,7 @@ static int prepare_migration(MigrateArgs& a, int64_t& grid, int64_t n, const voi
     if (grid > cap) grid = cap;
   } else if (a.total_pieces > grid * 4 && (pointer_is_ipc_mapped(src_pool) || pointer_is_ipc_mapped(dst_pool) ||
                                             pointer_device(src_pool, device) != device || pointer_device(dst_pool, device) != device)) {
-    grid = static_cast<int64_t>(sm_count) * 2;
+    grid = static_cast<int64_t>(sm_count);
   }
   if (grid > a.total_pieces) grid = a.total_pieces;
   return HI_OK;
