@@ -54,6 +54,7 @@ constexpr uint32_t kP2TmemCols = 512;
 constexpr uint32_t kP2ColTile = 256;          // columns per query tile: S[0] at +0, S[1] at +64, O at +128
 constexpr uint32_t kP2ColO = 128;
 constexpr float kP2Rescale = 8.0f;
+constexpr int kP2Xchg = kP2D + 4;             // floats per row of the tile-1 -> tile-0 state exchange of an interleaved decode item: O[128], m, l, pad
 constexpr int kP2ClaimAhead = 8;              // 64-key steps of the current item left (for the K producer) when the next item is claimed;
                                               // swept on B200: 4, 8 and 16 are equivalent, 32 loses 2.5 % on the config-3 mixed batch, whole-item
                                               // lookahead 26 %
@@ -76,6 +77,7 @@ struct P2Args {
   unsigned int* work_counter;  // zeroed before the launch; NULL = static (boustrophedon) assignment
   int n_items;       // work items of the launch = CTA-sized units: (sequence, KV head, pair of tiles, split)
   int max_pairs;     // without a host plan: pair slots per sequence, ceil(max_q_len / (2 tq))
+  int interleave_decode;  // decode items (q_len == 1) are walked by BOTH tiles: tile t takes the 64-key steps of parity t (see P2Item::il)
   int use_tma_store;  // epilogue of whole direct tiles through shared memory + cp.async.bulk.tensor (needs tm_o and head_dim 128)
   int debug;  // timing experiments only (HI_PAIR_DEBUG): bit 0 = softmax warps skip their math, bit 1 = no MMA is issued,
               // bit 2 = K/V tiles are not loaded (barriers only)
@@ -129,8 +131,10 @@ struct P2Item {
   int q_start, q_len, kv_len;
   int i0;        // first query token of the pair (position within the sequence)
   int j_begin;   // first 64-key step of this split
-  int nt[2];     // steps walked for tile t (local step j is global step j_begin + j)
-  int n_all;     // max(nt[0], nt[1]); 0 = nothing to do
+  int nt[2];     // steps walked for tile t (local step j is global step j_begin + j; interleaved items: j_begin + 2 j + t)
+  int n_all;     // ring steps of the item: max(nt[0], nt[1]), or nt[0] + nt[1] for an interleaved item; 0 = nothing to do
+  bool il;       // interleaved decode item: one query token, BOTH tiles hold its rows, tile t owns the steps of parity t and the two
+                 // (m, l, O) states are merged in the epilogue - a decode row keeps both halves of the CTA busy instead of one
   bool direct[2];  // tile t sees all its keys in this one split: its rows go straight to `out`, not to the fp32 partials
   int blk0, n_pages;
 };
@@ -190,6 +194,16 @@ __device__ __forceinline__ void p2_item_body(const P2Args& a, int pair, P2Item& 
     }
   }
   it.n_all = max(it.nt[0], it.nt[1]);
+  it.il = false;
+  if constexpr (!VL) {
+    if (a.interleave_decode && it.q_len == 1 && it.nt[0] >= 2) {
+      it.il = true;
+      it.n_all = it.nt[0];
+      it.nt[1] = it.nt[0] >> 1;          // odd steps
+      it.nt[0] = it.nt[0] - it.nt[1];    // even steps
+      it.direct[1] = it.direct[0];
+    }
+  }
 }
 
 template <bool VL = false>
@@ -325,7 +339,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   // with at least two steps (P.V(n-2) barrier).
   if (warp >= 8) {
     // ========================== TMA producers (warps 8, 11) and MMA warps (9, 10) ====================================
-    ptx::setmaxnreg_dec<72>();
+    ptx::setmaxnreg_dec<88>();  // 4 x 88 + 8 x 208 registers per lane = 2016 of 2048; at 72 the MMA-issue loop spills once it tracks interleaved items
     if (warp == 8 || warp == 11) {
       // ---- TMA producer: warp 8 stages Q and the K ring, warp 11 the V ring.  The warp stays converged; one elected lane
       // issues.
@@ -370,8 +384,9 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
               if (ptx::elect_one()) {
                 const uint32_t dst = smem_base + L::kQ + t * kP2QTile;
                 ptx::mbar_arrive_expect_tx(bar(L::bQFull + t), n_halves * static_cast<uint32_t>(a.group * a.tq) * 128u);
-                ptx::tma_load_3d(dst, &tm_q, bar(L::bQFull + t), 0, it.kvh * a.group, it.q_start + it.i0 + t * a.tq);
-                if (n_halves == 2u) ptx::tma_load_3d(dst + kP2QHalf, &tm_q, bar(L::bQFull + t), 64, it.kvh * a.group, it.q_start + it.i0 + t * a.tq);
+                const int q_tok = it.q_start + it.i0 + (it.il ? 0 : t * a.tq);  // interleaved items: both tiles hold the same rows
+                ptx::tma_load_3d(dst, &tm_q, bar(L::bQFull + t), 0, it.kvh * a.group, q_tok);
+                if (n_halves == 2u) ptx::tma_load_3d(dst + kP2QHalf, &tm_q, bar(L::bQFull + t), 64, it.kvh * a.group, q_tok);
               }
               __syncwarp();
               ++n_q[t];
@@ -504,6 +519,13 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         }
         const int n_t = t ? it.nt[1] : it.nt[0];
         const int n_all = it.n_all;
+        // Which ring steps this tile consumes, and its running index over them.  Ordinary items: steps 0 .. n_t - 1, Q.K^T issued two
+        // steps ahead of P.V.  Interleaved decode items: the steps of parity t (own index j >> 1); the look-ahead of two ring steps is
+        // then ONE own step, so S(u + 1) is issued right behind P.V(u) and the two tiles alternate on the tensor pipe.
+        const int il_sh = it.il ? 1 : 0;     // own index of ring step j = j >> il_sh
+        const int il_par = it.il ? t : 0;    // ... and the tile owns it iff (j & il_sh) == il_par (and the index is below n_t)
+        auto owns = [&](int j) -> bool { return (j & il_sh) == il_par && (j >> il_sh) < n_t; };
+        auto own_idx = [&](int j) -> int { return j >> il_sh; };
         trace(1, n_it, n_t);
         // prologue: S_t(0) and S_t(1).  Steps at or beyond n_t (this tile sees fewer keys than its sibling) only release
         // the ring stages.
@@ -517,7 +539,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
             ptx::mbar_wait(bar(L::bKFull + ks), k_phase(gj));
             ptx::tc_fence_after_sync();
             if (ptx::elect_one()) {
-              if (jj < n_t) issue_qk(ks, (gs + jj) & 1, jj == n_t - 1); else ptx::mbar_arrive(bar(L::bKEmpty + ks));
+              if (owns(jj)) issue_qk(ks, (gs + own_idx(jj)) & 1, own_idx(jj) == n_t - 1); else ptx::mbar_arrive(bar(L::bKEmpty + ks));
             }
             __syncwarp();
           }
@@ -525,8 +547,9 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         // step j: P_t.V(j), then Q_t.K(j+2) into the S buffer P_t(j) just vacated (in order behind P_t.V(j))
         for (int j = 0; j < n_all; ++j) {
           const uint32_t gj = g + j;
-          const int s = static_cast<int>(v_stage(gj)), s2 = static_cast<int>(k_stage(gj + 2)), buf = (gs + j) & 1;
-          const bool has_pv = j < n_t;
+          const int u = own_idx(j);  // own index of step j (meaningful when this tile owns it)
+          const int s = static_cast<int>(v_stage(gj)), s2 = static_cast<int>(k_stage(gj + 2)), buf = (gs + u) & 1;
+          const bool has_pv = owns(j);
           const bool more = j + 2 < n_all;
           if (j == max(n_all - 2, 0)) {  // warp 8 published the next index when it finished this item's K loads, steps ago
             const int k = next_item(n_it++, true);
@@ -537,21 +560,22 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
           ptx::mbar_wait(bar(L::bVFull + s), v_phase(gj));
           if (more) ptx::mbar_wait(bar(L::bKFull + s2), k_phase(gj + 2));
           if (has_pv) {
-            if (j == 0) ptx::mbar_wait(bar(L::bOEmpty + t), (n_act & 1u) ^ 1u);  // the previous item's O_t has been read out
-            ptx::mbar_wait(bar(L::bPFull + 2 * t + buf), ((gs + j) >> 1) & 1u);
+            if (u == 0) ptx::mbar_wait(bar(L::bOEmpty + t), (n_act & 1u) ^ 1u);  // the previous item's O_t has been read out
+            ptx::mbar_wait(bar(L::bPFull + 2 * t + buf), ((gs + u) >> 1) & 1u);
           }
           ptx::tc_fence_after_sync();
           trace(3, n_it, j);
           if (ptx::elect_one()) {
             if (has_pv) {
-              issue_pv(s, buf, j > 0);
-              if (j == n_t - 2) ptx::mma_commit(bar(L::bPvDone + t));
-              if (j == n_t - 1) ptx::mma_commit(bar(L::bOFull + t));
+              issue_pv(s, buf, u > 0);
+              if (u == n_t - 2) ptx::mma_commit(bar(L::bPvDone + t));
+              if (u == n_t - 1) ptx::mma_commit(bar(L::bOFull + t));
             } else {
               ptx::mbar_arrive(bar(L::bVEmpty + s));
             }
             if (more) {
-              if (j + 2 < n_t) issue_qk(s2, buf, j + 2 == n_t - 1); else ptx::mbar_arrive(bar(L::bKEmpty + s2));
+              const int u2 = own_idx(j + 2);
+              if (owns(j + 2)) issue_qk(s2, (gs + u2) & 1, u2 == n_t - 1); else ptx::mbar_arrive(bar(L::bKEmpty + s2));
             }
           }
           __syncwarp();
@@ -605,7 +629,8 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         continue;
       }
       trace(1, n_it, n_mine);
-      const int first = it.i0 + t * a.tq;
+      const bool il = it.il;                           // interleaved decode item: both tiles hold the token, tile t walks the steps of parity t
+      const int first = it.i0 + (il ? 0 : t * a.tq);
       const int i = first + tok;                       // query position within the sequence
       const bool row_valid = (tok < a.tq) && (i < it.q_len);
       const int lim = (VL && !a.causal) ? it.kv_len - 1 : i + (it.kv_len - it.q_len);  // last visible key index of this row
@@ -619,7 +644,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         const uint32_t sj = gs + j;
         const int buf = sj & 1;
         const uint32_t tmem_s = tmem_t + buf * kP2TileN;
-        const int kv0 = (it.j_begin + j) * kP2TileN;
+        const int kv0 = (it.j_begin + (il ? 2 * j + t : j)) * kP2TileN;
         const int col_lim = lim - kv0;                 // columns [0, col_lim] are visible
         ptx::mbar_wait(bar(L::bSFull + 2 * t + buf), (sj >> 1) & 1u);
         ptx::tc_fence_after_sync();
@@ -656,8 +681,11 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
             // Lazy rescale: the warp pays the TMEM round trip only when some row's max grew by more than 2^8.  O_t must be
             // quiescent: P_t.V(j-1) complete (implied by S_t(j+1), issued behind it; the last step has its own commit) and
             // P_t.V(j) not issued before this thread's P arrival below.
-            if (j + 1 < n_mine) ptx::mbar_wait(bar(L::bSFull + 2 * t + (buf ^ 1)), ((sj + 1) >> 1) & 1u);
-            else ptx::mbar_wait(bar(L::bPvDone + t), n_pv2 & 1u);
+            // (interleaved items: Q.K(j) was issued right behind P.V(j - 1), so the S(j) this thread already waited for implies it)
+            if (!il) {
+              if (j + 1 < n_mine) ptx::mbar_wait(bar(L::bSFull + 2 * t + (buf ^ 1)), ((sj + 1) >> 1) & 1u);
+              else ptx::mbar_wait(bar(L::bPvDone + t), n_pv2 & 1u);
+            }
             ptx::tc_fence_after_sync();
             const float m_new = fmaxf(m_used, mxs);
             const float alpha = fast_exp2(m_used - m_new);
@@ -708,6 +736,77 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       if (more) p2_item_body<VL>(a, pair_nxt, nxt);
       ptx::tc_fence_after_sync();
       trace(5, n_it, 0);
+      // Interleaved decode item: tile 1 hands its (m, l, O) to tile 0 through shared memory (tile 1's staging buffer, rows of
+      // kP2Xchg floats: O, m, l) and is done; tile 0 folds that state into its own O in TMEM and then leaves through the ordinary epilogue
+      // below.  Two CTA-wide rendezvous per item: "tile 1's state is in shared memory" and "tile 0 has read it" (the buffer is
+      // tile 1's TMA staging buffer for its next whole tile).  A separate pass on purpose: the epilogue below keeps its
+      // register footprint (see the note on spills in DESIGN.md).
+      if (il) {
+        float* xchg = reinterpret_cast<float*>(smem_gen + L::kOst + kP2QHalf) + r * kP2Xchg;  // 16-byte aligned rows
+        if (t == 1) {
+          if (r == 0) ptx::bulk_wait_group_read<0>();  // this tile's last TMA store has read the buffer
+          ptx::named_bar_sync(2, kP2TileM);
+          if (warp_active) {
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+              uint32_t v[32];
+              ptx::tmem_ld_x32(tmem_o + c * 32, v);
+              ptx::tmem_wait_ld();
+              if (row_valid) {
+                float4* x4 = reinterpret_cast<float4*>(xchg + c * 32);
+#pragma unroll
+                for (int e = 0; e < 32; e += 4)
+                  x4[e >> 2] = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+              }
+            }
+            if (row_valid) {
+              xchg[kP2D] = m_used;
+              xchg[kP2D + 1] = l;
+            }
+          }
+          ptx::tc_fence_before_sync();
+          ptx::mbar_arrive(bar(L::bOEmpty + t));       // O_1 has left TMEM
+          ptx::named_bar_sync(3, 2 * kP2TileM);        // tile 1's state is in shared memory
+          ptx::named_bar_sync(3, 2 * kP2TileM);        // tile 0 has read it
+          trace(6, n_it, 0);
+          gs += n_mine;
+          ++n_act;
+          if (n_mine >= 2) ++n_pv2;
+          continue;
+        }
+        ptx::named_bar_sync(3, 2 * kP2TileM);          // tile 1's state is in shared memory
+        if (warp_active) {
+          float w_own = 1.f, w_peer = 0.f;
+          if (row_valid) {
+            const float m_peer = xchg[kP2D], l_peer = xchg[kP2D + 1];
+            const float m_new = fmaxf(m_used, m_peer);
+            w_own = fast_exp2(m_used - m_new);
+            w_peer = fast_exp2(m_peer - m_new);
+            l = l * w_own + l_peer * w_peer;
+            m_used = m_new;
+          }
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            ptx::tmem_ld_x32(tmem_o + c * 32, v);
+            ptx::tmem_wait_ld();
+            if (row_valid) {
+              const float4* x4 = reinterpret_cast<const float4*>(xchg + c * 32);
+#pragma unroll
+              for (int e = 0; e < 32; e += 4) {
+                const float4 p = x4[e >> 2];
+                v[e] = __float_as_uint(__uint_as_float(v[e]) * w_own + p.x * w_peer);
+                v[e + 1] = __float_as_uint(__uint_as_float(v[e + 1]) * w_own + p.y * w_peer);
+                v[e + 2] = __float_as_uint(__uint_as_float(v[e + 2]) * w_own + p.z * w_peer);
+                v[e + 3] = __float_as_uint(__uint_as_float(v[e + 3]) * w_own + p.w * w_peer);
+              }
+            }
+            ptx::tmem_st_x32(tmem_o + c * 32, v);
+          }
+          ptx::tmem_wait_st();
+        }
+        ptx::named_bar_sync(3, 2 * kP2TileM);          // tile 0 has read the exchange buffer
+      }
       const float inv_l = 1.f / l;
       const int head = it.kvh * a.group + g;
       const int d_out = VD ? a.head_dim : kP2D;
@@ -1035,6 +1134,9 @@ int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
                                  : launch_pair_t<__half, 0, 2>(args.device, a, mq, mk, mv, mo, stream);
   }
 
+  // decode rows of a mixed batch are walked by both tiles (the exchange rows of kP2Xchg floats fit tile 1's 16 KiB staging buffer)
+  a.interleave_decode = a.group * kP2Xchg * 4 <= kP2QHalf ? 1 : 0;
+  if (const char* env = tuning_env("HI_PAIR_INTERLEAVE")) a.interleave_decode = a.interleave_decode && atoi(env) != 0;  // A/B switch
   a.use_tma_store = 1;
 #ifdef HI_P2_NO_STAGING
   a.use_tma_store = 0;
