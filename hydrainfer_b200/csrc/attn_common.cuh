@@ -28,6 +28,7 @@ struct SimtArgs {
   // Merge only: > 0 when the producer handled query rows in tiles of this many tokens per sequence and wrote a tile whose
   // LAST row needs a single chunk straight to `out` (normalised); the merge leaves those rows alone.
   int direct_tile_tokens;
+  int direct_tiles;  // ... with at most this many 16-token tiles of visible keys (0: chunk_tiles, i.e. "fits the first chunk")
 };
 
 // One merged row = LSE-weighted sum of its valid chunks; chunk c covers 16-token tiles [c*chunk_tiles, (c+1)*chunk_tiles).

@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(kMergeThreads) merge_partials_kernel(const Sim
     // the producer wrote this row's tile directly when the tile's last row fits in one chunk
     const int i_last = min(q_len, ((t - q_start) / a.direct_tile_tokens + 1) * a.direct_tile_tokens) - 1;
     const int vis_last = kv_len - q_len + i_last + 1;
-    if (((vis_last + 15) >> 4) <= a.chunk_tiles) return;
+    if (((vis_last + 15) >> 4) <= (a.direct_tiles > 0 ? a.direct_tiles : a.chunk_tiles)) return;
   }
   const int vis = kv_len - q_len + (t - q_start) + 1;
   const int tiles_total = (vis + 15) >> 4;

@@ -72,6 +72,8 @@ struct P2Args {
   float scale_log2;
   int n_splits;
   int tiles_per_split;  // in 64-key steps
+  int direct_limit;     // a tile that sees at most this many steps (>= tiles_per_split) is ONE work item - split 0 walks all of it and
+                        // writes `out` directly, its other splits are empty - so that only the heaviest tiles of a launch are cut
   float* part_o;
   float* part_ml;
   unsigned int* work_counter;  // zeroed before the launch; NULL = static (boustrophedon) assignment
@@ -189,8 +191,8 @@ __device__ __forceinline__ void p2_item_body(const P2Args& a, int pair, P2Item& 
       const int i_last = min(it.q_len, first + a.tq) - 1;
       const int kv_end = (VL && !a.causal) ? it.kv_len : i_last + (it.kv_len - it.q_len) + 1;  // keys [0, kv_end) are visible to the tile
       const int n_vis = (kv_end + kP2TileN - 1) / kP2TileN;
-      it.nt[t] = max(0, min(n_vis - it.j_begin, a.tiles_per_split));
-      it.direct[t] = n_vis <= a.tiles_per_split;  // the same rule merge_partials_kernel applies (direct_tile_tokens)
+      it.direct[t] = n_vis <= a.direct_limit;  // the same rule merge_partials_kernel applies (direct_tile_tokens, direct_tiles)
+      it.nt[t] = it.direct[t] ? (it.sp == 0 ? n_vis : 0) : max(0, min(n_vis - it.j_begin, a.tiles_per_split));
     }
   }
   it.n_all = max(it.nt[0], it.nt[1]);
@@ -1048,6 +1050,7 @@ int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
   const int64_t base_ctas = a.work_items != nullptr ? n_list * args.n_kv_heads : static_cast<int64_t>(n_pairs) * args.n_kv_heads * args.n_seqs;
   const int max_kv_tiles = (args.max_kv_len + kP2TileN - 1) / kP2TileN;
   int n_splits = 1;
+  int direct_limit = 0;  // 0: whatever fits one split
   if (args.qk_work_hint > 0 && a.work_items != nullptr) {
     // CTA-steps: every work item walks its visible keys in 64-key steps, once per KV head
     const double total_steps = static_cast<double>(args.qk_work_hint) / kP2TileN * args.n_kv_heads;
@@ -1056,9 +1059,24 @@ int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
     // chunked-prefill rows alone - longest item 1.44 shares - run 0.1275 ms unsplit against 0.131 / 0.132 / 0.129 ms with
     // 2 / 3 / 4 chunks, the mixed batch 0.153 ms unsplit against 0.175 / 0.193 with 2 / 3: partial traffic, the merge and the
     // extra item boundaries cost more than the last few per cent of balance.)
-    int chunk = static_cast<int>(1.5 * total_steps / kSms) + 1;
-    if (chunk < kMinTilesPerSplit) chunk = kMinTilesPerSplit;
-    if (chunk < max_kv_tiles) n_splits = (max_kv_tiles + chunk - 1) / chunk;
+    // Round 2: only the HEAVY tiles are cut.  Tiles of up to one share stay whole work items (`direct_limit`), longer ones are cut
+    // into pieces of about half a share, so the tail of the launch is made of half-share pieces instead of whole long items
+    // (config-3 chunked prefill: 60 items of 128 steps at 94 steps per SM -> 180 pieces of 43).
+    const double share = total_steps / kSms;
+    if (max_kv_tiles > 1.15 * share && !(tuning_env("HI_PAIR_HEAVY_SPLIT") && tuning_env("HI_PAIR_HEAVY_SPLIT")[0] == '0')) {
+      double whole_frac = 1.0, piece_frac = 0.55;  // tuning overrides: HI_PAIR_WHOLE_FRAC, HI_PAIR_PIECE_FRAC
+      if (const char* env = tuning_env("HI_PAIR_WHOLE_FRAC")) whole_frac = atof(env);
+      if (const char* env = tuning_env("HI_PAIR_PIECE_FRAC")) piece_frac = atof(env);
+      direct_limit = static_cast<int>(whole_frac * share) > kMinTilesPerSplit ? static_cast<int>(whole_frac * share) : kMinTilesPerSplit;
+      double piece = piece_frac * share;
+      if (piece < kMinTilesPerSplit) piece = kMinTilesPerSplit;
+      const int pieces = static_cast<int>((max_kv_tiles + piece - 1) / piece);
+      if (pieces > 1) n_splits = pieces;
+    } else {
+      int chunk = static_cast<int>(1.5 * total_steps / kSms) + 1;
+      if (chunk < kMinTilesPerSplit) chunk = kMinTilesPerSplit;
+      if (chunk < max_kv_tiles) n_splits = (max_kv_tiles + chunk - 1) / chunk;
+    }
   } else if (base_ctas < 2 * kSms) {
     n_splits = static_cast<int>((2 * kSms + base_ctas - 1) / base_ctas);
     const int max_splits = (max_kv_tiles + kMinTilesPerSplit - 1) / kMinTilesPerSplit;
@@ -1079,6 +1097,7 @@ int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
   }
   a.tiles_per_split = (max_kv_tiles + n_splits - 1) / n_splits;
   a.n_splits = (max_kv_tiles + a.tiles_per_split - 1) / a.tiles_per_split;
+  a.direct_limit = (a.n_splits > 1 && direct_limit > a.tiles_per_split) ? direct_limit : a.tiles_per_split;
   if (a.n_splits > 1) {
     const int64_t entries = static_cast<int64_t>(args.n_tokens) * args.n_qo_heads * a.n_splits;
     a.part_o = static_cast<float*>(args.workspace);
@@ -1168,6 +1187,7 @@ int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
   m.part_o = a.part_o;
   m.part_ml = a.part_ml;
   m.direct_tile_tokens = a.tq;
+  m.direct_tiles = a.direct_limit * (kP2TileN / 16);
   return launch_merge_partials(m, args.dtype, kP2D, stream);
 }
 
@@ -1203,6 +1223,7 @@ int launch_varlen_pair(const HiVarlenArgs& v, cudaStream_t stream) {
   a.idesc_pv = ptx::make_idesc_f16(v.dtype == HI_BF16, false, true, kP2TileM, a.n_kk * 16);
   a.n_splits = 1;  // sequences of a vision batch are plentiful and short: no split-KV
   a.tiles_per_split = (v.max_kv_len + kP2TileN - 1) / kP2TileN;
+  a.direct_limit = a.tiles_per_split;
   a.max_pairs = (v.max_q_len + 2 * a.tq - 1) / (2 * a.tq);
   const int64_t n_items = static_cast<int64_t>(a.max_pairs) * v.n_kv_heads * v.n_seqs;
   if (n_items > 0x7fffffff) {
