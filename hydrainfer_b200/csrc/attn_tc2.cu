@@ -1063,7 +1063,9 @@ int launch_attn_pair(const HiAttnArgs& args, cudaStream_t stream) {
     // into pieces of about half a share, so the tail of the launch is made of half-share pieces instead of whole long items
     // (config-3 chunked prefill: 60 items of 128 steps at 94 steps per SM -> 180 pieces of 43).
     const double share = total_steps / kSms;
-    if (max_kv_tiles > 1.15 * share && !(tuning_env("HI_PAIR_HEAVY_SPLIT") && tuning_env("HI_PAIR_HEAVY_SPLIT")[0] == '0')) {
+    double trig = 1.15;
+    if (const char* env = tuning_env("HI_PAIR_HEAVY_TRIG")) trig = atof(env);
+    if (max_kv_tiles > trig * share && !(tuning_env("HI_PAIR_HEAVY_SPLIT") && tuning_env("HI_PAIR_HEAVY_SPLIT")[0] == '0')) {
       double whole_frac = 1.0, piece_frac = 0.55;  // tuning overrides: HI_PAIR_WHOLE_FRAC, HI_PAIR_PIECE_FRAC
       if (const char* env = tuning_env("HI_PAIR_WHOLE_FRAC")) whole_frac = atof(env);
       if (const char* env = tuning_env("HI_PAIR_PIECE_FRAC")) piece_frac = atof(env);
