@@ -640,6 +640,8 @@ def measure_migration(rank: int, world: int, local: int, dev: torch.device, pool
         if world > 1:
             dist.barrier()
 
+    per_receiver: list[list[float]] = []  # one entry per timed leg: the median of every receiving rank (the figure is their max)
+
     def timed(fn) -> float:
         ts = []
         for i in range(reps + 2):
@@ -654,7 +656,11 @@ def measure_migration(rank: int, world: int, local: int, dev: torch.device, pool
                 ts.append(s.elapsed_time(e))
         t = torch.tensor([statistics.median(ts) if is_receiver else 0.0], dtype=torch.float64, device=dev)
         if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            every = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(every, t)
+            per_receiver.append([round(float(x.item()), 5) for x in every[1::2]])
+            return max(per_receiver[-1])
+        per_receiver.append([round(float(t.item()), 5)])
         return float(t.item())
 
     # verification material BEFORE the copy: checksums of the source blocks, computed by the rank that owns them
@@ -693,6 +699,7 @@ def measure_migration(rank: int, world: int, local: int, dev: torch.device, pool
             "ms": ms, "gbs_per_pair": gbs, "gbs_aggregate": pairs * gbs, "pattern": pattern,
             "bit_exact": ok, "verified": f"all {n_move} moved blocks: position-weighted 64-bit checksums of the destination blocks == those the source rank computed",
             "memcpy_peer_gbs": copy_gbs, "memcpy_peer_ms": copy_ms,
+            "ms_per_receiver": per_receiver[0], "memcpy_peer_ms_per_receiver": per_receiver[1],
             "memcpy_peer_what": ("cudaMemcpyPeerAsync" if world > 1 else "cudaMemcpyAsync (same GPU)") + f" of {copy_bytes} contiguous bytes, timed in this run",
             "frac_of_memcpy_peer": gbs / copy_gbs, "frac_of_nvlink_900": (gbs / 900.0) if world > 1 else None}
 
