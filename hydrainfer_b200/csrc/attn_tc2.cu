@@ -165,17 +165,38 @@ __device__ __forceinline__ int p2_item_head(const P2Args& a, int k, P2Item& it) 
   return pair;
 }
 
+// The sequence metadata of an item as loaded; p2_item_loads issues the loads, p2_item_finish does the arithmetic, so that a role can
+// put its own work between the two (the softmax warps: their whole epilogue - the loads used to be consumed right behind the
+// wait for the last P.V, a global-load latency in front of the O read-out of every item).
+struct P2Raw {
+  int q0, q1, k0, k1, c0, c1;
+};
+
 template <bool VL = false>
-__device__ __forceinline__ void p2_item_body(const P2Args& a, int pair, P2Item& it) {
-  it.q_start = __ldg(a.q_cu + it.b);
-  it.q_len = __ldg(a.q_cu + it.b + 1) - it.q_start;
-  it.kv_len = __ldg(a.kv_cu + it.b + 1) - __ldg(a.kv_cu + it.b);
+__device__ __forceinline__ void p2_item_loads(const P2Args& a, const P2Item& it, P2Raw& w) {
+  w.q0 = __ldg(a.q_cu + it.b);
+  w.q1 = __ldg(a.q_cu + it.b + 1);
+  w.k0 = __ldg(a.kv_cu + it.b);
+  w.k1 = __ldg(a.kv_cu + it.b + 1);
   if constexpr (VL) {
-    it.blk0 = __ldg(a.kv_cu + it.b);  // first K/V row of the sequence
+    w.c0 = w.c1 = 0;
+  } else {
+    w.c0 = __ldg(a.cu_blocks + it.b);
+    w.c1 = __ldg(a.cu_blocks + it.b + 1);
+  }
+}
+
+template <bool VL = false>
+__device__ __forceinline__ void p2_item_finish(const P2Args& a, int pair, const P2Raw& w, P2Item& it) {
+  it.q_start = w.q0;
+  it.q_len = w.q1 - w.q0;
+  it.kv_len = w.k1 - w.k0;
+  if constexpr (VL) {
+    it.blk0 = w.k0;  // first K/V row of the sequence
     it.n_pages = (it.kv_len + a.block_size - 1) / a.block_size;
   } else {
-    it.blk0 = __ldg(a.cu_blocks + it.b);
-    it.n_pages = __ldg(a.cu_blocks + it.b + 1) - it.blk0;
+    it.blk0 = w.c0;
+    it.n_pages = w.c1 - w.c0;
   }
   const int pair_tokens = 2 * a.tq;
   if (pair < 0) pair += (it.q_len + pair_tokens - 1) / pair_tokens;  // n_pairs - 1 - slot
@@ -209,6 +230,13 @@ __device__ __forceinline__ void p2_item_body(const P2Args& a, int pair, P2Item& 
 }
 
 template <bool VL = false>
+__device__ __forceinline__ void p2_item_body(const P2Args& a, int pair, P2Item& it) {
+  P2Raw w;
+  p2_item_loads<VL>(a, it, w);
+  p2_item_finish<VL>(a, pair, w, it);
+}
+
+template <bool VL = false>
 __device__ __forceinline__ void p2_decode_item(const P2Args& a, int k, P2Item& it) {
   const int pair = p2_item_head(a, k, it);
   p2_item_body<VL>(a, pair, it);
@@ -235,7 +263,7 @@ __device__ __forceinline__ int p2_claim_item(const P2Args& a, int round, int lan
 // Timeline instrumentation (dev builds with -DHI_PAIR_TRACE, tools/pair_trace.py): CTA 0 records, per role, clock64 stamps
 // of its hand-off points.  Record = clock (40 bits) | tag << 40 | step << 44 | item << 56.
 #ifdef HI_PAIR_TRACE
-constexpr int kTraceRoles = 6, kTraceCap = 8192;
+constexpr int kTraceRoles = 12, kTraceCap = 4096;  // K TMA, V TMA, MMA 0 / 1, lane 0 of the 8 softmax warps
 static __device__ unsigned long long g_pair_trace[kTraceRoles * kTraceCap];
 static __device__ unsigned int g_pair_trace_n[kTraceRoles];
 // Per CTA (MMA warp of tile 0): {globaltimer at entry, globaltimer after the last item, items walked, 64-key steps walked}.
@@ -279,8 +307,8 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   const int lane = threadIdx.x & 31;
   const int pages_per_tile = kP2TileN / a.block_size;
 #ifdef HI_PAIR_TRACE
-  const int tr_role = (warp == 8) ? 0 : (warp == 11) ? 1 : (warp == 9) ? 2 : (warp == 10) ? 3 : (threadIdx.x == 0) ? 4 : (threadIdx.x == 128) ? 5 : -1;
-  const bool tr_on = blockIdx.x == 0 && tr_role >= 0 && (warp < 8 || lane == 0);
+  const int tr_role = (warp == 8) ? 0 : (warp == 11) ? 1 : (warp == 9) ? 2 : (warp == 10) ? 3 : 4 + warp;
+  const bool tr_on = blockIdx.x == 0 && lane == 0;
   unsigned int tr_n = 0;
   auto trace = [&](int tag, unsigned int item, int step) {
     if (tr_on && tr_n < kTraceCap)
@@ -500,10 +528,10 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       const unsigned long long cta_t0 = trace_globaltimer();
       unsigned int cta_items = 0;
 #endif
-      // The next item is decoded during the last two steps of the current one (plan entry at the top of step n-2, sequence
-      // metadata at the top of step n-1: both loads complete behind the waits for P), so Q.K(0) and Q.K(1) of the next item
-      // follow the last P.V without a decode in between.
+      // The next item is decoded during the last steps of the current one: plan entry at the top of step n-3, sequence metadata
+      // loads at the top of step n-2, the arithmetic behind the last P.V - so no load latency sits between a P and its P.V.
       P2Item nxt;
+      P2Raw raw_nxt;
       bool more_items = false;
       int pair_nxt = 0;
       {
@@ -553,12 +581,12 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
           const int s = static_cast<int>(v_stage(gj)), s2 = static_cast<int>(k_stage(gj + 2)), buf = (gs + u) & 1;
           const bool has_pv = owns(j);
           const bool more = j + 2 < n_all;
-          if (j == max(n_all - 2, 0)) {  // warp 8 published the next index when it finished this item's K loads, steps ago
+          if (j == max(n_all - 3, 0)) {  // warp 8 published the next index when it had issued this item's last K load: the K this step's Q.K(j + 2) needs
             const int k = next_item(n_it++, true);
             more_items = k < a.n_items;
             if (more_items) pair_nxt = p2_item_head(a, k, nxt);
           }
-          if (j == n_all - 1 && more_items) p2_item_body<VL>(a, pair_nxt, nxt);
+          if (j == max(n_all - 2, 0) && more_items) p2_item_loads<VL>(a, nxt, raw_nxt);  // consumed behind the last P.V (below the loop)
           ptx::mbar_wait(bar(L::bVFull + s), v_phase(gj));
           if (more) ptx::mbar_wait(bar(L::bKFull + s2), k_phase(gj + 2));
           if (has_pv) {
@@ -583,6 +611,9 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
           __syncwarp();
           trace(4, n_it, j);
         }
+        // (the arithmetic of the decode - a global-load latency when it sat at the top of the last step, in front of the P.V every
+        // softmax thread of the tile is waiting for - runs here, off the chain last P -> P.V -> O read-out)
+        if (more_items) p2_item_finish<VL>(a, pair_nxt, raw_nxt, nxt);
         g += n_all;
         gs += n_t;
         if (n_t > 0) ++n_act;
@@ -684,6 +715,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
             // quiescent: P_t.V(j-1) complete (implied by S_t(j+1), issued behind it; the last step has its own commit) and
             // P_t.V(j) not issued before this thread's P arrival below.
             // (interleaved items: Q.K(j) was issued right behind P.V(j - 1), so the S(j) this thread already waited for implies it)
+            trace(7, n_it, j);
             if (!il) {
               if (j + 1 < n_mine) ptx::mbar_wait(bar(L::bSFull + 2 * t + (buf ^ 1)), ((sj + 1) >> 1) & 1u);
               else ptx::mbar_wait(bar(L::bPvDone + t), n_pv2 & 1u);
@@ -734,8 +766,9 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         more = k < a.n_items;
         if (more) pair_nxt = p2_item_head(a, k, nxt);
       }
+      P2Raw raw_nxt;
+      if (more) p2_item_loads<VL>(a, nxt, raw_nxt);  // needs the plan entry: that latency and these loads' run behind the wait for the last P.V
       ptx::mbar_wait(bar(L::bOFull + t), n_act & 1u);
-      if (more) p2_item_body<VL>(a, pair_nxt, nxt);
       ptx::tc_fence_after_sync();
       trace(5, n_it, 0);
       // Interleaved decode item: tile 1 hands its (m, l, O) to tile 0 through shared memory (tile 1's staging buffer, rows of
@@ -771,6 +804,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
           ptx::named_bar_sync(3, 2 * kP2TileM);        // tile 1's state is in shared memory
           ptx::named_bar_sync(3, 2 * kP2TileM);        // tile 0 has read it
           trace(6, n_it, 0);
+          if (more) p2_item_finish<VL>(a, pair_nxt, raw_nxt, nxt);
           gs += n_mine;
           ++n_act;
           if (n_mine >= 2) ++n_pv2;
@@ -873,6 +907,7 @@ paged_attn_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         }
       }
       trace(6, n_it, 0);
+      if (more) p2_item_finish<VL>(a, pair_nxt, raw_nxt, nxt);  // the loads were issued before the epilogue
       gs += n_mine;
       ++n_act;
       if (n_mine >= 2) ++n_pv2;
@@ -1272,7 +1307,7 @@ extern "C" int hi_debug_mbar_timeout(unsigned int out[64]) {
 
 #ifdef HI_PAIR_TRACE
 // Dev builds only: copies the timeline CTA 0 recorded during the last pair-kernel launch (see tools/pair_trace.py).
-extern "C" int hi_debug_pair_trace(unsigned long long* records /* [6][8192] */, unsigned int* counts /* [6] */) {
+extern "C" int hi_debug_pair_trace(unsigned long long* records /* [kTraceRoles][kTraceCap] */, unsigned int* counts /* [kTraceRoles] */) {
   cudaDeviceSynchronize();
   if (cudaMemcpyFromSymbol(records, hi::g_pair_trace, sizeof(unsigned long long) * hi::kTraceRoles * hi::kTraceCap) != cudaSuccess) return -1;
   if (cudaMemcpyFromSymbol(counts, hi::g_pair_trace_n, sizeof(unsigned int) * hi::kTraceRoles) != cudaSuccess) return -1;

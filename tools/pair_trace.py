@@ -21,10 +21,13 @@ from hydrainfer_b200 import _lib  # noqa: E402
 from hydrainfer_b200._C.kernel.flash_attn import mha_varlen_fwd  # noqa: E402
 from hydrainfer_b200.workloads import make_batch  # noqa: E402
 
-ROLES = ["K-tma", "V-tma", "mma0", "mma1", "smx0", "smx1"]
+ROLES = ["K-tma", "V-tma", "mma0", "mma1"] + [f"smx{w >> 2}w{w & 3}" for w in range(8)]  # lane 0 of each softmax warp
+N_ROLES, CAP = 12, 4096
+SMX0, SMX1 = 4, 8  # first softmax warp of tile 0 / 1
+_SMX_TAGS = {1: "item", 3: "S", 4: "P", 5: "Ofull", 6: "epi-done", 7: "rescale"}
 TAGS = {0: {1: "item", 2: "Qempty", 3: "stage-free"}, 1: {1: "item", 3: "stage-free"},
         2: {1: "item", 2: "Qfull", 3: "ready", 4: "issued"}, 3: {1: "item", 2: "Qfull", 3: "ready", 4: "issued"},
-        4: {1: "item", 3: "S", 4: "P", 5: "Ofull", 6: "epi-done"}, 5: {1: "item", 3: "S", 4: "P", 5: "Ofull", 6: "epi-done"}}
+        **{4 + w: _SMX_TAGS for w in range(8)}}
 CASES = {
     "pre256": ([(256, 256)] * 32, 28, 4), "pre1k": ([(1024, 1024)] * 8, 28, 4), "pre4k": ([(4096, 4096)] * 2, 28, 4),
     "pre8k": ([(8192, 8192)], 28, 4), "cfg3p": ([(512, 512), (512, 2048), (512, 4096), (512, 8192)], 28, 4),
@@ -71,14 +74,14 @@ def main():
         print("latest CTAs (end us, items, steps, us per step):", [(round((r[1] - t_first) / 1e3, 1), r[2], r[3], round((r[1] - r[0]) / 1e3 / max(r[3], 1), 3)) for r in worst])
         best = sorted(rows, key=lambda r: r[1])[:5]
         print("earliest CTAs (end us, items, steps, us per step):", [(round((r[1] - t_first) / 1e3, 1), r[2], r[3], round((r[1] - r[0]) / 1e3 / max(r[3], 1), 3)) for r in best])
-    cap = 8192
-    rec = (ctypes.c_ulonglong * (6 * cap))()
-    cnt = (ctypes.c_uint * 6)()
+    cap = CAP
+    rec = (ctypes.c_ulonglong * (N_ROLES * cap))()
+    cnt = (ctypes.c_uint * N_ROLES)()
     fn = _lib.lib.hi_debug_pair_trace
     fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
     assert fn(ctypes.byref(rec), ctypes.byref(cnt)) == 0
     events = []  # (clock, role, tag, step, item)
-    for r in range(6):
+    for r in range(N_ROLES):
         for i in range(cnt[r]):
             v = rec[r * cap + i]
             events.append((v & 0xffffffffff, r, (v >> 40) & 15, (v >> 44) & 4095, (v >> 56) & 255))
@@ -96,7 +99,7 @@ def main():
     prev_last_issue = None
     for item in range(1, n_items + 1):
         m = sorted(by.get((2, item), []))
-        s = sorted(by.get((4, item), []))
+        s = sorted(by.get((SMX0, item), []))
         if not m:
             continue
         g = lambda evs, tag: [c for c, tg, _ in evs if tg == tag]
@@ -112,13 +115,23 @@ def main():
         print(line)
         if item >= args.items and not args.raw:
             pass
+    # skew between the four warps of a tile and between the tiles: when lane 0 of each softmax warp published P of step j
+    print("P arrival per softmax warp (cycles; tile 0 warps 0-3 | tile 1 warps 0-3)")
+    for item in range(1, min(n_items, args.items) + 1):
+        steps = sorted({st for w in range(8) for _, tg, st in by.get((4 + w, item), []) if tg == 4})
+        for st in steps:
+            cols = []
+            for w in range(8):
+                c = [c for c, tg, s_ in by.get((4 + w, item), []) if tg == 4 and s_ == st]
+                cols.append(f"{c[0]:7d}" if c else "      -")
+            print(f"  item {item:2d} step {st:3d}: " + " ".join(cols[:4]) + " | " + " ".join(cols[4:]))
     # steady-state per-step cost inside items vs item boundaries
     total_steps = sum(1 for c, r, tag, step, item in events if r == 2 and tag == 4)
     print(f"mma0 steps {total_steps}; cycles per step overall {(t_end - t0) / max(total_steps, 1):.0f} (tensor-pipe floor 2 tiles x 512 = 1024)")
     if args.raw:
         for c, r, tag, step, item in sorted(events)[: 400 * args.items]:
             if item <= args.items:
-                print(f"{c - t0:9d} {ROLES[r]:6s} item {item:3d} {TAGS[r].get(tag, tag):10s} {step}")
+                print(f"{c - t0:9d} {ROLES[r]:7s} item {item:3d} {TAGS[r].get(tag, tag):10s} {step}")
 
 
 if __name__ == "__main__":
