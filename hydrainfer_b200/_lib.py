@@ -17,6 +17,7 @@ LIB_PATH = _PKG / "lib" / "libhi_b200.so"
 
 HI_F32, HI_F16, HI_BF16 = 0, 1, 2
 HI_ATTN_AUTO, HI_ATTN_SIMT, HI_ATTN_TCGEN05, HI_ATTN_TCGEN05_DECODE, HI_ATTN_TCGEN05_PAIR = 0, 1, 2, 3, 4
+HI_ATTN_OPT_WINDOW, HI_ATTN_OPT_SOFTCAP, HI_ATTN_OPT_ALIBI = 1, 2, 4
 
 _DTYPES = {torch.float32: HI_F32, torch.float16: HI_F16, torch.bfloat16: HI_BF16}
 
@@ -33,6 +34,8 @@ class HiAttnArgs(Structure):
         ("workspace", c_void_p), ("workspace_bytes", c_int64),
         ("path", c_int32), ("device", c_int32), ("kv_blocks_hint", c_int32), ("reserved", c_int32 * 3),
         ("work_items", c_void_p), ("qk_work_hint", c_int64), ("n_work_items", c_int32), ("work_tile_tokens", c_int32),
+        ("options", c_int32), ("window_left", c_int32), ("window_right", c_int32), ("softcap", c_float),
+        ("alibi_slopes", c_void_p), ("alibi_batch_stride", c_int64),
     ]
 
 

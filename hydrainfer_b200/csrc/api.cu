@@ -6,7 +6,7 @@
 
 #include "common.cuh"
 
-static_assert(sizeof(HiAttnArgs) == 192, "HiAttnArgs layout is part of the ABI (ctypes mirror in hydrainfer_b200/_lib.py)");
+static_assert(sizeof(HiAttnArgs) == 224, "HiAttnArgs layout is part of the ABI (ctypes mirror in hydrainfer_b200/_lib.py)");
 static_assert(sizeof(HiPoolGeom) == 32, "HiPoolGeom layout is part of the ABI");
 static_assert(sizeof(HiRopeArgs) == 144, "HiRopeArgs layout is part of the ABI");
 static_assert(sizeof(HiVarlenArgs) == 160, "HiVarlenArgs layout is part of the ABI");
@@ -127,6 +127,15 @@ extern "C" int hi_paged_attention(const HiAttnArgs* p, void* stream_) {
     if (env[0] == 't') path = HI_ATTN_TCGEN05;
     if (env[0] == 'd') path = HI_ATTN_TCGEN05_DECODE;
     if (env[0] == 'p') path = HI_ATTN_TCGEN05_PAIR;
+  }
+  if (a.options != 0) {
+    // mha_varlen_fwd's score options run on the any-shape CUDA-core kernel only (the paged attention layer never passes them)
+    HI_CHECK_ARG((a.options & ~(HI_ATTN_OPT_WINDOW | HI_ATTN_OPT_SOFTCAP | HI_ATTN_OPT_ALIBI)) == 0, "paged_attention: unknown option bits 0x%x", a.options);
+    HI_CHECK_ARG(!(a.options & HI_ATTN_OPT_SOFTCAP) || a.softcap > 0.f, "paged_attention: softcap must be positive, got %f", static_cast<double>(a.softcap));
+    HI_CHECK_ARG(!(a.options & HI_ATTN_OPT_ALIBI) || a.alibi_slopes != nullptr, "paged_attention: HI_ATTN_OPT_ALIBI without alibi_slopes");
+    HI_CHECK_SUPPORTED(path == HI_ATTN_AUTO || path == HI_ATTN_SIMT,
+                       "paged_attention: softcap / sliding window / alibi run on the CUDA-core path only (path %d requested)", path);
+    path = HI_ATTN_SIMT;
   }
   if (path == HI_ATTN_AUTO) {
     // Rows with q_len > 1 are dense contractions: tensor pipe.  Pure decode batches stream KV once per row: the

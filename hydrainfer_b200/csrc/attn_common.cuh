@@ -29,6 +29,14 @@ struct SimtArgs {
   // LAST row needs a single chunk straight to `out` (normalised); the merge leaves those rows alone.
   int direct_tile_tokens;
   int direct_tiles;  // ... with at most this many 16-token tiles of visible keys (0: chunk_tiles, i.e. "fits the first chunk")
+  // mha_varlen_fwd's score options (flash_api.cpp:93-111, src/mask.h:54-62, 158-195, flash_fwd_kernel.h:244-245, 283); read by the
+  // OPT instances of paged_attn_simt_kernel only
+  float softcap_log2;      // softcap * log2(e); 0 = off.  score = softcap * tanh(q.k * scale / softcap)
+  float inv_softcap_log2;  // 1 / softcap_log2
+  int window_left;         // keys below i_abs - window_left are masked; < 0 = unlimited
+  int window_right;        // keys above i_abs + window_right are masked; < 0 = unlimited (0 = causal)
+  const float* alibi_slopes;     // [n_qo_heads] or [n_seqs][n_qo_heads] fp32, NULL = off.  score -= slope * |i_abs - j|
+  int64_t alibi_batch_stride;    // 0 for the per-head form
 };
 
 // One merged row = LSE-weighted sum of its valid chunks; chunk c covers 16-token tiles [c*chunk_tiles, (c+1)*chunk_tiles).

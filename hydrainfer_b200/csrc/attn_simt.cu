@@ -158,7 +158,11 @@ __device__ __forceinline__ void zero_row_heads(const SimtArgs& a, int t, int fir
   for (int i = threadIdx.x; i < n_elems; i += blockDim.x) orow[i] = Elem<T>::from_f32(0.f);
 }
 
-template <typename T, int D, int G>
+// OPT: the instance behind mha_varlen_fwd's softcap / sliding-window / alibi arguments (the reference's FlashAttention-2 build has all
+// three enabled, flash_api.cpp:93-111, 197-213): scores become softcap * tanh(q.k * scale / softcap), minus slope_h * |i_abs - j|,
+// restricted to keys i_abs - window_left <= j <= i_abs + window_right, where i_abs = i + kv_len - q_len is the query's position in key
+// coordinates (src/mask.h:54-62, 173-195).  Unsplit (one chunk), one head per CTA.
+template <typename T, int D, int G, bool OPT = false>
 __global__ void __launch_bounds__(kSimtThreads) paged_attn_simt_kernel(const SimtArgs a) {
   constexpr int E = D / 16;                                        // head dims per lane
   constexpr int W = LaneRow<T, E>::W;                              // 32-bit words per lane per row
@@ -175,10 +179,16 @@ __global__ void __launch_bounds__(kSimtThreads) paged_attn_simt_kernel(const Sim
   const int q_start = __ldg(a.q_cu + b);
   const int q_len = __ldg(a.q_cu + b + 1) - q_start;
   const int kv_len = __ldg(a.kv_cu + b + 1) - __ldg(a.kv_cu + b);
-  const int vis = kv_len - q_len + (t - q_start) + 1;  // keys 0 .. vis-1 are visible to this row
+  const int i_abs = kv_len - q_len + (t - q_start);  // the row's position in key coordinates
+  int vis = i_abs + 1;                               // keys 0 .. vis-1 are visible to this row
+  int first_key = 0;
+  if constexpr (OPT) {
+    vis = a.window_right < 0 ? kv_len : min(kv_len, i_abs + 1 + a.window_right);
+    first_key = a.window_left < 0 ? 0 : max(0, i_abs - a.window_left);
+  }
   const int tiles_total = (vis + 15) >> 4;
-  const int tile_begin = chunk * a.chunk_tiles;
-  if (vis <= 0) {  // no visible key (kv_len < q_len: malformed metadata): a defined result instead of whatever `out` held
+  const int tile_begin = OPT ? (first_key >> 4) : chunk * a.chunk_tiles;
+  if (vis <= first_key) {  // no visible key (kv_len < q_len: malformed metadata; or an empty window): a defined result instead of whatever `out` held
     if (chunk == 0) zero_row_heads<T>(a, t, qh0 * D, G * D);
     return;
   }
@@ -222,7 +232,7 @@ __global__ void __launch_bounds__(kSimtThreads) paged_attn_simt_kernel(const Sim
   for (int it = 0; it < n_iters; ++it) {
     const int tile = tile_begin + it * kHalfWarps + hw;
     const int pos = tile * 16 + l16;
-    const bool valid = (tile < tile_end) && (pos < vis);
+    const bool valid = (tile < tile_end) && (pos < vis) && (!OPT || pos >= first_key);
     // Physical slot of this lane's token (block_table[pos / bs] * bs + pos % bs, token_cache_manger.py:126-133).
     int slot = -1;
     if (valid) {
@@ -259,7 +269,17 @@ __global__ void __launch_bounds__(kSimtThreads) paged_attn_simt_kernel(const Sim
 #pragma unroll
     for (int g = 0; g < G; ++g) {
       transpose_reduce16<16>(acc[g], l16);
-      const float s = valid ? acc[g][0] : -INFINITY;
+      float sc = acc[g][0];
+      if constexpr (OPT) {  // scores are in the exp2 domain (q was pre-multiplied by scale * log2 e)
+        if (a.softcap_log2 > 0.f) {
+          float th;
+          asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(sc * a.inv_softcap_log2));
+          sc = a.softcap_log2 * th;
+        }
+        if (a.alibi_slopes != nullptr)
+          sc -= __ldg(a.alibi_slopes + b * a.alibi_batch_stride + qh0 + g) * 1.4426950408889634f * fabsf(static_cast<float>(i_abs - pos));
+      }
+      const float s = valid ? sc : -INFINITY;
       float mx = s;
 #pragma unroll
       for (int off = 8; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, off));
@@ -627,7 +647,23 @@ static int pick_group(int group, int max_g) {
 }
 
 template <typename T, int D>
+static int launch_simt_opt(SimtArgs& a, cudaStream_t stream) {
+  // score options: one chunk (a window's first tiles are skipped inside the kernel, so the chunk bookkeeping of the merge does not apply),
+  // one head per CTA
+  a.n_chunks = 1;
+  a.chunk_tiles = 1 << 28;
+  const dim3 grid(a.n_tokens, a.n_qo_heads, 1);
+  timing_mark_start(stream);
+  HI_CUDA(launch_pdl(paged_attn_simt_kernel<T, D, 1, true>, grid, dim3(kSimtThreads), 0, stream, a));
+  timing_mark_stop(stream);
+  note_launch();
+  HI_CUDA(cudaGetLastError());
+  return HI_OK;
+}
+
+template <typename T, int D>
 static int launch_simt_td(SimtArgs& a, const HiAttnArgs& args, cudaStream_t stream) {
+  if (args.options != 0) return launch_simt_opt<T, D>(a, stream);
   // fp32 is the reference-parity path only: one head per CTA keeps it within the register budget.
   const int G = pick_group(a.group, sizeof(T) == 4 ? 1 : 4);
   const int64_t ctas_per_chunk = static_cast<int64_t>(a.n_tokens) * a.n_kv_heads * (a.group / G);
@@ -697,6 +733,20 @@ int launch_attn_simt(const HiAttnArgs& args, cudaStream_t stream) {
   a.group = args.n_qo_heads / args.n_kv_heads;
   a.block_size = args.block_size;
   a.scale_log2 = args.softmax_scale * 1.4426950408889634f;
+  a.window_left = -1;
+  a.window_right = 0;
+  if (args.options & HI_ATTN_OPT_WINDOW) {
+    a.window_left = args.window_left;
+    a.window_right = args.window_right;
+  }
+  if ((args.options & HI_ATTN_OPT_SOFTCAP) && args.softcap > 0.f) {
+    a.softcap_log2 = args.softcap * 1.4426950408889634f;
+    a.inv_softcap_log2 = 1.f / a.softcap_log2;
+  }
+  if ((args.options & HI_ATTN_OPT_ALIBI) && args.alibi_slopes != nullptr) {
+    a.alibi_slopes = args.alibi_slopes;
+    a.alibi_batch_stride = args.alibi_batch_stride;
+  }
   switch (args.dtype) {
     case HI_F32: return launch_simt_t<float>(a, args, stream);
     case HI_F16: return launch_simt_t<__half>(a, args, stream);

@@ -259,9 +259,16 @@ void varlen_fwd(Tensor& out, const Tensor& q, const Tensor& k, const Tensor& v, 
   check(hi_varlen_attention(&a, stream));
 }
 
+// mha_varlen_fwd's score options (flash_api.cpp:225-232); the default is what the paged attention layer passes: causal, nothing else
+struct ScoreOptions {
+  const Tensor* alibi_slopes = nullptr;
+  double softcap = 0.0;
+  int64_t window_left = -1, window_right = 0;
+};
+
 void paged_fwd(int dev, Tensor& out, const Tensor& q, const Tensor& k, const Tensor& v, const Tensor& cu_q, const Tensor& cu_k, const Tensor& block_table,
                const Tensor& cu_block_lens, int64_t max_q, int64_t max_k, double scale, int64_t path, const std::optional<Tensor>& work_items,
-               int64_t work_tile_tokens, int64_t qk_work_hint) {
+               int64_t work_tile_tokens, int64_t qk_work_hint, const ScoreOptions& opt = ScoreOptions()) {
   if (q.dim() != 3 || out.sizes() != q.sizes() || !heads_contiguous(q) || !heads_contiguous(out))
     fail("mha_varlen_fwd: q and out must be [n_tokens, n_heads, head_dim], contiguous over the last two dims");
   if (k.dim() != 4 || k.sizes() != v.sizes() || !k.is_contiguous() || !v.is_contiguous())
@@ -316,6 +323,27 @@ void paged_fwd(int dev, Tensor& out, const Tensor& q, const Tensor& k, const Ten
   }
   a.qk_work_hint = qk_work_hint;
   a.work_tile_tokens = static_cast<int32_t>(work_tile_tokens);
+  if (!(opt.window_left < 0 && opt.window_right == 0)) {  // anything but plain causal (flash_api.cpp:104-111)
+    a.options |= HI_ATTN_OPT_WINDOW;
+    a.window_left = static_cast<int32_t>(opt.window_left < 0 ? -1 : opt.window_left);
+    a.window_right = static_cast<int32_t>(opt.window_right < 0 ? -1 : opt.window_right);
+  }
+  if (opt.softcap > 0.0) {
+    a.options |= HI_ATTN_OPT_SOFTCAP;
+    a.softcap = static_cast<float>(opt.softcap);
+  }
+  if (opt.alibi_slopes != nullptr) {  // flash_api.cpp:202-209
+    const Tensor& al = *opt.alibi_slopes;
+    if (al.scalar_type() != at::kFloat) fail("mha_varlen_fwd: ALiBi slopes must have dtype fp32");
+    if (!al.is_cuda() || al.get_device() != dev) fail("mha_varlen_fwd: alibi_slopes must be on the device of q");
+    if (al.stride(-1) != 1) fail("mha_varlen_fwd: ALiBi slopes tensor must have contiguous last dimension");
+    const bool per_head = al.dim() == 1 && al.size(0) == n_qo_heads;
+    const bool per_seq = al.dim() == 2 && al.size(0) == n_seqs && al.size(1) == n_qo_heads;
+    if (!per_head && !per_seq) fail("mha_varlen_fwd: alibi_slopes must be [num_heads] or [batch_size, num_heads]");
+    a.options |= HI_ATTN_OPT_ALIBI;
+    a.alibi_slopes = al.data_ptr<float>();
+    a.alibi_batch_stride = per_seq ? al.stride(0) : 0;
+  }
   check(hi_paged_attention(&a, stream));
 }
 
@@ -323,7 +351,7 @@ void paged_fwd(int dev, Tensor& out, const Tensor& q, const Tensor& k, const Ten
 // `work_tile_tokens` and `qk_work_hint` are optional extensions after them (the host plan of AttentionParametersBuilder).
 // Paged form (block_table + cu_block_lens, window (-1, 0) == causal: causal_attention.py:274-291) and un-paged form
 // (block_table None, k / v [T, Hkv, d], window (-1, -1) or (-1, 0): multihead_attention.py:140-157, 194-211).  alibi, softcap and
-// sliding windows raise like TORCH_CHECK.
+// sliding windows are taken by the paged form (any-shape kernel); the un-paged form raises for them like TORCH_CHECK.
 void mha_varlen_fwd(Tensor& out, const Tensor& q, const Tensor& k, const Tensor& v, const Tensor& cu_seqlens_q, const Tensor& cu_seqlens_k,
                     const std::optional<Tensor>& block_table, const std::optional<Tensor>& cu_block_lens, const std::optional<Tensor>& alibi_slopes,
                     int64_t max_seqlen_q, int64_t max_seqlen_k, double softmax_scale, double softcap, int64_t window_size_left, int64_t window_size_right,
@@ -336,11 +364,17 @@ void mha_varlen_fwd(Tensor& out, const Tensor& q, const Tensor& k, const Tensor&
     return;
   }
   if (!cu_block_lens.has_value()) fail("mha_varlen_fwd: a block_table needs cu_block_lens (flattened CSR block table)");
-  if (alibi_slopes.has_value() || softcap != 0 || window_size_left != -1 || window_size_right != 0)
-    fail("mha_varlen_fwd: alibi / softcap / sliding window are not used by the paged attention layer and are not implemented");
+  // alibi / softcap / local windows: never passed by the paged attention layer (causal_attention.py:274-291), part of the entry point all
+  // the same (the reference's FlashAttention-2 build has them enabled); they run on the any-shape CUDA-core kernel
+  ScoreOptions opt;
+  if (alibi_slopes.has_value()) opt.alibi_slopes = &*alibi_slopes;
+  if (softcap < 0) fail("mha_varlen_fwd: softcap must be non-negative");
+  opt.softcap = softcap;
+  opt.window_left = window_size_left;
+  opt.window_right = window_size_right;
   const int dev = require_cuda({&out, &q, &k, &v, &cu_seqlens_q, &cu_seqlens_k, &*block_table, &*cu_block_lens});
   paged_fwd(dev, out, q, k, v, cu_seqlens_q, cu_seqlens_k, *block_table, *cu_block_lens, max_seqlen_q, max_seqlen_k, softmax_scale, path, work_items,
-            work_tile_tokens, qk_work_hint);
+            work_tile_tokens, qk_work_hint, opt);
 }
 
 // CausalGroupedQueryPageAttention.forward in one call (causal_attention.py:394-406): append the new K / V rows to the paged cache,

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HI_B200_ABI_VERSION 5
+#define HI_B200_ABI_VERSION 6
 
 typedef enum HiStatus {
   HI_OK = 0,
@@ -178,7 +178,23 @@ typedef struct HiAttnArgs {
                                 L_b - q_b + min(q_b, (tile + 1) * tile_tokens); 0 = unknown */
   int32_t n_work_items;
   int32_t work_tile_tokens;  /* tile size the plan was built for; the plan is ignored if it does not match the kernel's */
+  /* ABI 6: the score options of mha_varlen_fwd (flash_api.cpp:225-232; the reference's FlashAttention-2 build has alibi, local
+   * windows and softcap enabled, :93-111, :197-213).  The paged attention layer never passes them (causal_attention.py:274-291),
+   * so they run on the any-shape CUDA-core kernel (head_dim 64 / 128 / 256, unsplit), not on the tcgen05 kernels.
+   * With i_abs = i + kv_len - q_len (the query's position in key coordinates, src/mask.h:54-55):
+   *   HI_ATTN_OPT_WINDOW   key j is visible iff i_abs - window_left <= j <= i_abs + window_right, a negative bound = unlimited
+   *                        (the default without the flag is window_left = -1, window_right = 0: causal)
+   *   HI_ATTN_OPT_SOFTCAP  score = softcap * tanh(q.k * softmax_scale / softcap)                        (softcap > 0)
+   *   HI_ATTN_OPT_ALIBI    score -= alibi_slopes[b * alibi_batch_stride + h] * |i_abs - j|, applied after the softcap
+   * A row without a visible key gets zeros. */
+  int32_t options;           /* HiAttnOptions bit mask; 0 = plain causal attention */
+  int32_t window_left, window_right;
+  float softcap;
+  const float* alibi_slopes; /* [dev] fp32, [n_qo_heads] (alibi_batch_stride 0) or [n_seqs, n_qo_heads] */
+  int64_t alibi_batch_stride;
 } HiAttnArgs;
+
+typedef enum HiAttnOptions { HI_ATTN_OPT_WINDOW = 1, HI_ATTN_OPT_SOFTCAP = 2, HI_ATTN_OPT_ALIBI = 4 } HiAttnOptions;
 
 /* Upper bound of the scratch hi_paged_attention needs for a batch with these extents (split-KV partials). */
 int64_t hi_attention_workspace_bytes(int32_t n_tokens, int32_t n_qo_heads, int32_t head_dim, int32_t max_kv_len);

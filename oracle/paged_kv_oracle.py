@@ -196,6 +196,57 @@ def paged_attention_fp32(query: Tensor, key_cache: Tensor, value_cache: Tensor, 
     return torch.cat(outputs, dim=0).reshape(-1, n_qo_heads * head_dim)
 
 
+def paged_attention_options_fp32(query: Tensor, key_cache: Tensor, value_cache: Tensor, q_cu_seq_lens, kv_cu_seq_lens,
+                                 block_tables: Tensor, cu_blocks_lens, n_qo_heads: int, n_kv_heads: int, head_dim: int,
+                                 softmax_scale: float, softcap: float = 0.0, window_size_left: int = -1, window_size_right: int = 0,
+                                 alibi_slopes: Tensor | None = None) -> Tensor:
+    """fp32 result of the reference's fused backend `mha_varlen_fwd` (paged form) WITH its score options - what no Python handler of the
+    reference computes, restated from its vendored FlashAttention-2 (csrc/kernel/flash_attn):
+
+      * softcap > 0: the kernel turns q.k into tanh(q.k * softmax_scale / softcap) (flash_api.cpp:93-96 sets params.softcap =
+        softmax_scale / softcap, src/flash_fwd_kernel.h:282-284 applies it) and then scales by softcap instead of softmax_scale
+        (flash_api.cpp:95-96), i.e. score = softcap * tanh(q.k * softmax_scale / softcap);
+      * alibi: score -= slope[b, h] * |i_abs - j| with i_abs = i + kv_len - q_len (src/mask.h:183-186; the slope is divided by the
+        softmax scale there because it is added before the scaling, flash_fwd_kernel.h:244), after the softcap (:283-288);
+      * windows: key j is visible iff i_abs - window_left <= j <= i_abs + window_right (src/mask.h:54-62 with the ACTUAL sequence
+        lengths, flash_fwd_kernel.h:245); a negative bound means unlimited (flash_api.cpp:104-111: (-1, 0) is causal, (-1, -1) no
+        mask).  A row without a visible key yields zeros.
+
+    PARITY: pinned on the GPU against the reference's compiled FlashAttention-2 (oracle/_ref, tests/test_gpu_reference_native.py)."""
+    q_cu = [int(x) for x in q_cu_seq_lens]
+    kv_cu = [int(x) for x in kv_cu_seq_lens]
+    cu_blocks = [int(x) for x in cu_blocks_lens]
+    block_tables = block_tables.long()
+    group = n_qo_heads // n_kv_heads
+    outputs = []
+    for b in range(len(q_cu) - 1):
+        table = block_tables[cu_blocks[b]: cu_blocks[b + 1]]
+        kv_len = kv_cu[b + 1] - kv_cu[b]
+        k = key_cache[table].reshape(-1, n_kv_heads, head_dim)[:kv_len].to(torch.float).repeat_interleave(repeats=group, dim=1)
+        v = value_cache[table].reshape(-1, n_kv_heads, head_dim)[:kv_len].to(torch.float).repeat_interleave(repeats=group, dim=1)
+        q = query[q_cu[b]: q_cu[b + 1]].to(torch.float)
+        q_len = q.shape[0]
+        scores = torch.einsum("qhd,khd->hqk", q, k) * softmax_scale
+        if softcap > 0:
+            scores = softcap * torch.tanh(scores / softcap)
+        j = torch.arange(kv_len)[None, None, :]
+        i_abs = torch.arange(q_len)[None, :, None] + (kv_len - q_len)
+        if alibi_slopes is not None:
+            slopes = alibi_slopes.to(torch.float).cpu()
+            slopes = slopes[b] if slopes.dim() == 2 else slopes
+            scores = scores - slopes[:, None, None] * (i_abs - j).abs().to(torch.float)
+        hidden = torch.zeros_like(scores, dtype=torch.bool)
+        if window_size_right >= 0:
+            hidden |= j > i_abs + window_size_right
+        if window_size_left >= 0:
+            hidden |= j < i_abs - window_size_left
+        scores = scores.masked_fill(hidden, float("-inf"))
+        probs = torch.softmax(scores, dim=-1)
+        probs = torch.where(hidden.all(dim=-1, keepdim=True), torch.zeros_like(probs), probs)  # rows without a visible key
+        outputs.append(torch.einsum("hqk,khd->qhd", probs, v))
+    return torch.cat(outputs, dim=0).reshape(-1, n_qo_heads * head_dim)
+
+
 def paged_attention(query: Tensor, key_cache: Tensor, value_cache: Tensor, q_cu_seq_lens, kv_cu_seq_lens,
                     block_tables: Tensor, cu_blocks_lens, n_qo_heads: int, n_kv_heads: int, head_dim: int) -> Tensor:
     """The handler's return value: the fp32 result rounded to the query dtype (causal_attention.py:370-372)."""

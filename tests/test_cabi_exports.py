@@ -30,13 +30,13 @@ def test_binding_table_matches_header():
 
 
 def test_abi_version_and_error_string():
-    assert _lib.lib.hi_abi_version() == 5
+    assert _lib.lib.hi_abi_version() == 6
     assert isinstance(_lib.lib.hi_last_error(), bytes)
 
 
 def test_struct_layout_matches_header():
     # HiAttnArgs: 4 ptrs + 2 i64 + 4 ptrs + 8 i32 + i64 + i32 + f32 + ptr + i64 + 2 i32 + 4 i32 (natural alignment, no packing)
-    assert ctypes.sizeof(_lib.HiAttnArgs) == 4 * 8 + 2 * 8 + 4 * 8 + 8 * 4 + 8 + 4 + 4 + 8 + 8 + 2 * 4 + 4 * 4 + 8 + 8 + 4 + 4
+    assert ctypes.sizeof(_lib.HiAttnArgs) == 4 * 8 + 2 * 8 + 4 * 8 + 8 * 4 + 8 + 4 + 4 + 8 + 8 + 2 * 4 + 4 * 4 + 8 + 8 + 4 + 4 + 4 * 4 + 8 + 8 == 224
     assert ctypes.sizeof(_lib.HiPoolGeom) == 32
     # HiRopeArgs: 3 ptrs + 3 i64 + 5 ptrs + i64 + 12 i32
     assert ctypes.sizeof(_lib.HiRopeArgs) == 3 * 8 + 3 * 8 + 5 * 8 + 8 + 12 * 4
@@ -85,7 +85,8 @@ def test_compiled_modules_export_the_reference_init_symbols():
 
 def test_mha_varlen_fwd_keeps_the_reference_positional_signature():
     """16 positional arguments (hydrainfer/_C/kernel/flash_attn/__init__.pyi:22-40); a call with 15 is a TypeError, CPU tensors
-    a RuntimeError (no CPU fallback), alibi / softcap / windows a RuntimeError like TORCH_CHECK."""
+    a RuntimeError (no CPU fallback), a negative softcap a RuntimeError like TORCH_CHECK (softcap / windows / alibi themselves are
+    accepted by the paged form: tests/test_gpu_attention.py::test_score_options_match_oracle)."""
     import pytest
     import torch
 
@@ -100,7 +101,7 @@ def test_mha_varlen_fwd_keeps_the_reference_positional_signature():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         mha_varlen_fwd(q, q, kc, kc, cu, cu, bt, cub, None, 2, 2, 0.1, 0, -1, 0, 0)
     with pytest.raises(RuntimeError, match="softcap"):
-        mha_varlen_fwd(q, q, kc, kc, cu, cu, bt, cub, None, 2, 2, 0.1, 30.0, -1, 0, 0)
+        mha_varlen_fwd(q, q, kc, kc, cu, cu, bt, cub, None, 2, 2, 0.1, -30.0, -1, 0, 0)
     with pytest.raises(RuntimeError, match="cu_block_lens"):
         mha_varlen_fwd(q, q, kc, kc, cu, cu, bt, None, None, 2, 2, 0.1, 0, -1, 0, 0)
 

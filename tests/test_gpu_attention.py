@@ -405,9 +405,18 @@ def test_unsupported_arguments_raise():
     bad = list(args); bad[7] = None
     with pytest.raises(RuntimeError, match="cu_block_lens"):
         mha_varlen_fwd(*bad)
-    bad = list(args); bad[12] = 30.0
+    bad = list(args); bad[12] = -30.0
     with pytest.raises(RuntimeError, match="softcap"):
         mha_varlen_fwd(*bad)
+    bad = list(args); bad[8] = torch.ones(4, dtype=torch.float16, device=DEV)  # flash_api.cpp:204
+    with pytest.raises(RuntimeError, match="fp32"):
+        mha_varlen_fwd(*bad)
+    bad = list(args); bad[8] = torch.ones(3, dtype=torch.float32, device=DEV)  # flash_api.cpp:207
+    with pytest.raises(RuntimeError, match="num_heads"):
+        mha_varlen_fwd(*bad)
+    # the score options run on the CUDA-core path: asking for a tcgen05 path with them is an error, not a silent switch
+    with pytest.raises(RuntimeError, match="CUDA-core"):
+        mha_varlen_fwd(*args[:12], 30.0, -1, 0, 0, 4)
     bad = list(args); bad[4] = i32([0, 1]).long()
     with pytest.raises(RuntimeError, match="int32"):
         mha_varlen_fwd(*bad)
@@ -467,3 +476,59 @@ def test_tcgen05_prefill_for_head_dim_256(dtype):
         check_batch(batch, [TC, 0], f"head_dim 256 heads {heads}")
     batch = make_batch([(200, 3000)], 4, 2, 256, 16, dtype=dtype, seed=72)  # 2 tiles x 2 heads: split-KV
     check_batch(batch, [TC], "head_dim 256 split")
+
+
+# ---- mha_varlen_fwd's score options: softcap, sliding window, alibi (flash_api.cpp:93-111, 197-213; src/mask.h) ---------------------
+OPTION_CASES = [
+    # (softcap, window_left, window_right, alibi: None | "head" | "batch")
+    (30.0, -1, 0, None), (0.0, 48, 0, None), (0.0, 0, 0, None), (0.0, -1, -1, None), (0.0, 32, 16, None), (0.0, -1, 7, None),
+    (0.0, -1, 0, "head"), (0.0, -1, -1, "batch"), (20.0, 64, 0, "head"), (5.0, 17, 3, "batch"),
+]
+
+
+@pytest.mark.parametrize("case", OPTION_CASES, ids=lambda c: f"cap{c[0]}_w{c[1]}_{c[2]}_alibi{c[3]}")
+@pytest.mark.parametrize("geom", [(torch.bfloat16, 8, 2, 128, 16), (torch.float16, 4, 4, 64, 16), (torch.bfloat16, 2, 1, 256, 32), (torch.float32, 4, 2, 128, 16)],
+                         ids=["bf16_gqa_d128", "f16_mha_d64", "bf16_gqa_d256_bs32", "f32_d128"])
+def test_score_options_match_oracle(geom, case):
+    from hydrainfer_b200._C.kernel.flash_attn import mha_varlen_fwd
+    dtype, hq, hkv, d, bs = geom
+    softcap, wl, wr, alibi = case
+    seq_lens = [(1, 300), (37, 37), (5, 130), (64, 200), (1, 1), (9, 9)]  # decode rows, prefills, chunked prefills, one-token sequences
+    batch = make_batch(seq_lens, hq, hkv, d, bs, dtype=dtype, device=DEV, seed=3)
+    t = batch.n_tokens
+    q3 = batch.query.view(t, hq, d)
+    out = torch.full_like(q3, float("nan"))
+    i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=DEV)
+    slopes = None
+    if alibi == "head":
+        slopes = (2.0 ** -torch.arange(1, hq + 1, dtype=torch.float32)).to(DEV)
+    elif alibi == "batch":
+        slopes = (torch.rand(len(seq_lens), hq, generator=torch.Generator().manual_seed(5)) * 0.2).to(DEV)
+    scale = 1.0 / math.sqrt(d)
+    mha_varlen_fwd(out, q3, batch.key_cache, batch.value_cache, i32(batch.q_cu_seq_lens), i32(batch.kv_cu_seq_lens), i32(batch.block_tables),
+                   i32(batch.cu_blocks_lens), slopes, batch.q_max, batch.kv_max, scale, softcap, wl, wr, 0)
+    ref = oracle.paged_attention_options_fp32(q3.cpu(), batch.key_cache.cpu(), batch.value_cache.cpu(), batch.q_cu_seq_lens, batch.kv_cu_seq_lens,
+                                              torch.tensor(batch.block_tables), batch.cu_blocks_lens, hq, hkv, d, scale, softcap, wl, wr,
+                                              None if slopes is None else slopes.cpu())
+    got = out.float().cpu().reshape(t, hq * d)
+    assert torch.isfinite(got).all()
+    atol, rtol = (1e-4, 1e-3) if dtype == torch.float32 else (2e-2, 1e-2)  # fp32: tanh.approx carries ~2^-11 relative error
+    if dtype == torch.float32 and softcap > 0:
+        atol = 2e-3
+    err = (got - ref).abs()
+    assert bool((err <= atol + rtol * ref.abs()).all()), float(err.max())
+
+
+def test_score_options_default_equals_plain_causal():
+    """window (-1, 0), softcap 0, no alibi through the option-taking entry == the ordinary launch, bit for bit (same kernel path forced)."""
+    from hydrainfer_b200._C.kernel.flash_attn import mha_varlen_fwd
+    batch = make_batch([(1, 200), (20, 50)], 8, 2, 128, 16, dtype=torch.bfloat16, device=DEV, seed=4)
+    t = batch.n_tokens
+    q3 = batch.query.view(t, 8, 128)
+    i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=DEV)
+    meta = (i32(batch.q_cu_seq_lens), i32(batch.kv_cu_seq_lens), i32(batch.block_tables), i32(batch.cu_blocks_lens))
+    a, b = torch.empty_like(q3), torch.empty_like(q3)
+    mha_varlen_fwd(a, q3, batch.key_cache, batch.value_cache, *meta, None, batch.q_max, batch.kv_max, 0.088, 0.0, -1, 0, 0, 1)
+    # a window wider than any sequence masks nothing beyond causal: the option instance must agree with the plain one within rounding
+    mha_varlen_fwd(b, q3, batch.key_cache, batch.value_cache, *meta, None, batch.q_max, batch.kv_max, 0.088, 0.0, 100000, 0, 0)
+    assert torch.allclose(a.float(), b.float(), atol=1e-2, rtol=1e-2)

@@ -303,3 +303,36 @@ def _oracle_pin_child(handle, shape, nb_src, nb_dst, src_bt, dst_bt, out):
     ref_bm.migrate_blocks(src_bt, dst_bt, handle, dst, nb_src)
     torch.cuda.synchronize()
     torch.save(dst.cpu(), out)
+
+
+# ---- mha_varlen_fwd with its score options: ours against the reference's compiled FlashAttention-2 -----------------------------------
+@pytest.mark.parametrize("case", [
+    # (softcap, window_left, window_right, alibi)
+    (0.0, -1, 0, False), (30.0, -1, 0, False), (0.0, 48, 0, False), (0.0, 32, 16, False), (0.0, -1, -1, False), (0.0, -1, 0, True), (20.0, 64, 0, True),
+], ids=lambda c: f"cap{c[0]}_w{c[1]}_{c[2]}_alibi{int(c[3])}")
+@pytest.mark.parametrize("geom", [(torch.bfloat16, 8, 2, 128), (torch.float16, 4, 4, 64), (torch.bfloat16, 4, 1, 256)], ids=["bf16_d128", "f16_d64", "bf16_d256"])
+def test_paged_mha_varlen_fwd_options_match_reference_fa2(geom, case):
+    """The reference's own `mha_varlen_fwd` (csrc/kernel/flash_attn/flash_api.cpp:216-355, compiled unmodified with its vendored
+    FlashAttention-2) and ours on the same paged inputs, including the options the paged layer never passes (softcap, local windows,
+    alibi: flash_api.cpp:93-111, 197-213)."""
+    import math
+    from hydrainfer_b200._C.kernel.flash_attn import mha_varlen_fwd as ours
+    from hydrainfer_b200.workloads import make_batch
+    theirs = _need("flash_attn").mha_varlen_fwd
+    dtype, hq, hkv, d = geom
+    softcap, wl, wr, alibi = case
+    seq_lens = [(1, 300), (37, 37), (5, 130), (64, 200), (9, 9)]
+    batch = make_batch(seq_lens, hq, hkv, d, 16, dtype=dtype, device=DEV, seed=11)
+    t = batch.n_tokens
+    q3 = batch.query.view(t, hq, d).contiguous()
+    i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=DEV)
+    meta = (i32(batch.q_cu_seq_lens), i32(batch.kv_cu_seq_lens), i32(batch.block_tables), i32(batch.cu_blocks_lens))
+    slopes = (2.0 ** -torch.arange(1, hq + 1, dtype=torch.float32)).to(DEV) if alibi else None
+    scale = 1.0 / math.sqrt(d)
+    a, b = torch.empty_like(q3), torch.empty_like(q3)
+    ours(a, q3, batch.key_cache, batch.value_cache, *meta, slopes, batch.q_max, batch.kv_max, scale, softcap, wl, wr, 0)
+    theirs(b, q3, batch.key_cache, batch.value_cache, *meta, slopes, batch.q_max, batch.kv_max, scale, softcap, wl, wr, 0)
+    torch.cuda.synchronize()
+    err = (a.float() - b.float()).abs()
+    # two 16-bit implementations of the same sum: the reference's own cross-backend tolerance (tests/layer/test_attention.py:95-96)
+    assert bool((err <= 1e-2 + 1e-2 * b.float().abs()).all()), float(err.max())
