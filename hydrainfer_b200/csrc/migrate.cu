@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "ptx_sm100.cuh"
 
 namespace hi {
 
@@ -26,6 +27,7 @@ struct MigrateArgs {
   int64_t plane_begin;     // first (layer, kv) plane moved by this launch
   int64_t pieces_per_run;  // run_bytes / kPieceBytes (rounded up)
   int64_t total_pieces;
+  int bulk_stages;         // bulk-copy variant: 16-KiB shared-memory stages per CTA
 };
 
 constexpr int kMigrateThreads = 256;
@@ -90,6 +92,88 @@ __global__ void __launch_bounds__(kMigrateThreads) migrate_gather_inline_kernel(
   migrate_gather_body(a.base, InlineTables{&a});
 }
 
+// ---- bulk-copy variant: the TMA engine moves the bytes ---------------------------------------------------------------------
+// For LARGE transfers from / to peer memory.  One warp per CTA, one CTA per SM: an elected lane issues a 1-D bulk copy
+// (cp.async.bulk) of each 16-KiB piece from the source pool into a shared-memory stage and, when its bytes have landed, a bulk
+// copy from the stage to the destination pool; two stages (32 KiB) keep two pieces in flight per SM = 4.7 MB over the GPU, twice
+// what 800 GB/s x 3 us of NVLink latency needs.  No thread touches the data, the SM's issue slots stay with whatever else runs
+// on the GPU (the decode step of the receiving instance, epdnode.py:362-447), and 32 KiB of shared memory fit beside three
+// resident decode CTAs of 64 KiB.
+constexpr int kBulkStages = 2;      // default; HI_MIGRATE_BULK_STAGES (2..8) for experiments
+constexpr int kBulkMaxStages = 8;
+constexpr int kBulkThreads = 32;
+constexpr uint32_t kBulkPiece = 16384;
+struct BulkPiece {
+  const char* src;
+  char* dst;
+  uint32_t bytes;
+};
+template <typename Tables>
+__device__ __forceinline__ BulkPiece bulk_piece(const MigrateArgs& a, const Tables& tables, int64_t piece) {
+  const int64_t run = piece / a.pieces_per_run;
+  const int64_t off = (piece - run * a.pieces_per_run) * kBulkPiece;
+  const int64_t plane_rel = run / a.n;
+  const int64_t i = run - plane_rel * a.n;
+  const int64_t plane = a.plane_begin + plane_rel;
+  const int64_t left = a.run_bytes - off;
+  BulkPiece p;
+  p.src = a.src_pool + plane * a.src_plane_bytes + tables.src(i) * a.run_bytes + off;
+  p.dst = a.dst_pool + plane * a.dst_plane_bytes + tables.dst(i) * a.run_bytes + off;
+  p.bytes = static_cast<uint32_t>(left < kBulkPiece ? left : kBulkPiece);
+  return p;
+}
+template <typename Tables>
+__device__ __forceinline__ void migrate_bulk_body(const MigrateArgs& a, const Tables& tables) {
+  extern __shared__ __align__(128) uint8_t bulk_smem[];
+  __shared__ __align__(8) uint64_t full[kBulkMaxStages];
+  const uint32_t stage0 = ptx::smem_u32(bulk_smem);
+  const int n_st = a.bulk_stages;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < n_st; ++s) ptx::mbar_init(ptx::smem_u32(&full[s]), 1);
+    ptx::fence_mbar_init();
+  }
+  __syncwarp();
+  if (threadIdx.x != 0) return;
+  // pieces blockIdx.x, blockIdx.x + gridDim.x, ...: local index k.  Destination and size of the pieces in flight live in shared memory.
+  __shared__ BulkPiece ring[kBulkMaxStages];
+  const int64_t first = blockIdx.x, stride = gridDim.x;
+  const int64_t n_local = first < a.total_pieces ? (a.total_pieces - first + stride - 1) / stride : 0;
+  for (int s = 0; s < n_st && s < n_local; ++s) {
+    const BulkPiece p = bulk_piece(a, tables, first + s * stride);
+    ring[s] = p;
+    ptx::mbar_arrive_expect_tx(ptx::smem_u32(&full[s]), p.bytes);
+    ptx::bulk_load_1d(stage0 + s * kBulkPiece, p.src, p.bytes, ptx::smem_u32(&full[s]));
+  }
+  int s = 0;
+  uint32_t phase = 0;
+  for (int64_t k = 0; k < n_local; ++k) {
+    const bool more = k + n_st < n_local;
+    BulkPiece nxt{};
+    if (more) nxt = bulk_piece(a, tables, first + (k + n_st) * stride);  // table loads in flight behind the wait below
+    ptx::mbar_wait(ptx::smem_u32(&full[s]), phase);
+    const BulkPiece p = ring[s];
+    ptx::bulk_store_1d(p.dst, stage0 + s * kBulkPiece, p.bytes);
+    ptx::bulk_commit_group();
+    if (more) {
+      ptx::bulk_wait_group_read<0>();  // the store has read the stage: it may be refilled
+      ring[s] = nxt;
+      ptx::mbar_arrive_expect_tx(ptx::smem_u32(&full[s]), nxt.bytes);
+      ptx::bulk_load_1d(stage0 + s * kBulkPiece, nxt.src, nxt.bytes, ptx::smem_u32(&full[s]));
+    }
+    if (++s == n_st) {
+      s = 0;
+      phase ^= 1u;
+    }
+  }
+  ptx::bulk_wait_group<0>();  // the writes are done before the kernel ends
+}
+__global__ void __launch_bounds__(kBulkThreads) migrate_bulk_kernel(const MigrateArgs a) {
+  migrate_bulk_body(a, DeviceTables{a.src_blocks, a.dst_blocks});
+}
+__global__ void __launch_bounds__(kBulkThreads) migrate_bulk_inline_kernel(const __grid_constant__ MigrateInlineArgs a) {
+  migrate_bulk_body(a.base, InlineTables{&a});
+}
+
 // ---- IPC mapping cache -------------------------------------------------------------------------------------------
 struct IpcEntry {
   uint8_t handle[64];
@@ -145,8 +229,9 @@ static int pointer_device(const void* ptr, int fallback) {
   return dev;
 }
 // Shared by the device-table and the inline-table entry points: checks + geometry -> MigrateArgs and the grid size.
-static int prepare_migration(MigrateArgs& a, int64_t& grid, int64_t n, const void* src_pool, void* dst_pool, const HiPoolGeom& src,
+static int prepare_migration(MigrateArgs& a, int64_t& grid, bool& bulk, int64_t n, const void* src_pool, void* dst_pool, const HiPoolGeom& src,
                              const HiPoolGeom& dst, int64_t layer_begin, int64_t layer_end, int device) {
+  bulk = false;
   HI_CHECK_ARG(src_pool && dst_pool, "migrate_blocks: null pointer");
   HI_CHECK_ARG(src.n_layers == dst.n_layers && src.n_tokens == dst.n_tokens && src.run_bytes == dst.run_bytes,
                "migrate_blocks: pools differ in more than n_blocks (layers %lld/%lld, tokens %lld/%lld, run bytes %lld/%lld)",
@@ -181,6 +266,11 @@ static int prepare_migration(MigrateArgs& a, int64_t& grid, int64_t n, const voi
   } else if (a.total_pieces > grid * 4 && (pointer_is_ipc_mapped(src_pool) || pointer_is_ipc_mapped(dst_pool) ||
                                             pointer_device(src_pool, device) != device || pointer_device(dst_pool, device) != device)) {
     grid = static_cast<int64_t>(sm_count);
+    // ... and the TMA engine can move them (migrate_bulk_kernel): HI_MIGRATE_BULK=0 keeps the load / store kernel
+    const char* env = tuning_env("HI_MIGRATE_BULK");
+    bulk = !(env != nullptr && env[0] == '0');
+    a.bulk_stages = kBulkStages;
+    if (const char* st = tuning_env("HI_MIGRATE_BULK_STAGES")) a.bulk_stages = atoi(st) < 2 ? 2 : atoi(st) > kBulkMaxStages ? kBulkMaxStages : atoi(st);
   }
   if (grid > a.total_pieces) grid = a.total_pieces;
   return HI_OK;
@@ -205,12 +295,18 @@ extern "C" int hi_migrate_blocks_layers(const int32_t* src_blocks, const int32_t
   HI_CHECK_ARG(src_blocks && dst_blocks, "migrate_blocks: null pointer");
   MigrateArgs a{};
   int64_t grid = 0;
-  const int rc = prepare_migration(a, grid, n, src_pool, dst_pool, src, dst, layer_begin, layer_end, device);
+  bool bulk = false;
+  const int rc = prepare_migration(a, grid, bulk, n, src_pool, dst_pool, src, dst, layer_begin, layer_end, device);
   if (rc != HI_OK) return rc;
   a.src_blocks = src_blocks;
   a.dst_blocks = dst_blocks;
   HI_DEVICE_GUARD(device);
-  migrate_gather_kernel<<<static_cast<unsigned>(grid), kMigrateThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  if (bulk) {
+    static PerDeviceFlags configured;
+    HI_CUDA(configure_dynamic_smem(configured, migrate_bulk_kernel, kBulkMaxStages * kBulkPiece));
+    migrate_bulk_kernel<<<static_cast<unsigned>(grid), kBulkThreads, a.bulk_stages * kBulkPiece, static_cast<cudaStream_t>(stream)>>>(a);
+  }
+  else migrate_gather_kernel<<<static_cast<unsigned>(grid), kMigrateThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
   note_launch();
   HI_CUDA(cudaGetLastError());
   return HI_OK;
@@ -230,12 +326,18 @@ extern "C" int hi_migrate_blocks_host_tables(const int32_t* src_blocks_host, con
   HI_CHECK_ARG(src_blocks_host && dst_blocks_host, "migrate_blocks: null pointer");
   MigrateInlineArgs a{};
   int64_t grid = 0;
-  const int rc = prepare_migration(a.base, grid, n, src_pool, dst_pool, src, dst, layer_begin, layer_end, device);
+  bool bulk = false;
+  const int rc = prepare_migration(a.base, grid, bulk, n, src_pool, dst_pool, src, dst, layer_begin, layer_end, device);
   if (rc != HI_OK) return rc;
   std::memcpy(a.src, src_blocks_host, static_cast<size_t>(n) * sizeof(int32_t));
   std::memcpy(a.dst, dst_blocks_host, static_cast<size_t>(n) * sizeof(int32_t));
   HI_DEVICE_GUARD(device);
-  migrate_gather_inline_kernel<<<static_cast<unsigned>(grid), kMigrateThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  if (bulk) {
+    static PerDeviceFlags configured;
+    HI_CUDA(configure_dynamic_smem(configured, migrate_bulk_inline_kernel, kBulkMaxStages * kBulkPiece));
+    migrate_bulk_inline_kernel<<<static_cast<unsigned>(grid), kBulkThreads, a.base.bulk_stages * kBulkPiece, static_cast<cudaStream_t>(stream)>>>(a);
+  }
+  else migrate_gather_inline_kernel<<<static_cast<unsigned>(grid), kMigrateThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
   note_launch();
   HI_CUDA(cudaGetLastError());
   return HI_OK;

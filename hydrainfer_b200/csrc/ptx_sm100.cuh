@@ -111,6 +111,18 @@ __device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t smem_src
       ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// 1-D bulk copies (no tensor map): global -> shared with byte-count completion on an mbarrier, shared -> global as part of the thread's
+// bulk group.  Addresses 16-byte aligned, size a multiple of 16.  The global side may be peer memory (NVLink).
+__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store_1d(void* gdst, uint32_t smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               ::"l"(reinterpret_cast<uint64_t>(gdst)), "r"(smem_src), "r"(bytes)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // Every bulk group of this thread except the newest N has finished READING its shared-memory source (the buffer may be reused).
 template <int N>
