@@ -785,7 +785,7 @@ def measure_migration_under_decode(rank: int, world: int, local: int, dev: torch
         if world > 1:
             dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         a_d, a_p, b_d, b_p = (float(x) for x in vals.tolist())
-        out["caps"]["auto (1 CTA per SM for a large transfer from / to peer memory, else 8)" if cap == 0 else str(cap)] = {
+        out["caps"]["auto (large transfer from / to peer memory: TMA bulk-copy kernel, 1 CTA of one warp per SM; else load / store kernel, 8 CTAs per SM)" if cap == 0 else str(cap) + " CTAs of the load / store kernel"] = {
             "decode_tokens_per_s_alone": BATCH / a_d * 1e3, "decode_tokens_per_s_under_pull": BATCH / b_d * 1e3, "decode_slowdown": b_d / a_d,
             "pull_gbs_alone": payload / a_p / 1e6, "pull_gbs_under_decode": payload / b_p / 1e6,
             "note": "the pull outlasts or ends inside the 40 timed decode steps depending on its rate; both figures are per-stream event times"}

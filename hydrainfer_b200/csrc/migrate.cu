@@ -272,6 +272,13 @@ static int prepare_migration(MigrateArgs& a, int64_t& grid, bool& bulk, int64_t 
     a.bulk_stages = kBulkStages;
     if (const char* st = tuning_env("HI_MIGRATE_BULK_STAGES")) a.bulk_stages = atoi(st) < 2 ? 2 : atoi(st) > kBulkMaxStages ? kBulkMaxStages : atoi(st);
   }
+  if (const char* env = tuning_env("HI_MIGRATE_BULK")) {
+    if (env[0] == '2') {  // test override: the bulk-copy kernel for EVERY launch (a one-GPU box covers it that way)
+      bulk = true;
+      a.bulk_stages = kBulkStages;
+      if (cap <= 0) grid = static_cast<int64_t>(sm_count);
+    }
+  }
   if (grid > a.total_pieces) grid = a.total_pieces;
   return HI_OK;
 }

@@ -52,6 +52,36 @@ def test_migrate_blocks_same_device(geom, dtype):
     assert torch.equal(src_d.cpu(), src), "source pool was modified"
 
 
+@pytest.mark.parametrize("geom", [
+    (4, 2, 16, 4, 128, 40, 33, 16),     # 16-KiB runs = exactly one piece, block tables inside the kernel parameters
+    (3, 2, 16, 32, 128, 24, 30, 20),    # 128-KiB runs = 8 pieces
+    (1, 1, 576, 2, 64, 6, 5, 4),        # 144-KiB runs = 9 pieces
+    (2, 2, 4, 1, 8, 300, 280, 257),     # 64-byte runs: bulk copies of 64 bytes
+    (2, 2, 16, 3, 40, 700, 650, 500),   # 3840-byte runs (not a power of two), more blocks than an inline table holds: device tables
+])
+def test_bulk_copy_kernel_same_device(geom, monkeypatch):
+    """The TMA bulk-copy kernel (chosen by itself only for large transfers from / to peer memory) forced onto ordinary launches:
+    same bytes as the oracle, untouched regions untouched."""
+    monkeypatch.setenv("HI_MIGRATE_BULK", "2")
+    bm = _bm()
+    L, T, bs, H, d, nb_src, nb_dst, n = geom
+    src, dst = _pools((L, T, nb_src, bs, H, d), (L, T, nb_dst, bs, H, d), torch.bfloat16, seed=n + 1)
+    g = torch.Generator().manual_seed(98)
+    src_bt = torch.randperm(nb_src, generator=g)[:n].tolist()
+    dst_bt = torch.randperm(nb_dst, generator=g)[:n].tolist()
+    ref = dst.clone()
+    oracle.migrate_blocks(src_bt, dst_bt, src, ref)
+    src_d, dst_d = src.to(DEV), dst.to(DEV)
+    bm.migrate_blocks(src_bt, dst_bt, bm.get_ipc_mem_handle(src_d), dst_d, nb_src)
+    torch.cuda.synchronize()
+    assert torch.equal(dst_d.cpu(), ref), "destination pool differs from the oracle (moved blocks or untouched regions)"
+    # a layer range through the same kernel
+    dst_d2 = dst.to(DEV)
+    bm.migrate_blocks_layers(src_bt, dst_bt, bm.get_ipc_mem_handle(src_d), dst_d2, nb_src, 0, L)
+    torch.cuda.synchronize()
+    assert torch.equal(dst_d2.cpu(), ref)
+
+
 def test_layer_ranges_compose_to_the_whole_request():
     """migrate_blocks_layers over a partition of the layers == one migrate_blocks; each call touches only its layers."""
     bm = _bm()
