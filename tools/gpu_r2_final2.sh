@@ -8,4 +8,5 @@ for c in pre8k cfg3mix pre1k cfg3p; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:paged_attn_pair -s 6 -c 1 -f -o gpurun_out/r02_pair_$c python tools/bench_configs.py --only $c > gpurun_out/r02_ncu_pair_$c.log 2>&1; echo "$c ncu rc=$?"
 done
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_launches_bench.csv python bench.py --steps 3 --warmup 3 > gpurun_out/r02_bench_under_ncu.log 2>&1; echo "launch list rc=$?"
+timeout 600 python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/final_bench_ref.json 2> gpurun_out/final_bench_ref.err; echo "ref rc=$?"; cut -c1-260 gpurun_out/final_bench_ref.json
 bash tools/gpu_r2_bench.sh 1
