@@ -24,7 +24,8 @@ from hydrainfer_b200.workloads import make_batch  # noqa: E402
 ROLES = ["K-tma", "V-tma", "mma0", "mma1"] + [f"smx{w >> 2}w{w & 3}" for w in range(8)]  # lane 0 of each softmax warp
 N_ROLES, CAP = 12, 4096
 SMX0, SMX1 = 4, 8  # first softmax warp of tile 0 / 1
-_SMX_TAGS = {1: "item", 3: "S", 4: "P", 5: "Ofull", 6: "epi-done", 7: "rescale"}
+_SMX_TAGS = {1: "item", 3: "S", 4: "P", 5: "Ofull", 6: "epi-done", 7: "rescale", 8: "h0-packed", 9: "h0-bufree", 10: "h0-bar1", 11: "h0-bar2",
+             12: "h1-packed", 13: "h1-bufree", 14: "h1-bar1", 15: "h1-bar2"}
 TAGS = {0: {1: "item", 2: "Qempty", 3: "stage-free"}, 1: {1: "item", 3: "stage-free"},
         2: {1: "item", 2: "Qfull", 3: "ready", 4: "issued"}, 3: {1: "item", 2: "Qfull", 3: "ready", 4: "issued"},
         **{4 + w: _SMX_TAGS for w in range(8)}}
