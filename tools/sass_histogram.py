@@ -12,7 +12,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parents[1]
 LIB = ROOT / "hydrainfer_b200" / "lib" / "libhi_b200.so"
-KEY = ["UTCHMMA", "UTCBAR", "UTMALDG", "UTMASTG", "UTMACMDFLUSH", "LDTM", "STTM", "LDGSTS", "SYNCS", "MUFU.EX2", "FFMA2", "FADD2", "HFMA2", "FMNMX3",
+KEY = ["UTCHMMA", "UTCBAR", "UTMALDG", "UTMASTG", "UBLKCP", "UTMACMDFLUSH", "LDTM", "STTM", "LDGSTS", "SYNCS", "MUFU.EX2", "FFMA2", "FADD2", "HFMA2", "FMNMX3",
        "LDG", "STG", "LDS", "STS", "ATOM", "RED", "SHFL", "BAR", "ACQBULK", "LDL", "STL", "ELECT", "USETMAXREG", "ERRBAR"]
 
 
@@ -31,7 +31,7 @@ def main():
             cur[op] += 1
     demangle = subprocess.run(["c++filt"], input="\n".join(kernels), capture_output=True, text=True).stdout.splitlines()
     print("# SASS opcode histogram per kernel of lib/libhi_b200.so (sm_100a, `cuobjdump -sass`)\n")
-    print("Counts are static instruction counts.  `UTCHMMA` = tcgen05.mma, `UTCBAR` = tcgen05.commit, `UTMALDG` / `UTMASTG` = TMA tensor load / store,")
+    print("Counts are static instruction counts.  `UTCHMMA` = tcgen05.mma, `UTCBAR` = tcgen05.commit, `UTMALDG` / `UTMASTG` = TMA tensor load / store, `UBLKCP` = 1-D bulk copy (cp.async.bulk),")
     print("`LDTM` / `STTM` = tcgen05.ld / st, `LDGSTS` = cp.async, `SYNCS` = mbarrier ops, `LDL` / `STL` = local-memory (spill) traffic.\n")
     print("| kernel | instr | " + " | ".join(KEY) + " |")
     print("|---|---|" + "---|" * len(KEY))
