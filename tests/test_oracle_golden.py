@@ -134,6 +134,59 @@ def test_varlen_fp32_causal_agrees_with_paged_oracle():
     assert torch.allclose(paged, flat, atol=1e-6, rtol=1e-6)
 
 
+def _tiny_paged_case(seed=12):
+    g = torch.Generator().manual_seed(seed)
+    hq, hkv, d, bs = 4, 2, 32, 16
+    lens = [(5, 40), (16, 16), (1, 33), (3, 3)]
+    q = torch.randn(sum(a for a, _ in lens), hq, d, generator=g)
+    n_blocks = sum((kv + bs - 1) // bs for _, kv in lens)
+    kc, vc = torch.randn(n_blocks, bs, hkv, d, generator=g), torch.randn(n_blocks, bs, hkv, d, generator=g)
+    q_cu, kv_cu, tables, cu_blocks, blk = [0], [0], [], [0], 0
+    for ql, kv in lens:
+        nb = (kv + bs - 1) // bs
+        tables += list(range(blk, blk + nb))
+        blk += nb
+        q_cu.append(q_cu[-1] + ql), kv_cu.append(kv_cu[-1] + kv), cu_blocks.append(cu_blocks[-1] + nb)
+    return q, kc, vc, q_cu, kv_cu, torch.tensor(tables, dtype=torch.int32), cu_blocks, hq, hkv, d, lens
+
+
+def test_score_options_oracle_reduces_to_the_pinned_function():
+    """`paged_attention_options_fp32` with mha_varlen_fwd's defaults (softcap 0, window (-1, 0), no alibi) IS the pinned restatement of
+    the reference's torch handler; a window wider than every sequence and a zero alibi slope change nothing either."""
+    q, kc, vc, q_cu, kv_cu, tables, cu_blocks, hq, hkv, d, _ = _tiny_paged_case()
+    scale = 1.0 / d ** 0.5
+    pinned = oracle.paged_attention_fp32(q, kc, vc, q_cu, kv_cu, tables, cu_blocks, hq, hkv, d)
+    for kwargs in ({}, {"window_size_left": 1000}, {"alibi_slopes": torch.zeros(hq)}, {"alibi_slopes": torch.zeros(len(q_cu) - 1, hq)}):
+        got = oracle.paged_attention_options_fp32(q, kc, vc, q_cu, kv_cu, tables, cu_blocks, hq, hkv, d, scale, **kwargs)
+        assert torch.allclose(got, pinned, atol=1e-6, rtol=1e-6), kwargs
+
+
+def test_score_options_oracle_hand_checked_rows():
+    """Rows whose result follows from the definitions (flash_api.cpp:93-111, src/mask.h:54-62, 183-186) without running a softmax:
+    window_left = 0 and window_right = 0 leave exactly the diagonal key, so the output row is that key's V row; a huge alibi slope
+    does the same through the bias; softcap -> 0+ flattens every visible score, so the row is the mean of the visible V rows."""
+    q, kc, vc, q_cu, kv_cu, tables, cu_blocks, hq, hkv, d, lens = _tiny_paged_case(13)
+    scale = 1.0 / d ** 0.5
+    group = hq // hkv
+    diag = oracle.paged_attention_options_fp32(q, kc, vc, q_cu, kv_cu, tables, cu_blocks, hq, hkv, d, scale, window_size_left=0, window_size_right=0)
+    steep = oracle.paged_attention_options_fp32(q, kc, vc, q_cu, kv_cu, tables, cu_blocks, hq, hkv, d, scale, alibi_slopes=torch.full((hq,), 1e4))
+    flat = oracle.paged_attention_options_fp32(q, kc, vc, q_cu, kv_cu, tables, cu_blocks, hq, hkv, d, scale, softcap=1e-6)
+    blk = 0
+    for b, (ql, kv) in enumerate(lens):
+        nb = (kv + 15) // 16
+        v = vc[blk:blk + nb].reshape(-1, hkv, d)[:kv].repeat_interleave(group, dim=1)  # [kv, hq, d]
+        blk += nb
+        for i in range(ql):
+            i_abs = i + kv - ql
+            row = q_cu[b] + i
+            assert torch.allclose(diag[row].view(hq, d), v[i_abs], atol=1e-6)
+            assert torch.allclose(steep[row].view(hq, d), v[i_abs], atol=1e-5)
+            assert torch.allclose(flat[row].view(hq, d), v[: i_abs + 1].mean(dim=0), atol=1e-4)
+    # an empty window (the row sees no key at all) yields zeros: q_len > kv_len rows under a causal window
+    out = oracle.paged_attention_options_fp32(q[:2], kc, vc, [0, 2], [0, 1], tables[:1], [0, 1], hq, hkv, d, scale)
+    assert torch.equal(out[0], torch.zeros(hq * d)) and bool(out[1].abs().sum() > 0)
+
+
 def test_get_image_cache_restatement():
     z = np.load(GOLDEN / "image_cache.npz")
     n_blocks, bs, heads, d = (int(v) for v in z["geometry"])
