@@ -41,9 +41,13 @@ def _random_case(seed: int):
 
 @pytest.mark.parametrize("seed", range(24))
 def test_random_batch_through_the_layer(seed):
+    run_case(_random_case(1000 + seed), seed)
+
+
+def run_case(c: dict, seed: int):
+    """One random batch through the layer on every path that takes it (also driven by tests/dev/fuzz_campaign.py with a wider space)."""
     from hydrainfer_b200.layer import AttentionParametersBuilder, CausalGroupedQueryPageAttention, CausalGroupedQueryPageAttentionConfig
     from hydrainfer_b200.memory import KVCache
-    c = _random_case(1000 + seed)
     batch = make_batch(c["seq_lens"], c["hq"], c["hkv"], c["d"], c["bs"], dtype=c["dtype"], seed=2000 + seed, fused_qkv=c["fused"])
     t = batch.n_tokens
     # oracle: append, then the fp32 recompute over the appended caches
