@@ -259,8 +259,10 @@ int hi_set_kernel_timing_events(void* start, void* stop);
  * (hydrainfer/memory/token_cache_manger.py:65).  For every (layer, kv, i) the run of
  * run_bytes = block_size*n_heads*head_size*itemsize bytes of src block src_blocks[i] is copied to dst block
  * dst_blocks[i] (block_migration.cpp:222-244); pools may differ in n_blocks only.
- * The reference issues n_layers*n_tokens*n cudaMemcpyAsync calls; this is ONE gather kernel that reads
- * the source through its (peer-mapped) pointer and writes local memory.
+ * The reference issues n_layers*n_tokens*n cudaMemcpyAsync calls; this is ONE launch: when either pool is
+ * memory of another GPU (a peer pointer or a CUDA-IPC mapping) the TMA engine moves the runs as 1-D bulk copies
+ * through shared memory, issued by one warp per SM (the receiver's SMs stay with its decode step); copies inside
+ * one GPU use a load / store gather kernel.
  * ------------------------------------------------------------------------------------------- */
 typedef struct HiPoolGeom {
   int64_t n_layers, n_tokens, n_blocks, run_bytes;
