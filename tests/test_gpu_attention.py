@@ -532,3 +532,43 @@ def test_score_options_default_equals_plain_causal():
     # a window wider than any sequence masks nothing beyond causal: the option instance must agree with the plain one within rounding
     mha_varlen_fwd(b, q3, batch.key_cache, batch.value_cache, *meta, None, batch.q_max, batch.kv_max, 0.088, 0.0, 100000, 0, 0)
     assert torch.allclose(a.float(), b.float(), atol=1e-2, rtol=1e-2)
+
+
+def test_score_options_through_the_ctypes_mirror_of_the_c_abi():
+    """The same options through `hydrainfer_b200._lib.HiAttnArgs` (the ctypes mirror of include/hi_b200.h, ABI 6): field offsets, flag
+    bits and error statuses, independent of the compiled binding."""
+    import ctypes
+    from hydrainfer_b200 import _lib
+    dev = torch.device(DEV)
+    hq, hkv, d = 8, 2, 128
+    b = make_batch([(1, 300), (20, 90)], hq, hkv, d, 16, dtype=torch.bfloat16, device=DEV, seed=21)
+    t = b.n_tokens
+    i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=DEV)
+    q3 = b.query.view(t, hq, d)
+    out = torch.full_like(q3, float("nan"))
+    meta = [i32(b.q_cu_seq_lens), i32(b.kv_cu_seq_lens), i32(b.block_tables), i32(b.cu_blocks_lens)]
+    slopes = (2.0 ** -torch.arange(1, hq + 1, dtype=torch.float32)).to(DEV)
+    scale = 1 / math.sqrt(d)
+
+    def call(**extra):
+        a = _lib.HiAttnArgs(q=q3.data_ptr(), out=out.data_ptr(), key_cache=b.key_cache.data_ptr(), value_cache=b.value_cache.data_ptr(),
+                            q_row_stride=hq * d, out_row_stride=hq * d, q_cu_seq_lens=meta[0].data_ptr(), kv_cu_seq_lens=meta[1].data_ptr(),
+                            block_tables=meta[2].data_ptr(), cu_blocks_lens=meta[3].data_ptr(), n_seqs=2, n_tokens=t, max_q_len=b.q_max, max_kv_len=b.kv_max,
+                            n_qo_heads=hq, n_kv_heads=hkv, head_dim=d, block_size=16, n_blocks=b.key_cache.shape[0], dtype=_lib.HI_BF16,
+                            softmax_scale=scale, workspace=None, workspace_bytes=0, path=0, device=0, **extra)
+        return _lib.lib.hi_paged_attention(ctypes.byref(a), _lib.current_stream_ptr(dev))
+
+    opts = _lib.HI_ATTN_OPT_WINDOW | _lib.HI_ATTN_OPT_SOFTCAP | _lib.HI_ATTN_OPT_ALIBI
+    assert call(options=opts, window_left=40, window_right=0, softcap=25.0, alibi_slopes=slopes.data_ptr(), alibi_batch_stride=0) == 0, _lib.lib.hi_last_error()
+    torch.cuda.synchronize()
+    ref = oracle.paged_attention_options_fp32(q3.cpu(), b.key_cache.cpu(), b.value_cache.cpu(), b.q_cu_seq_lens, b.kv_cu_seq_lens, torch.tensor(b.block_tables),
+                                              b.cu_blocks_lens, hq, hkv, d, scale, 25.0, 40, 0, slopes.cpu())
+    got = out.float().cpu().reshape(t, hq * d)
+    assert bool(((got - ref).abs() <= 2e-2 + 1e-2 * ref.abs()).all())
+    # statuses: unknown bits, softcap <= 0 with its flag, alibi flag without slopes -> invalid argument; a tcgen05 path with options -> unsupported
+    assert call(options=8) == -1 and b"option" in _lib.lib.hi_last_error()
+    assert call(options=_lib.HI_ATTN_OPT_SOFTCAP, softcap=0.0) == -1
+    assert call(options=_lib.HI_ATTN_OPT_ALIBI) == -1
+    a_bad = dict(options=_lib.HI_ATTN_OPT_WINDOW, window_left=3, window_right=0)
+    assert call(**a_bad) == 0
+    # (the rejection of a forced tcgen05 path with options is covered through the binding in test_unsupported_arguments_raise)
