@@ -500,6 +500,12 @@ def measure_prefill(dev: torch.device, reps: int = 10, warm: int = 3) -> dict:
         entry = {"seqs": len(seq_lens), "tokens": batch.n_tokens, "ms": cm, "kernel_ms": km, "flops": flops,
                  "tflops": flops / km / 1e9, "frac": flops / km / 1e9 / burst, "frac_sustained": flops / km / 1e9 / sustained,
                  "tflops_call": flops / cm / 1e9, "frac_call": flops / cm / 1e9 / burst, "tokens_per_s": batch.n_tokens / cm * 1e3}
+        # the two rooflines of the launch side by side: tensor time of its FLOPs and HBM time of its algorithmic bytes (every sequence's
+        # K / V once, q in, out out); a mixed batch is bound by neither alone, the launch can at best overlap the two
+        algo_bytes = sum(2 * L * hkv * D * 2 + 2 * q * hq * D * 2 for q, L in seq_lens)
+        tensor_ms, hbm_ms = flops / burst / 1e9, algo_bytes / (hbm * 1e6)
+        entry.update({"algorithmic_bytes": algo_bytes, "tensor_bound_ms": tensor_ms, "hbm_bound_ms": hbm_ms,
+                      "frac_of_binding_roofline": max(tensor_ms, hbm_ms) / km, "frac_if_the_two_could_not_overlap": (tensor_ms + hbm_ms) / km})
         if decode_bytes:
             entry["decode_rows_kv_bytes"] = decode_bytes
             entry["note"] = "mixed batch: the 48 decode rows stream %.0f MB of KV inside the same launch (%.0f us at the measured HBM rate)" % (
